@@ -1,0 +1,138 @@
+/* f4la_b200 -- B200-native GF(p) linear algebra for F4 (C ABI).
+ *
+ * Two levels, both plain C (pointers + sizes, no torch / C++ types):
+ *
+ *  1. "flat" level: a Macaulay matrix [A B; C D] given as CSR-like host (or
+ *     device-resident) arrays, reduced to the unique reduced row echelon form
+ *     of its lower rows modulo the known pivots.  This is the computational
+ *     content of neogb's  exact_sparse_reduced_echelon_form_ff_{8,16,32}
+ *     (reference src/neogb/la_ff_32.c:2595, la_ff_16.c:1046, la_ff_8.c:1319).
+ *
+ *  2. "neogb" level (include/f4la_b200_neogb.h): drop-in replacements for the
+ *     reference's global linear-algebra function pointers
+ *     (reference src/neogb/data.h:529-595), operating on mat_t/bs_t/md_t.
+ *
+ * There is no CPU fallback: every entry point that computes fails loudly
+ * (message on stderr + non-zero return / exit) when no sm_100 device is usable.
+ */
+#ifndef F4LA_B200_H
+#define F4LA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F4LA_OK            0
+#define F4LA_ERR_CUDA      1   /* CUDA runtime error (message on stderr) */
+#define F4LA_ERR_NODEVICE  2   /* no usable GPU */
+#define F4LA_ERR_ARG       3   /* malformed input */
+#define F4LA_ERR_BADPRIME  4   /* apply mode: a row reduced to zero */
+
+/* A Macaulay matrix in flat form.
+ *
+ * Rows 0 .. nru-1 are the known pivot rows ("rr" of mat_t, reference
+ * data.h:203-232): row i has its lead term in column i, lead coefficient 1
+ * and the lead term stored FIRST; the remaining entries may come in any
+ * order (reference convert.c:405-413 does not sort them).
+ * Rows nru .. nru+nrl-1 are the rows to be reduced ("tr").
+ * Columns 0 .. ncl-1 are the known pivot columns (ncl == nru in F4 rounds),
+ * columns ncl .. ncl+ncr-1 have no known pivot.
+ *
+ * Coefficients are shared between rows exactly as in the reference
+ * (row = monomial x basis polynomial, so many rows alias one coefficient
+ * array, reference hash.c:1369-1390): row r uses coefficient array row_cf[r],
+ * whose length equals the row's length, entry k of the row has column
+ * cols[row_ptr[r]+k] and coefficient cf[cf_ptr[row_cf[r]]+k].
+ */
+typedef struct f4la_flat_matrix {
+    uint32_t fc;        /* field characteristic p, prime, p < 2^31            */
+    uint32_t cf_bytes;  /* width of the coefficient pool entries: 1, 2 or 4   */
+    uint32_t nru;       /* number of known pivot rows                         */
+    uint32_t nrl;       /* number of rows to be reduced                       */
+    uint32_t ncl;       /* number of known pivot columns                      */
+    uint32_t ncr;       /* number of columns without known pivot              */
+    uint32_t ncf;       /* number of distinct coefficient arrays              */
+    uint32_t flags;     /* F4LA_FLAG_*                                        */
+    const uint64_t *row_ptr; /* [nru+nrl+1] offsets into cols                 */
+    const uint32_t *cols;    /* [row_ptr[nru+nrl]] column indices             */
+    const uint32_t *row_cf;  /* [nru+nrl] coefficient array id of each row    */
+    const uint64_t *cf_ptr;  /* [ncf+1] offsets (in elements) into cf         */
+    const void     *cf;      /* coefficient pool, cf_bytes wide entries       */
+} f4la_flat_matrix;
+
+/* flags */
+#define F4LA_FLAG_NONE        0u
+/* keep every lower row as its own (non inter-reduced, non normalised) normal
+ * form modulo the known pivots -- the nf>0 / final-reduction contract of the
+ * reference (la_ff_32.c:2676-2684, 2764-2766).  Result row i corresponds to
+ * input lower row i; rows reducing to zero have length 0. */
+#define F4LA_FLAG_NORMALFORM  1u
+/* known pivots are keyed by their lead column instead of by row index
+ * (in_final_reduction_step, la_ff_32.c:2618-2622) */
+#define F4LA_FLAG_PIVOT_BY_LEAD 2u
+
+/* Result: rows of the reduced row echelon form, as CSR over ALL columns
+ * (column ids in 0..ncl+ncr-1, ascending inside a row).  In echelon mode the
+ * rows come by DECREASING lead column, lead coefficient 1, fully
+ * inter-reduced (reference la_ff_32.c:2732-2762).  All arrays are malloc()ed
+ * by the library and released with f4la_b200_free_result(). */
+typedef struct f4la_flat_result {
+    uint32_t  nrows;     /* number of result rows (new pivots)                */
+    uint32_t  cf_bytes;  /* same as the input                                 */
+    uint64_t *row_ptr;   /* [nrows+1]                                         */
+    uint32_t *cols;      /* [row_ptr[nrows]]                                  */
+    void     *cf;        /* [row_ptr[nrows]] coefficients, cf_bytes wide      */
+    uint32_t *src_row;   /* [nrows] index of an input lower row whose
+                            reduction produced this pivot (BINDEX/MULT donor) */
+} f4la_flat_result;
+
+/* Per-call measurements (device times from CUDA events on the ctx stream). */
+typedef struct f4la_stats {
+    double   ms_total;        /* whole call, host wall clock                  */
+    double   ms_h2d;          /* host->device copies                          */
+    double   ms_prep;         /* device-side layout kernels                   */
+    double   ms_reduce;       /* sparse reduction by known pivots (hot kernel)*/
+    double   ms_echelon;      /* trailing block echelon form                  */
+    double   ms_d2h;          /* device->host copies + host materialisation   */
+    uint64_t units;           /* coefficient applications done by the hot
+                                 kernel (1 mul + 1 add each)                  */
+    uint64_t pivot_applications;
+    uint64_t bytes_h2d;
+    uint64_t bytes_d2h;
+    uint32_t kernel_launches; /* kernels launched by this library in the call */
+    uint32_t rank;            /* number of new pivots                         */
+} f4la_stats;
+
+typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */
+typedef struct f4la_resident f4la_resident; /* a matrix already in HBM        */
+
+/* Library / device management. */
+const char *f4la_b200_version(void);
+int  f4la_b200_device_count(void);
+/* Creates a context bound to CUDA device `device` with its own stream.
+ * Returns NULL (and prints why) when no device is usable. */
+f4la_ctx *f4la_b200_create(int device);
+void f4la_b200_destroy(f4la_ctx *ctx);
+const char *f4la_b200_last_error(const f4la_ctx *ctx);
+
+/* Echelon form from HOST buffers: copies in, reduces, copies the result out.
+ * Replaces the computational body of exact_sparse_reduced_echelon_form_ff_*
+ * (reference la_ff_32.c:2595-2770). */
+int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in,
+                     f4la_flat_result *out, f4la_stats *stats);
+
+/* Same computation with the input already resident in HBM (bench: `value`). */
+f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in);
+int  f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m,
+                               f4la_flat_result *out, f4la_stats *stats);
+void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m);
+
+void f4la_b200_free_result(f4la_flat_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F4LA_B200_H */

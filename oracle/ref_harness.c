@@ -1,0 +1,489 @@
+/* ref_harness.c -- TEST INFRASTRUCTURE ONLY (never part of the product path).
+ *
+ * Compiles the UNMODIFIED reference neogb (unity build, reference
+ * src/neogb/gb.c:27-51) together with a small driver into
+ * oracle/_ref/libneogb_ref.so.  The sources are compiled from where they lie
+ * under /root/reference; nothing of them is copied into this repository.
+ *
+ * What it offers to tests/ and to bench.py's cpu_baseline / reference arm:
+ *   - refh_f4():          run the reference F4 (export_f4, f4.c:769) on a
+ *                         polynomial system, with the linear algebra served
+ *                         by (0) the reference itself, (1) an installed
+ *                         backend, (2) both, compared step by step (shadow),
+ *                         (3) the reference, recording every matrix.
+ *   - refh_reference_la(): run the reference LA (dispatch_linear_algebra,
+ *                         io.c:878) on one flat matrix.
+ *   - refh_struct_layout(): offsets of the reference's mat_t/bs_t/md_t, so a
+ *                         CPU test can check include/f4la_b200_neogb.h.
+ *
+ * Because this file #includes the reference's gb.c it sees its static
+ * functions; the global LA function pointers (data.c:71-103) are the hooks.
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+
+#include "gb.c"                 /* the reference, unmodified (-I at build) */
+#include "f4la_b200.h"          /* flat exchange format only               */
+
+/* ------------------------------------------------------------------ */
+/* records                                                             */
+/* ------------------------------------------------------------------ */
+
+typedef struct refh_record {
+    /* input */
+    f4la_flat_matrix in;        /* owned copies                            */
+    uint32_t *bindex;           /* [nru+nrl] row[BINDEX]                   */
+    uint32_t *mult;             /* [nru+nrl] row[MULT]                     */
+    /* reference output */
+    f4la_flat_result out;
+    uint32_t *out_bindex;
+    uint32_t *out_mult;
+    /* meta */
+    int32_t  kind;              /* 0 linear_algebra, 1 exact_linear_algebra,
+                                   2 interreduce_matrix_rows               */
+    int32_t  laopt, ff_bits, nf, final_step, trace_level;
+    double   la_seconds;        /* reference wall time of this call        */
+    double   units;             /* coefficient applications (31-bit only)  */
+    double   pivot_apps;
+} refh_record;
+
+static refh_record *g_rec   = NULL;
+static int          g_nrec  = 0;
+static int          g_caprec = 0;
+
+static int    g_mode        = 0;   /* 0 ref, 1 backend, 2 shadow, 3 record */
+static int    g_max_records = 1 << 30;
+static int64_t g_shadow_mismatch = 0;
+static int64_t g_shadow_calls    = 0;
+static double g_la_seconds       = 0.0;   /* LA wall time, whichever served */
+static int    g_la_calls         = 0;
+static int    g_verbose          = 0;
+
+typedef void (*la_fn_t)(mat_t *, const bs_t *const, const bs_t *const, md_t *);
+typedef void (*ir_fn_t)(mat_t *, bs_t *, md_t *, int);
+static la_fn_t g_backend_la       = NULL;
+static la_fn_t g_backend_exact_la = NULL;
+static ir_fn_t g_backend_interred = NULL;
+
+static size_t cf_width(int ff_bits) { return ff_bits == 8 ? 1 : ff_bits == 16 ? 2 : 4; }
+
+static const void *cf_array_of(const bs_t *b, int ff_bits, hm_t idx)
+{
+    switch (ff_bits) {
+        case 8:  return b->cf_8[idx];
+        case 16: return b->cf_16[idx];
+        default: return b->cf_32[idx];
+    }
+}
+
+/* Flatten the LA input (mat_t before the call) into owned arrays.
+ * Coefficient arrays are deduplicated by (basis, COEFFS index). */
+static void flatten_input(refh_record *rec, const mat_t *mat, const bs_t *tbr,
+                          const bs_t *bs, const md_t *st, int rows_only_rr)
+{
+    const uint32_t nru = mat->nru, nrl = rows_only_rr ? 0 : mat->nrl;
+    const uint32_t n   = nru + nrl;
+    const size_t   w   = cf_width(st->ff_bits);
+    f4la_flat_matrix *m = &rec->in;
+    memset(m, 0, sizeof(*m));
+    m->fc = st->fc; m->cf_bytes = (uint32_t)w;
+    m->nru = nru; m->nrl = nrl; m->ncl = mat->ncl; m->ncr = mat->ncr;
+    uint64_t *rp = malloc((n + 1) * sizeof(uint64_t));
+    uint32_t *rcf = malloc((n ? n : 1) * sizeof(uint32_t));
+    rec->bindex = malloc((n ? n : 1) * sizeof(uint32_t));
+    rec->mult   = malloc((n ? n : 1) * sizeof(uint32_t));
+    uint64_t nnz = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        const hm_t *row = r < nru ? mat->rr[r] : mat->tr[r - nru];
+        rp[r] = nnz; nnz += row[LENGTH];
+    }
+    rp[n] = nnz;
+    uint32_t *cols = malloc((nnz ? nnz : 1) * sizeof(uint32_t));
+    /* dedupe coefficient arrays: map basis index -> pool id, separately for
+     * bs (pivots) and tbr (rows to be reduced) unless they are the same */
+    const uint32_t bs_ld  = bs->ld;
+    const uint32_t tbr_ld = tbr->ld;
+    int32_t *map_bs  = malloc((bs_ld + 1) * sizeof(int32_t));
+    int32_t *map_tbr = (tbr == bs) ? map_bs : malloc((tbr_ld + 1) * sizeof(int32_t));
+    for (uint32_t i = 0; i < bs_ld; ++i) map_bs[i] = -1;
+    if (tbr != bs) for (uint32_t i = 0; i < tbr_ld; ++i) map_tbr[i] = -1;
+    uint32_t ncf = 0; uint64_t ncoef = 0;
+    uint64_t *cfp = malloc((n + 2) * sizeof(uint64_t));
+    const void **cfsrc = malloc((n + 1) * sizeof(void *));
+    for (uint32_t r = 0; r < n; ++r) {
+        const hm_t *row = r < nru ? mat->rr[r] : mat->tr[r - nru];
+        const bs_t *b   = r < nru ? bs : tbr;
+        int32_t *map    = r < nru ? map_bs : map_tbr;
+        memcpy(cols + rp[r], row + OFFSET, row[LENGTH] * sizeof(uint32_t));
+        rec->bindex[r] = row[BINDEX];
+        rec->mult[r]   = row[MULT];
+        const hm_t ci = row[COEFFS];
+        if (map[ci] < 0) {
+            map[ci] = (int32_t)ncf;
+            cfp[ncf] = ncoef;
+            cfsrc[ncf] = cf_array_of(b, st->ff_bits, ci);
+            ncoef += row[LENGTH];
+            ncf++;
+        }
+        rcf[r] = (uint32_t)map[ci];
+    }
+    cfp[ncf] = ncoef;
+    unsigned char *pool = malloc((ncoef ? ncoef : 1) * w);
+    for (uint32_t c = 0; c < ncf; ++c)
+        memcpy(pool + cfp[c] * w, cfsrc[c], (cfp[c + 1] - cfp[c]) * w);
+    free(cfsrc); free(map_bs); if (tbr != bs) free(map_tbr);
+    m->ncf = ncf; m->row_ptr = rp; m->cols = cols; m->row_cf = rcf;
+    m->cf_ptr = cfp; m->cf = pool;
+    if (st->nf > 0) m->flags |= F4LA_FLAG_NORMALFORM;
+    if (st->in_final_reduction_step) m->flags |= F4LA_FLAG_PIVOT_BY_LEAD;
+}
+
+/* Flatten the LA output: mat->tr[0..np) (entries may be NULL in nf mode). */
+static void flatten_output(f4la_flat_result *res, uint32_t **obi, uint32_t **omu,
+                           const mat_t *mat, const md_t *st)
+{
+    const uint32_t np = mat->np;
+    const size_t w = cf_width(st->ff_bits);
+    memset(res, 0, sizeof(*res));
+    res->nrows = np; res->cf_bytes = (uint32_t)w;
+    res->row_ptr = malloc((np + 1) * sizeof(uint64_t));
+    *obi = malloc((np ? np : 1) * sizeof(uint32_t));
+    *omu = malloc((np ? np : 1) * sizeof(uint32_t));
+    uint64_t nnz = 0;
+    for (uint32_t i = 0; i < np; ++i) {
+        res->row_ptr[i] = nnz;
+        if (mat->tr[i]) nnz += mat->tr[i][LENGTH];
+    }
+    res->row_ptr[np] = nnz;
+    res->cols = malloc((nnz ? nnz : 1) * sizeof(uint32_t));
+    res->cf   = malloc((nnz ? nnz : 1) * w);
+    res->src_row = NULL;
+    for (uint32_t i = 0; i < np; ++i) {
+        const hm_t *row = mat->tr[i];
+        if (!row) { (*obi)[i] = 0; (*omu)[i] = 0; continue; }
+        memcpy(res->cols + res->row_ptr[i], row + OFFSET, row[LENGTH] * sizeof(uint32_t));
+        const void *cf = st->ff_bits == 8 ? (void *)mat->cf_8[row[COEFFS]]
+                       : st->ff_bits == 16 ? (void *)mat->cf_16[row[COEFFS]]
+                       : (void *)mat->cf_32[row[COEFFS]];
+        memcpy((unsigned char *)res->cf + res->row_ptr[i] * w, cf, row[LENGTH] * w);
+        (*obi)[i] = row[BINDEX]; (*omu)[i] = row[MULT];
+    }
+}
+
+static refh_record *new_record(void)
+{
+    if (g_nrec == g_caprec) {
+        g_caprec = g_caprec ? 2 * g_caprec : 64;
+        g_rec = realloc(g_rec, (size_t)g_caprec * sizeof(refh_record));
+    }
+    refh_record *r = &g_rec[g_nrec++];
+    memset(r, 0, sizeof(*r));
+    return r;
+}
+
+static void free_record(refh_record *r)
+{
+    free((void *)r->in.row_ptr); free((void *)r->in.cols); free((void *)r->in.row_cf);
+    free((void *)r->in.cf_ptr); free((void *)r->in.cf);
+    free(r->bindex); free(r->mult);
+    free(r->out.row_ptr); free(r->out.cols); free(r->out.cf); free(r->out.src_row);
+    free(r->out_bindex); free(r->out_mult);
+    memset(r, 0, sizeof(*r));
+}
+
+/* Deep copy of a mat_t's rows (for shadow mode: the LA consumes its input). */
+static mat_t *clone_matrix(const mat_t *mat)
+{
+    mat_t *c = calloc(1, sizeof(mat_t));
+    *c = *mat;
+    c->rr = malloc((mat->nru ? mat->nru : 1) * sizeof(hm_t *));
+    c->tr = malloc((mat->nrl ? mat->nrl : 1) * sizeof(hm_t *));
+    for (len_t i = 0; i < mat->nru; ++i) {
+        size_t sz = (mat->rr[i][LENGTH] + OFFSET) * sizeof(hm_t);
+        c->rr[i] = malloc(sz); memcpy(c->rr[i], mat->rr[i], sz);
+    }
+    for (len_t i = 0; i < mat->nrl; ++i) {
+        size_t sz = (mat->tr[i][LENGTH] + OFFSET) * sizeof(hm_t);
+        c->tr[i] = malloc(sz); memcpy(c->tr[i], mat->tr[i], sz);
+    }
+    c->cf_8 = NULL; c->cf_16 = NULL; c->cf_32 = NULL; c->cf_qq = NULL; c->cf_ab_qq = NULL;
+    c->rba = NULL; c->rbal = 0;
+    if (mat->rba && mat->rbal) {
+        /* rba[i] has ceil(nru/32) words (symbol.c:625-629) */
+        const size_t wl = mat->nru / 32 + ((mat->nru % 32) != 0);
+        c->rba = malloc(mat->rbal * sizeof(rba_t *));
+        c->rbal = mat->rbal;
+        for (len_t i = 0; i < mat->rbal; ++i) c->rba[i] = calloc(wl ? wl : 1, sizeof(rba_t));
+    }
+    return c;
+}
+
+static void free_clone_after_la(mat_t *c, const md_t *st)
+{
+    /* rows in c->tr[0..np) and their coefficient arrays are owned by us */
+    for (len_t i = 0; i < c->np; ++i) {
+        if (!c->tr || !c->tr[i]) continue;
+        hm_t ci = c->tr[i][COEFFS];
+        if (st->ff_bits == 8 && c->cf_8) free(c->cf_8[ci]);
+        else if (st->ff_bits == 16 && c->cf_16) free(c->cf_16[ci]);
+        else if (c->cf_32) free(c->cf_32[ci]);
+        free(c->tr[i]);
+    }
+    for (len_t i = 0; i < c->rbal; ++i) free(c->rba[i]);
+    free(c->rba);
+    free(c->rr); free(c->tr); free(c->cf_8); free(c->cf_16); free(c->cf_32);
+    free(c);
+}
+
+static int64_t compare_results(const f4la_flat_result *a, const f4la_flat_result *b)
+{
+    if (a->nrows != b->nrows) return 1 + (int64_t)(a->nrows > b->nrows ? a->nrows - b->nrows : b->nrows - a->nrows);
+    int64_t bad = 0;
+    for (uint32_t i = 0; i < a->nrows; ++i) {
+        uint64_t la = a->row_ptr[i + 1] - a->row_ptr[i];
+        uint64_t lb = b->row_ptr[i + 1] - b->row_ptr[i];
+        if (la != lb) { bad++; continue; }
+        if (memcmp(a->cols + a->row_ptr[i], b->cols + b->row_ptr[i], la * 4)) { bad++; continue; }
+        if (memcmp((unsigned char *)a->cf + a->row_ptr[i] * a->cf_bytes,
+                   (unsigned char *)b->cf + b->row_ptr[i] * b->cf_bytes, la * a->cf_bytes)) bad++;
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------------------ */
+/* the hooks                                                           */
+/* ------------------------------------------------------------------ */
+
+static void hook_common(int kind, mat_t *mat, const bs_t *tbr, const bs_t *bs, md_t *st)
+{
+    la_fn_t ref_fn = kind == 0 ? dispatch_linear_algebra : dispatch_exact_linear_algebra;
+    la_fn_t be_fn  = kind == 0 ? g_backend_la : g_backend_exact_la;
+    const double t0 = realtime();
+    g_la_calls++;
+    if (g_mode == 1 && be_fn) {
+        be_fn(mat, tbr, bs, st);
+        g_la_seconds += realtime() - t0;
+        return;
+    }
+    if (g_mode == 2 && be_fn) {
+        mat_t *c = clone_matrix(mat);
+        md_t stc = *st;
+        be_fn(c, tbr, bs, &stc);
+        f4la_flat_result rb, rr; uint32_t *b1, *m1, *b2, *m2;
+        flatten_output(&rb, &b1, &m1, c, &stc);
+        const double t1 = realtime();
+        ref_fn(mat, tbr, bs, st);
+        g_la_seconds += realtime() - t1;
+        flatten_output(&rr, &b2, &m2, mat, st);
+        int64_t bad = compare_results(&rb, &rr);
+        if (bad && g_verbose)
+            fprintf(stderr, "[refh] shadow mismatch kind %d call %d: %ld (np backend %u, ref %u)\n",
+                    kind, g_la_calls, (long)bad, rb.nrows, rr.nrows);
+        g_shadow_mismatch += bad; g_shadow_calls++;
+        free(rb.row_ptr); free(rb.cols); free(rb.cf); free(b1); free(m1);
+        free(rr.row_ptr); free(rr.cols); free(rr.cf); free(b2); free(m2);
+        free_clone_after_la(c, &stc);
+        return;
+    }
+    if (g_mode == 3 && g_nrec < g_max_records) {
+        refh_record *rec = new_record();
+        flatten_input(rec, mat, tbr, bs, st, 0);
+        rec->kind = kind; rec->laopt = st->laopt; rec->ff_bits = st->ff_bits;
+        rec->nf = st->nf; rec->final_step = st->in_final_reduction_step;
+        rec->trace_level = st->trace_level;
+        const double m0 = st->application_nr_mult, r0 = (double)st->application_nr_red;
+        const double t1 = realtime();
+        ref_fn(mat, tbr, bs, st);
+        rec->la_seconds = realtime() - t1;
+        g_la_seconds += rec->la_seconds;
+        rec->units = (st->application_nr_mult - m0) * 1000.0;
+        rec->pivot_apps = (double)st->application_nr_red - r0;
+        flatten_output(&rec->out, &rec->out_bindex, &rec->out_mult, mat, st);
+        return;
+    }
+    ref_fn(mat, tbr, bs, st);
+    g_la_seconds += realtime() - t0;
+}
+
+static void hook_la(mat_t *mat, const bs_t *const tbr, const bs_t *const bs, md_t *st)
+{ hook_common(0, mat, tbr, bs, st); }
+static void hook_exact_la(mat_t *mat, const bs_t *const tbr, const bs_t *const bs, md_t *st)
+{ hook_common(1, mat, tbr, bs, st); }
+
+static void hook_interred(mat_t *mat, bs_t *bs, md_t *st, int free_basis)
+{
+    const double t0 = realtime();
+    if (g_mode == 1 && g_backend_interred) g_backend_interred(mat, bs, st, free_basis);
+    else dispatch_interreduce_matrix_rows(mat, bs, st, free_basis);
+    g_la_seconds += realtime() - t0;
+}
+
+/* ------------------------------------------------------------------ */
+/* exported API                                                        */
+/* ------------------------------------------------------------------ */
+
+void refh_set_mode(int mode, int max_records, int verbose)
+{
+    g_mode = mode; g_max_records = max_records > 0 ? max_records : (1 << 30);
+    g_verbose = verbose;
+    linear_algebra = hook_la;
+    exact_linear_algebra = hook_exact_la;
+    interreduce_matrix_rows = hook_interred;
+}
+
+void refh_set_backend(void *la, void *exact_la, void *interred)
+{
+    g_backend_la = (la_fn_t)la;
+    g_backend_exact_la = (la_fn_t)exact_la;
+    g_backend_interred = (ir_fn_t)interred;
+}
+
+void refh_reset(void)
+{
+    for (int i = 0; i < g_nrec; ++i) free_record(&g_rec[i]);
+    g_nrec = 0;
+    g_shadow_mismatch = 0; g_shadow_calls = 0; g_la_seconds = 0.0; g_la_calls = 0;
+}
+
+int     refh_num_records(void)      { return g_nrec; }
+int64_t refh_shadow_mismatches(void){ return g_shadow_mismatch; }
+int64_t refh_shadow_calls(void)     { return g_shadow_calls; }
+double  refh_la_seconds(void)       { return g_la_seconds; }
+int     refh_la_calls(void)         { return g_la_calls; }
+const refh_record *refh_get_record(int i) { return (i >= 0 && i < g_nrec) ? &g_rec[i] : NULL; }
+void    refh_drop_record(int i)     { if (i >= 0 && i < g_nrec) free_record(&g_rec[i]); }
+size_t  refh_record_size(void)      { return sizeof(refh_record); }
+
+/* Result of one F4 run, owned by the harness until the next run. */
+typedef struct refh_gb {
+    int32_t  nelts;
+    int64_t  nterms;
+    int32_t *lens;      /* [nelts]            */
+    int32_t *exps;      /* [nterms * nvars]   */
+    int32_t *cfs;       /* [nterms]           */
+    double   f4_seconds;
+    double   la_seconds;
+    int32_t  la_calls;
+} refh_gb;
+
+static refh_gb g_gb;
+
+/* Runs the reference F4 (export_f4, f4.c:769-899) on the given system. */
+const refh_gb *refh_f4(const int32_t *lens, const int32_t *exps, const int32_t *cfs,
+                       uint32_t field_char, int32_t nvars, int32_t ngens,
+                       int32_t threads, int32_t laopt, int32_t info_level)
+{
+    free(g_gb.lens); free(g_gb.exps); free(g_gb.cfs);
+    memset(&g_gb, 0, sizeof(g_gb));
+    g_la_seconds = 0.0; g_la_calls = 0;
+    int32_t bld = 0; int32_t *blen = NULL, *bexp = NULL; void *bcf = NULL;
+    const double t0 = realtime();
+    int64_t nterms = export_f4(malloc, &bld, &blen, &bexp, &bcf, lens, exps, cfs,
+                               field_char, 0 /* DRL */, 0, nvars, ngens, 17,
+                               threads, 0, 0, laopt, 1 /* reduce gb */, 0, info_level);
+    g_gb.f4_seconds = realtime() - t0;
+    g_gb.la_seconds = g_la_seconds; g_gb.la_calls = g_la_calls;
+    g_gb.nelts = bld; g_gb.nterms = nterms;
+    g_gb.lens = blen; g_gb.exps = bexp; g_gb.cfs = (int32_t *)bcf;
+    return &g_gb;
+}
+
+/* Runs the reference LA on one flat matrix: builds mat_t/bs_t/md_t exactly
+ * as the F4 driver would hand them over (rows malloc()ed one by one with the
+ * 6-word prelude, data.h:49-59) and calls the dispatcher (io.c:878/962). */
+int refh_reference_la(const f4la_flat_matrix *in, int32_t laopt, int32_t threads,
+                      f4la_flat_result *out, double *seconds, double *units,
+                      double *pivot_apps)
+{
+    const uint32_t n = in->nru + in->nrl;
+    const size_t w = in->cf_bytes;
+    const int ff_bits = w == 1 ? 8 : w == 2 ? 16 : 32;
+    mat_t *mat = calloc(1, sizeof(mat_t));
+    bs_t  *bs  = calloc(1, sizeof(bs_t));
+    md_t  *st  = calloc(1, sizeof(md_t));
+    st->fc = in->fc; st->gfc = in->fc; st->nthrds = threads; st->laopt = laopt;
+    st->ff_bits = ff_bits; st->trace_level = NO_TRACER; st->info_level = 0;
+    st->nf = (in->flags & F4LA_FLAG_NORMALFORM) ? 1 : 0;
+    st->in_final_reduction_step = (in->flags & F4LA_FLAG_PIVOT_BY_LEAD) ? 1 : 0;
+    reset_function_pointers(in->fc, laopt);
+    bs->ld = bs->sz = in->ncf;
+    void **cfarr = calloc(in->ncf ? in->ncf : 1, sizeof(void *));
+    for (uint32_t c = 0; c < in->ncf; ++c)
+        cfarr[c] = (unsigned char *)in->cf + in->cf_ptr[c] * w;   /* never freed by the LA */
+    bs->cf_8 = (cf8_t **)cfarr; bs->cf_16 = (cf16_t **)cfarr; bs->cf_32 = (cf32_t **)cfarr;
+    mat->nru = in->nru; mat->nrl = in->nrl; mat->ncl = in->ncl; mat->ncr = in->ncr;
+    mat->nc = in->ncl + in->ncr; mat->nr = mat->sz = n;
+    mat->rr = malloc((in->nru ? in->nru : 1) * sizeof(hm_t *));
+    mat->tr = malloc((in->nrl ? in->nrl : 1) * sizeof(hm_t *));
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint64_t len = in->row_ptr[r + 1] - in->row_ptr[r];
+        hm_t *row = malloc((len + OFFSET) * sizeof(hm_t));
+        row[DEG] = 0; row[BINDEX] = r; row[MULT] = 0; row[COEFFS] = in->row_cf[r];
+        row[PRELOOP] = (hm_t)(len % UNROLL); row[LENGTH] = (hm_t)len;
+        memcpy(row + OFFSET, in->cols + in->row_ptr[r], len * sizeof(hm_t));
+        if (r < in->nru) mat->rr[r] = row; else mat->tr[r - in->nru] = row;
+    }
+    const double m0 = st->application_nr_mult;
+    const double t0 = realtime();
+    if (in->flags & (F4LA_FLAG_NORMALFORM | F4LA_FLAG_PIVOT_BY_LEAD))
+        dispatch_exact_linear_algebra(mat, bs, bs, st);
+    else
+        dispatch_linear_algebra(mat, bs, bs, st);
+    if (seconds) *seconds = realtime() - t0;
+    if (units) *units = (st->application_nr_mult - m0) * 1000.0;
+    if (pivot_apps) *pivot_apps = (double)st->application_nr_red;
+    uint32_t *bi, *mu;
+    flatten_output(out, &bi, &mu, mat, st);
+    out->src_row = bi;      /* BINDEX was set to the input row index above */
+    free(mu);
+    /* release what the LA left behind */
+    for (len_t i = 0; i < mat->np; ++i) {
+        if (!mat->tr[i]) continue;
+        hm_t ci = mat->tr[i][COEFFS];
+        if (ff_bits == 8) free(mat->cf_8[ci]); else if (ff_bits == 16) free(mat->cf_16[ci]); else free(mat->cf_32[ci]);
+        free(mat->tr[i]);
+    }
+    /* -l 44 frees mat->rr itself and NULLs it (la_ff_32.c:2495-2496) */
+    free(mat->rr);
+    free(mat->tr); free(mat->cf_8); free(mat->cf_16); free(mat->cf_32);
+    free(mat); free(cfarr); free(bs); free(st);
+    return 0;
+}
+
+void refh_free_result(f4la_flat_result *r)
+{
+    free(r->row_ptr); free(r->cols); free(r->cf); free(r->src_row);
+    memset(r, 0, sizeof(*r));
+}
+
+/* Offsets of the reference structs, for the ABI check of the product header.
+ * Order is fixed; see tests/test_abi_layout.py. */
+int refh_struct_layout(uint64_t *o, int cap)
+{
+    int k = 0;
+#define PUSH(x) do { if (k < cap) o[k] = (uint64_t)(x); k++; } while (0)
+    PUSH(sizeof(mat_t));
+    PUSH(offsetof(mat_t, tr)); PUSH(offsetof(mat_t, rba)); PUSH(offsetof(mat_t, rr));
+    PUSH(offsetof(mat_t, cf_8)); PUSH(offsetof(mat_t, cf_16)); PUSH(offsetof(mat_t, cf_32));
+    PUSH(offsetof(mat_t, cf_qq)); PUSH(offsetof(mat_t, cf_ab_qq));
+    PUSH(offsetof(mat_t, sz)); PUSH(offsetof(mat_t, np)); PUSH(offsetof(mat_t, nr));
+    PUSH(offsetof(mat_t, nc)); PUSH(offsetof(mat_t, nru)); PUSH(offsetof(mat_t, nrl));
+    PUSH(offsetof(mat_t, ncl)); PUSH(offsetof(mat_t, ncr)); PUSH(offsetof(mat_t, rbal));
+    PUSH(offsetof(mat_t, cd));
+    PUSH(sizeof(bs_t));
+    PUSH(offsetof(bs_t, ld)); PUSH(offsetof(bs_t, sz)); PUSH(offsetof(bs_t, hm));
+    PUSH(offsetof(bs_t, cf_8)); PUSH(offsetof(bs_t, cf_16)); PUSH(offsetof(bs_t, cf_32));
+    PUSH(sizeof(md_t));
+    PUSH(offsetof(md_t, tr)); PUSH(offsetof(md_t, trace_level)); PUSH(offsetof(md_t, np));
+    PUSH(offsetof(md_t, la_ctime)); PUSH(offsetof(md_t, la_rtime));
+    PUSH(offsetof(md_t, num_zerored)); PUSH(offsetof(md_t, fc)); PUSH(offsetof(md_t, laopt));
+    PUSH(offsetof(md_t, nthrds)); PUSH(offsetof(md_t, ff_bits)); PUSH(offsetof(md_t, nf));
+    PUSH(offsetof(md_t, in_final_reduction_step)); PUSH(offsetof(md_t, info_level));
+    PUSH(offsetof(md_t, application_nr_mult)); PUSH(offsetof(md_t, application_nr_add));
+    PUSH(offsetof(md_t, application_nr_red));
+    PUSH(OFFSET); PUSH(LENGTH); PUSH(PRELOOP); PUSH(COEFFS); PUSH(MULT); PUSH(BINDEX); PUSH(DEG);
+#undef PUSH
+    return k;
+}

@@ -1,0 +1,188 @@
+"""ctypes binding of oracle/_ref/libneogb_ref.so -- TEST INFRASTRUCTURE ONLY.
+
+The shared object is the UNMODIFIED reference neogb plus oracle/ref_harness.c.
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU-baseline /
+``--impl reference`` legs may import this module; the product package
+``msolve_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from msolve_b200.flat import CFlatMatrix, CFlatResult, FlatMatrix, FlatResult, _np_from_ptr  # noqa: E402
+
+LIB_PATH = os.path.join(_HERE, "_ref", "libneogb_ref.so")
+
+MODE_REFERENCE, MODE_BACKEND, MODE_SHADOW, MODE_RECORD = 0, 1, 2, 3
+
+
+class _CRecord(C.Structure):
+    _fields_ = [
+        ("inp", CFlatMatrix), ("bindex", C.c_void_p), ("mult", C.c_void_p),
+        ("out", CFlatResult), ("out_bindex", C.c_void_p), ("out_mult", C.c_void_p),
+        ("kind", C.c_int32), ("laopt", C.c_int32), ("ff_bits", C.c_int32),
+        ("nf", C.c_int32), ("final_step", C.c_int32), ("trace_level", C.c_int32),
+        ("la_seconds", C.c_double), ("units", C.c_double), ("pivot_apps", C.c_double),
+    ]
+
+
+class _CGb(C.Structure):
+    _fields_ = [
+        ("nelts", C.c_int32), ("nterms", C.c_int64),
+        ("lens", C.c_void_p), ("exps", C.c_void_p), ("cfs", C.c_void_p),
+        ("f4_seconds", C.c_double), ("la_seconds", C.c_double), ("la_calls", C.c_int32),
+    ]
+
+
+@dataclass
+class Record:
+    matrix: FlatMatrix
+    result: FlatResult
+    kind: int
+    laopt: int
+    ff_bits: int
+    nf: int
+    final_step: int
+    trace_level: int
+    la_seconds: float
+    units: float
+    pivot_apps: float
+
+
+@dataclass
+class GroebnerBasis:
+    lens: np.ndarray
+    exps: np.ndarray
+    cfs: np.ndarray
+    f4_seconds: float
+    la_seconds: float
+    la_calls: int
+
+    def digest(self) -> str:
+        import hashlib
+        h = hashlib.sha256()
+        for a in (self.lens, self.exps, self.cfs):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.refh_set_mode.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.refh_set_backend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refh_num_records.restype = C.c_int
+        L.refh_shadow_mismatches.restype = C.c_int64
+        L.refh_shadow_calls.restype = C.c_int64
+        L.refh_la_seconds.restype = C.c_double
+        L.refh_la_calls.restype = C.c_int
+        L.refh_get_record.restype = C.POINTER(_CRecord)
+        L.refh_get_record.argtypes = [C.c_int]
+        L.refh_drop_record.argtypes = [C.c_int]
+        L.refh_record_size.restype = C.c_size_t
+        L.refh_f4.restype = C.POINTER(_CGb)
+        L.refh_f4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                              C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.refh_reference_la.restype = C.c_int
+        L.refh_reference_la.argtypes = [C.POINTER(CFlatMatrix), C.c_int32, C.c_int32,
+                                        C.POINTER(CFlatResult), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.refh_free_result.argtypes = [C.POINTER(CFlatResult)]
+        L.refh_struct_layout.restype = C.c_int
+        L.refh_struct_layout.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+        assert L.refh_record_size() == C.sizeof(_CRecord), "refh_record layout drifted"
+        _lib = L
+    return _lib
+
+
+def set_mode(mode: int, max_records: int = 0, verbose: int = 0) -> None:
+    lib().refh_set_mode(mode, max_records, verbose)
+
+
+def set_backend(la=None, exact_la=None, interred=None) -> None:
+    """Addresses (ints / ctypes function pointers) of the backend entry points."""
+    def addr(f):
+        if f is None:
+            return None
+        return C.cast(f, C.c_void_p).value if not isinstance(f, int) else f
+    lib().refh_set_backend(addr(la), addr(exact_la), addr(interred))
+
+
+def reset() -> None:
+    lib().refh_reset()
+
+
+def run_f4(system, p: int, threads: int = 1, laopt: int = 2, info_level: int = 0) -> GroebnerBasis:
+    lens, exps, cfs = system.encode(p)
+    g = lib().refh_f4(lens.ctypes.data, exps.ctypes.data, cfs.ctypes.data, p,
+                      system.nvars, len(lens), threads, laopt, info_level).contents
+    n, nt = g.nelts, g.nterms
+    return GroebnerBasis(_np_from_ptr(g.lens, n, np.int32),
+                         _np_from_ptr(g.exps, nt * system.nvars, np.int32),
+                         _np_from_ptr(g.cfs, nt, np.int32),
+                         g.f4_seconds, g.la_seconds, g.la_calls)
+
+
+def records(drop: bool = True) -> List[Record]:
+    """Copies the recorded matrices out of the harness (and frees them there)."""
+    L = lib()
+    out = []
+    for i in range(L.refh_num_records()):
+        r = L.refh_get_record(i).contents
+        out.append(Record(FlatMatrix.from_c(r.inp), FlatResult.from_c(r.out), r.kind, r.laopt,
+                          r.ff_bits, r.nf, r.final_step, r.trace_level, r.la_seconds,
+                          r.units, r.pivot_apps))
+        if drop:
+            L.refh_drop_record(i)
+    return out
+
+
+def record_f4(system, p: int, threads: int = 1, laopt: int = 2, max_records: int = 0):
+    """Runs the reference F4 and returns (GroebnerBasis, [Record per LA call])."""
+    reset()
+    set_mode(MODE_RECORD, max_records)
+    gb = run_f4(system, p, threads, laopt)
+    recs = records()
+    reset()
+    set_mode(MODE_REFERENCE)
+    return gb, recs
+
+
+def reference_la(m: FlatMatrix, laopt: int = 2, threads: int = 1):
+    """Reference LA on one flat matrix -> (FlatResult, seconds, units, pivot_apps)."""
+    cm = m.c_struct()
+    res = CFlatResult()
+    sec, units, apps = C.c_double(), C.c_double(), C.c_double()
+    rc = lib().refh_reference_la(C.byref(cm), laopt, threads, C.byref(res),
+                                 C.byref(sec), C.byref(units), C.byref(apps))
+    assert rc == 0
+    out = FlatResult.from_c(res)
+    lib().refh_free_result(C.byref(res))
+    return out, sec.value, units.value, apps.value
+
+
+def struct_layout() -> List[int]:
+    buf = (C.c_uint64 * 128)()
+    n = lib().refh_struct_layout(buf, 128)
+    return [int(buf[i]) for i in range(n)]
