@@ -118,6 +118,12 @@ f4la_ctx *f4la_b200_create(int device);
 void f4la_b200_destroy(f4la_ctx *ctx);
 const char *f4la_b200_last_error(const f4la_ctx *ctx);
 
+/* Page-locked host memory for the flat arrays handed to f4la_b200_reduce():
+ * host->device copies from such buffers run at full PCIe rate and
+ * asynchronously.  Plain malloc() memory works too, only slower. */
+void *f4la_b200_pinned_alloc(size_t bytes);
+void  f4la_b200_pinned_free(void *p);
+
 /* Echelon form from HOST buffers: copies in, reduces, copies the result out.
  * Replaces the computational body of exact_sparse_reduced_echelon_form_ff_*
  * (reference la_ff_32.c:2595-2770). */

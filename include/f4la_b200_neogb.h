@@ -1,0 +1,70 @@
+/* f4la_b200_neogb.h -- drop-in replacements for neogb's linear-algebra
+ * function pointers (reference src/neogb/data.h:529-595, defaults in
+ * data.c:71-103, dispatchers in io.c:868-1044).
+ *
+ * The reference selects its GF(p) linear algebra through WRITABLE GLOBAL
+ * FUNCTION POINTERS; assigning them once before core_f4()/core_gba() takes
+ * over the path.  This header declares functions with
+ * exactly those signatures.  mat_t / bs_t / md_t are NOT re-declared here:
+ * the reference-side stub passes their field offsets (computed by its own
+ * compiler with offsetof) in an f4la_neogb_layout, so the backend stays ABI
+ * correct if the reference adds or reorders fields.  See INTEGRATION.md for
+ * the stub a maintainer adds to the reference.
+ */
+#ifndef F4LA_B200_NEOGB_H
+#define F4LA_B200_NEOGB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Field offsets (bytes) of the reference structs, filled in with offsetof()
+ * on the reference side.  Row prelude indices are the OFFSET/LENGTH/... macros
+ * of data.h:49-59. */
+typedef struct f4la_neogb_layout {
+    uint32_t struct_size;       /* sizeof(f4la_neogb_layout), version check   */
+    /* mat_t, data.h:203-232 */
+    uint32_t mat_tr, mat_rba, mat_rr, mat_cf_8, mat_cf_16, mat_cf_32;
+    uint32_t mat_sz, mat_np, mat_nr, mat_nc, mat_nru, mat_nrl, mat_ncl, mat_ncr, mat_rbal;
+    /* bs_t, data.h:178-200 */
+    uint32_t bs_ld, bs_cf_8, bs_cf_16, bs_cf_32;
+    /* md_t, data.h:327-437 */
+    uint32_t md_trace_level, md_np, md_la_ctime, md_la_rtime, md_num_zerored;
+    uint32_t md_fc, md_laopt, md_nthrds, md_ff_bits, md_nf, md_in_final_reduction_step;
+    uint32_t md_info_level, md_application_nr_mult, md_application_nr_add, md_application_nr_red;
+    /* row prelude, data.h:49-59 */
+    uint32_t row_offset, row_length, row_preloop, row_coeffs, row_mult, row_bindex, row_deg;
+    uint32_t unroll;            /* UNROLL (data.h:47), PRELOOP = len % UNROLL */
+} f4la_neogb_layout;
+
+/* Must be called once before any of the entry points below; copies *layout. */
+int f4la_b200_neogb_configure(const f4la_neogb_layout *layout);
+
+/* CUDA device used by the calling host thread (default: $F4LA_B200_DEVICE or
+ * 0).  The QQ multi-modular loop runs one F4 instance per OpenMP thread
+ * (reference src/msolve/msolve.c:1815-1824); bind thread t to GPU t mod G. */
+void f4la_b200_neogb_set_device(int device);
+
+/* Replaces `linear_algebra` (data.h:545-550; default dispatch_linear_algebra,
+ * io.c:878): st->laopt 1, 2, 42, 43, 44 all yield the same unique reduced row
+ * echelon form, which is what this computes (exactly, every time). */
+void f4la_b200_linear_algebra(void *mat, const void *tbr, const void *bs, void *st);
+
+/* Replaces `exact_linear_algebra` (data.h:531-536; io.c:962). */
+void f4la_b200_exact_linear_algebra(void *mat, const void *tbr, const void *bs, void *st);
+
+/* Accumulated device statistics of the calling thread since the last reset. */
+typedef struct f4la_neogb_totals {
+    uint64_t calls;
+    double   ms_total, ms_flatten, ms_h2d, ms_prep, ms_reduce, ms_echelon, ms_d2h, ms_materialize;
+    uint64_t units, bytes_h2d, bytes_d2h, kernel_launches;
+} f4la_neogb_totals;
+void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

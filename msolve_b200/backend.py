@@ -1,0 +1,183 @@
+"""Host-side binding of the product library ``csrc/libf4la_b200.so``.
+
+The library is the only compute path: if it is missing, or no sm_100 device is
+usable, construction fails loudly -- there is no CPU fallback (the plain-C
+restatement under ``oracle/`` is test infrastructure and is never imported
+from here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .flat import CFlatMatrix, CFlatResult, CStats, FlatMatrix, FlatResult
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libf4la_b200.so")
+
+EXPORTED_SYMBOLS = [
+    # include/f4la_b200.h
+    "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
+    "f4la_b200_last_error", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
+    "f4la_b200_reduce", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
+    "f4la_b200_free_result",
+    # include/f4la_b200_neogb.h
+    "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_linear_algebra",
+    "f4la_b200_exact_linear_algebra", "f4la_b200_neogb_get_totals",
+]
+
+
+class F4LAError(RuntimeError):
+    pass
+
+
+class NeogbTotals(C.Structure):
+    _fields_ = [
+        ("calls", C.c_uint64),
+        ("ms_total", C.c_double), ("ms_flatten", C.c_double), ("ms_h2d", C.c_double),
+        ("ms_prep", C.c_double), ("ms_reduce", C.c_double), ("ms_echelon", C.c_double),
+        ("ms_d2h", C.c_double), ("ms_materialize", C.c_double),
+        ("units", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the product library and declare the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise F4LAError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C msolve_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L.f4la_b200_version.restype = C.c_char_p
+    L.f4la_b200_device_count.restype = C.c_int
+    L.f4la_b200_create.restype = C.c_void_p
+    L.f4la_b200_create.argtypes = [C.c_int]
+    L.f4la_b200_destroy.argtypes = [C.c_void_p]
+    L.f4la_b200_last_error.restype = C.c_char_p
+    L.f4la_b200_last_error.argtypes = [C.c_void_p]
+    L.f4la_b200_pinned_alloc.restype = C.c_void_p
+    L.f4la_b200_pinned_alloc.argtypes = [C.c_size_t]
+    L.f4la_b200_pinned_free.argtypes = [C.c_void_p]
+    L.f4la_b200_reduce.restype = C.c_int
+    L.f4la_b200_reduce.argtypes = [C.c_void_p, C.POINTER(CFlatMatrix), C.POINTER(CFlatResult), C.POINTER(CStats)]
+    L.f4la_b200_upload.restype = C.c_void_p
+    L.f4la_b200_upload.argtypes = [C.c_void_p, C.POINTER(CFlatMatrix)]
+    L.f4la_b200_reduce_resident.restype = C.c_int
+    L.f4la_b200_reduce_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CFlatResult), C.POINTER(CStats)]
+    L.f4la_b200_release.argtypes = [C.c_void_p, C.c_void_p]
+    L.f4la_b200_free_result.argtypes = [C.POINTER(CFlatResult)]
+    L.f4la_b200_neogb_configure.restype = C.c_int
+    L.f4la_b200_neogb_configure.argtypes = [C.c_void_p]
+    L.f4la_b200_neogb_set_device.argtypes = [C.c_int]
+    L.f4la_b200_neogb_get_totals.argtypes = [C.POINTER(NeogbTotals), C.c_int]
+    _lib = L
+    return L
+
+
+def pinned_copy(L: C.CDLL, a: np.ndarray) -> Tuple[np.ndarray, int]:
+    """Copy ``a`` into page-locked memory; returns (view, base address to free)."""
+    a = np.ascontiguousarray(a)
+    nbytes = max(a.nbytes, 1)
+    ptr = L.f4la_b200_pinned_alloc(nbytes)
+    if not ptr:
+        raise F4LAError("pinned host allocation failed")
+    buf = (C.c_ubyte * nbytes).from_address(ptr)
+    view = np.frombuffer(buf, dtype=a.dtype, count=a.size)
+    view[...] = a.reshape(-1)
+    return view, ptr
+
+
+class Backend:
+    """One device context (its own CUDA stream); not shared between threads."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.ctx = self.lib.f4la_b200_create(device)
+        if not self.ctx:
+            raise F4LAError(f"f4la_b200_create({device}) failed: no usable sm_100 GPU (no CPU fallback)")
+        self.device = device
+
+    def close(self) -> None:
+        if self.ctx:
+            self.lib.f4la_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.f4la_b200_last_error(self.ctx)
+            raise F4LAError(f"f4la_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+    def reduce(self, m: FlatMatrix):
+        """Echelon form from host buffers -> (FlatResult, stats dict)."""
+        cm, res, st = m.c_struct(), CFlatResult(), CStats()
+        self._check(self.lib.f4la_b200_reduce(self.ctx, C.byref(cm), C.byref(res), C.byref(st)))
+        out = FlatResult.from_c(res)
+        self.lib.f4la_b200_free_result(C.byref(res))
+        return out, st.as_dict()
+
+    def pin(self, m: FlatMatrix) -> "PinnedMatrix":
+        return PinnedMatrix(self.lib, m)
+
+    def upload(self, m: FlatMatrix) -> "ResidentMatrix":
+        cm = m.c_struct()
+        h = self.lib.f4la_b200_upload(self.ctx, C.byref(cm))
+        if not h:
+            raise F4LAError("f4la_b200_upload failed")
+        return ResidentMatrix(self, h)
+
+    def reduce_resident(self, rm: "ResidentMatrix", want_result: bool = True):
+        res, st = CFlatResult(), CStats()
+        self._check(self.lib.f4la_b200_reduce_resident(self.ctx, rm.handle, C.byref(res), C.byref(st)))
+        out = FlatResult.from_c(res) if want_result else None
+        self.lib.f4la_b200_free_result(C.byref(res))
+        return out, st.as_dict()
+
+
+class ResidentMatrix:
+    def __init__(self, be: Backend, handle):
+        self.be, self.handle = be, handle
+
+    def release(self) -> None:
+        if self.handle:
+            self.be.lib.f4la_b200_release(self.be.ctx, self.handle)
+            self.handle = None
+
+
+class PinnedMatrix:
+    """A FlatMatrix whose arrays live in page-locked host memory."""
+
+    def __init__(self, L: C.CDLL, m: FlatMatrix):
+        self.lib = L
+        self._ptrs = []
+        arrs = {}
+        for name in ("row_ptr", "cols", "row_cf", "cf_ptr", "cf"):
+            view, ptr = pinned_copy(L, getattr(m, name))
+            arrs[name] = view
+            self._ptrs.append(ptr)
+        self.matrix = FlatMatrix.__new__(FlatMatrix)
+        self.matrix.__dict__.update(m.__dict__)
+        self.matrix.__dict__.update(arrs)
+
+    def free(self) -> None:
+        for p in self._ptrs:
+            self.lib.f4la_b200_pinned_free(p)
+        self._ptrs = []

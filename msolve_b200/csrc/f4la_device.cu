@@ -1,0 +1,565 @@
+/* f4la_device.cu -- host side of the flat C ABI (include/f4la_b200.h):
+ * device memory, streams, launch orchestration, result materialisation.
+ * The kernels live in f4la_kernels.cuh.  No CPU fallback: without a usable
+ * sm_100 device f4la_b200_create() fails and says so. */
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "f4la_b200.h"
+#include "f4la_kernels.cuh"
+
+using namespace f4la;
+
+namespace {
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostBuf {            /* pinned */
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr size_t kL2Budget = (size_t)88 << 20;   /* bytes of V kept in flight */
+
+double now_ms()
+{
+    using clk = std::chrono::steady_clock;
+    return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct f4la_ctx {
+    int           device = 0;
+    cudaStream_t  stream = nullptr;
+    cudaEvent_t   ev[8] = {};
+    int           sm_count = 0;
+    char          err[512] = {0};
+    uint32_t      launches = 0;
+    /* scratch (grow-only) */
+    DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
+    DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
+    HostBuf h_small, h_dense;
+};
+
+struct f4la_resident {
+    f4la_flat_matrix dims;        /* pointers below are DEVICE pointers */
+    uint64_t *row_ptr = nullptr;
+    uint32_t *cols = nullptr;
+    uint32_t *row_cf = nullptr;
+    uint64_t *cf_ptr = nullptr;
+    void     *cf = nullptr;
+    uint64_t  nnz = 0, ncoef = 0;
+    uint64_t  bytes = 0;
+};
+
+namespace {
+
+int fail(f4la_ctx *ctx, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[f4la_b200] error: %s\n", ctx->err);
+    return code;
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail(ctx, F4LA_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define OK(call)                                                                       \
+    do {                                                                               \
+        int rc_ = (call);                                                              \
+        if (rc_ != F4LA_OK) return rc_;                                                \
+    } while (0)
+
+int ensure(f4la_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return F4LA_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return F4LA_OK;
+}
+
+int ensure_host(f4la_ctx *ctx, HostBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return F4LA_OK;
+    if (b.p) CU(cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return F4LA_OK;
+}
+
+void free_dev(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+template <typename T> T *as(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+inline unsigned blocks_for_warps(uint64_t nwarps, int threads = 256)
+{
+    uint64_t b = (nwarps * 32 + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > 148 * 64) b = 148 * 64;
+    return (unsigned)b;
+}
+
+template <int T>
+void launch_solve(f4la_ctx *ctx, const SolveArgs &a, unsigned nchunks, bool wide)
+{
+    const unsigned gx = a.n_long + (a.n_short + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (gx == 0 || nchunks == 0) return;
+    dim3 grid(gx, nchunks);
+    if (wide) k_pull_solve<T, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);
+    else      k_pull_solve<T, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a);
+    ctx->launches++;
+}
+
+void launch_solve_T(f4la_ctx *ctx, int T, const SolveArgs &a, unsigned nchunks, bool wide)
+{
+    switch (T) {
+        case 1: launch_solve<1>(ctx, a, nchunks, wide); break;
+        case 2: launch_solve<2>(ctx, a, nchunks, wide); break;
+        case 3: launch_solve<3>(ctx, a, nchunks, wide); break;
+        default: launch_solve<4>(ctx, a, nchunks, wide); break;
+    }
+}
+
+void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
+{
+    memset(out, 0, sizeof(*out));
+    out->cf_bytes = cf_bytes;
+    out->row_ptr = (uint64_t *)calloc(1, sizeof(uint64_t));
+    out->cols = (uint32_t *)malloc(sizeof(uint32_t));
+    out->cf = malloc(4);
+    out->src_row = (uint32_t *)malloc(sizeof(uint32_t));
+}
+
+/* The whole pipeline on a device-resident matrix. */
+int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f4la_stats *st)
+{
+    const f4la_flat_matrix &d = m->dims;
+    const uint32_t nru = d.nru, nrl = d.nrl, ncl = d.ncl, ncr = d.ncr, p = d.fc;
+    const uint32_t nc = ncl + ncr;
+    const uint64_t pinv = ~0ULL / p;
+    const bool wide = p >= 65536u;
+    cudaStream_t s = ctx->stream;
+    const uint32_t launches0 = ctx->launches;
+
+    if (d.flags != F4LA_FLAG_NONE)
+        return fail(ctx, F4LA_ERR_ARG, "flags 0x%x not supported by the device pipeline yet", d.flags);
+    if (nru != ncl)
+        return fail(ctx, F4LA_ERR_ARG, "echelon mode needs nru == ncl (got %u, %u)", nru, ncl);
+    if (m->nnz >= 0xfffffff0ull)
+        return fail(ctx, F4LA_ERR_ARG, "matrix too large: %llu non-zeros", (unsigned long long)m->nnz);
+    if (nrl == 0 || ncr == 0) { empty_result(out, d.cf_bytes); return F4LA_OK; }
+
+    CU(cudaEventRecord(ctx->ev[0], s));
+
+    /* ---- 1. pull lists (CSC of the strictly upper part of the pivot rows) ---- */
+    OK(ensure(ctx, ctx->col_cnt, ((size_t)nc + 2) * 4));
+    OK(ensure(ctx, ctx->col_ptr, ((size_t)nc + 2) * 4));
+    OK(ensure(ctx, ctx->flags32, 64));
+    OK(ensure_host(ctx, ctx->h_small, 1 << 20));
+    uint32_t *h_small = (uint32_t *)ctx->h_small.p;
+    uint32_t *d_err = as<uint32_t>(ctx->flags32);           /* [0] err, [1] changed, [2] max level */
+    CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));
+    CU(cudaMemsetAsync(d_err, 0, 64, s));
+    if (nru) {
+        k_pull_count<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
+                                                           d.cf_bytes, nru, ncl, nc, as<uint32_t>(ctx->col_cnt), d_err);
+        ctx->launches++;
+    }
+    k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->col_cnt), as<uint32_t>(ctx->col_ptr), nc);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(h_small, as<uint32_t>(ctx->col_ptr) + nc, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_small + 1, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    const uint32_t nnz_pull = h_small[0];
+    if (h_small[1])
+        return fail(ctx, F4LA_ERR_ARG, "malformed pivot rows (error bits 0x%x: 1 lead not first, 2 not upper "
+                    "triangular, 4 column out of range, 8 lead coefficient != 1)", h_small[1]);
+    OK(ensure(ctx, ctx->ent, ((size_t)nnz_pull + 1) * sizeof(uint2)));
+    CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));   /* reuse as cursor */
+    if (nru) {
+        k_pull_fill<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
+                                                          nru, nc, p, as<uint32_t>(ctx->col_ptr),
+                                                          as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent));
+        ctx->launches++;
+    }
+
+    /* ---- 2. levels of the pivot columns ---- */
+    uint32_t nlev = 0;
+    std::vector<uint32_t> slot_ptr_h;
+    if (ncl) {
+        OK(ensure(ctx, ctx->level, (size_t)ncl * 4));
+        CU(cudaMemsetAsync(ctx->level.p, 0, (size_t)ncl * 4, s));
+        for (int it = 0;; ++it) {
+            CU(cudaMemsetAsync(d_err + 1, 0, 4, s));
+            for (int k = 0; k < 4; ++k) {
+                k_level_relax<<<blocks_for_warps(ncl), 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), as<uint2>(ctx->ent),
+                                                                    ncl, as<uint32_t>(ctx->level), d_err + 1);
+                ctx->launches++;
+            }
+            CU(cudaMemcpyAsync(h_small, d_err + 1, 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+            if (!h_small[0]) break;
+            if (it > (int)ncl) return fail(ctx, F4LA_ERR_ARG, "level relaxation does not converge (cyclic pivots?)");
+        }
+        /* class histogram: slot 2l = long columns of level l, 2l+1 = short ones */
+        OK(ensure(ctx, ctx->slots, ((size_t)2 * ncl + 4) * 4));
+        OK(ensure(ctx, ctx->slot_ptr, ((size_t)2 * ncl + 4) * 4));
+        OK(ensure(ctx, ctx->order, (size_t)ncl * 4));
+        CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)2 * ncl + 4) * 4, s));
+        k_level_count<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->level), as<uint32_t>(ctx->col_ptr), ncl,
+                                                        as<uint32_t>(ctx->slots), d_err + 2);
+        ctx->launches++;
+        CU(cudaMemcpyAsync(h_small, d_err + 2, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+        nlev = h_small[0] + 1;
+        const uint32_t nslots = 2 * nlev;
+        k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->slots), as<uint32_t>(ctx->slot_ptr), nslots);
+        ctx->launches++;
+        CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)nslots + 1) * 4, s));  /* reuse as cursor */
+        k_level_fill<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->level), as<uint32_t>(ctx->col_ptr), ncl,
+                                                       as<uint32_t>(ctx->slot_ptr), as<uint32_t>(ctx->slots),
+                                                       as<uint32_t>(ctx->order));
+        ctx->launches++;
+        slot_ptr_h.resize(nslots + 1);
+        OK(ensure_host(ctx, ctx->h_small, ((size_t)nslots + 16) * 4));
+        h_small = (uint32_t *)ctx->h_small.p;
+        CU(cudaMemcpyAsync(h_small, ctx->slot_ptr.p, ((size_t)nslots + 1) * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+        memcpy(slot_ptr_h.data(), h_small, ((size_t)nslots + 1) * 4);
+    }
+    CU(cudaEventRecord(ctx->ev[1], s));
+
+    /* ---- 3. chunking of the lower rows ---- */
+    int T = (int)((nrl + kRowsPerT - 1) / kRowsPerT);
+    if (T > kMaxT) T = kMaxT;
+    while (T > 1 && (size_t)nc * kRowsPerT * T * 4 > kL2Budget) --T;
+    const uint32_t Rc = kRowsPerT * T;
+    const uint32_t nchunks = (nrl + Rc - 1) / Rc;
+    uint32_t G = (uint32_t)(kL2Budget / ((size_t)nc * Rc * 4));
+    if (G < 1) G = 1;
+    if (G > nchunks) G = nchunks;
+    const uint64_t ld = (uint64_t)nchunks * Rc;
+    OK(ensure(ctx, ctx->V, (size_t)G * nc * Rc * 4));
+    OK(ensure(ctx, ctx->D, (size_t)ncr * ld * 4));
+
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.col_ptr = as<uint32_t>(ctx->col_ptr);
+    a.ent = as<uint2>(ctx->ent);
+    a.V = as<uint32_t>(ctx->V);
+    a.nc = nc; a.Rc = Rc; a.p = p; a.pinv = pinv;
+
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
+        const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
+        CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
+        const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
+        k_scatter_lower<<<blocks_for_warps(rows_here), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
+                                                                    d.cf_bytes, nru, nrl, nc, p, c0, g, Rc,
+                                                                    as<uint32_t>(ctx->V), d_err);
+        ctx->launches++;
+        /* level 0 columns have no sources: V[j] already final */
+        for (uint32_t l = 1; l < nlev; ++l) {
+            SolveArgs b = a;
+            b.long_cols = as<uint32_t>(ctx->order) + slot_ptr_h[2 * l];
+            b.n_long = slot_ptr_h[2 * l + 1] - slot_ptr_h[2 * l];
+            b.short_cols = as<uint32_t>(ctx->order) + slot_ptr_h[2 * l + 1];
+            b.n_short = slot_ptr_h[2 * l + 2] - slot_ptr_h[2 * l + 1];
+            b.out = nullptr;
+            launch_solve_T(ctx, T, b, g, wide);
+        }
+        /* the non-pivot columns: D' = D - M B, written to the trailing block */
+        SolveArgs b = a;
+        b.long_cols = nullptr; b.short_cols = nullptr; b.col_base = ncl;
+        b.n_long = ncr; b.n_short = 0;
+        b.out = as<uint32_t>(ctx->D); b.out_ld = ld; b.out_col0 = ncl; b.chunk0 = c0;
+        launch_solve_T(ctx, T, b, g, wide);
+    }
+    CU(cudaEventRecord(ctx->ev[2], s));
+
+    /* ---- 4. Gauss-Jordan on the trailing block ---- */
+    const uint32_t maxrank = nrl < ncr ? nrl : ncr;
+    OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
+    OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
+    OK(ensure(ctx, ctx->used, (size_t)ld + 16));
+    OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
+    OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
+    OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
+    OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
+    CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
+    CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
+    CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
+    uint32_t *Dm = as<uint32_t>(ctx->D);
+    k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+    ctx->launches++;
+    GEState *h_state = (GEState *)ctx->h_small.p;
+    for (uint32_t done_steps = 0;;) {
+        const int batch = 16;
+        for (int k = 0; k < batch; ++k) {
+            k_ge_find<<<1, 1024, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                         as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                                         as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p);
+            k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                               as<GEState>(ctx->gestate), p, pinv);
+            ctx->launches += 2;
+        }
+        done_steps += batch;
+        CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+        if (h_state->done) break;
+        if (done_steps > maxrank + 2 * batch)
+            return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+    }
+    const uint32_t rank = h_state->rank;
+    CU(cudaEventRecord(ctx->ev[3], s));
+
+    /* ---- 5. reduced rows back to the host ---- */
+    if (rank == 0) {
+        empty_result(out, d.cf_bytes);
+    } else {
+        const size_t dense_bytes = (size_t)rank * ncr * 4;
+        OK(ensure(ctx, ctx->dense_out, dense_bytes));
+        OK(ensure_host(ctx, ctx->h_dense, dense_bytes + (size_t)rank * 8));
+        dim3 grid((ncr + 255) / 256, rank);
+        k_ge_extract<<<grid, 256, 0, s>>>(Dm, ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                          as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
+                                          as<uint32_t>(ctx->dense_out), p, pinv);
+        ctx->launches++;
+        uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
+        uint32_t *h_pivrow = h_dense + (size_t)rank * ncr;
+        CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_pivrow, ctx->pivrow.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+        memset(out, 0, sizeof(*out));
+        out->nrows = rank; out->cf_bytes = d.cf_bytes;
+        out->row_ptr = (uint64_t *)malloc(((size_t)rank + 1) * sizeof(uint64_t));
+        out->src_row = (uint32_t *)malloc((size_t)rank * sizeof(uint32_t));
+        uint64_t nnz = 0;
+        for (uint32_t t = 0; t < rank; ++t) {
+            out->row_ptr[t] = nnz;
+            const uint32_t *row = h_dense + (size_t)t * ncr;
+            for (uint32_t c = 0; c < ncr; ++c) nnz += row[c] != 0;
+            out->src_row[t] = h_pivrow[rank - 1 - t];
+        }
+        out->row_ptr[rank] = nnz;
+        out->cols = (uint32_t *)malloc((nnz ? nnz : 1) * sizeof(uint32_t));
+        out->cf = malloc((nnz ? nnz : 1) * (size_t)d.cf_bytes);
+        uint64_t k = 0;
+        for (uint32_t t = 0; t < rank; ++t) {
+            const uint32_t *row = h_dense + (size_t)t * ncr;
+            for (uint32_t c = 0; c < ncr; ++c) {
+                const uint32_t v = row[c];
+                if (!v) continue;
+                out->cols[k] = ncl + c;
+                if (d.cf_bytes == 4) ((uint32_t *)out->cf)[k] = v;
+                else if (d.cf_bytes == 2) ((uint16_t *)out->cf)[k] = (uint16_t)v;
+                else ((uint8_t *)out->cf)[k] = (uint8_t)v;
+                ++k;
+            }
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[4], s));
+    CU(cudaEventSynchronize(ctx->ev[4]));
+
+    if (st) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_prep = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_reduce = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st->ms_echelon = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_d2h = ms;
+        st->units = (uint64_t)nnz_pull * nrl;
+        st->pivot_applications = (uint64_t)nnz_pull;
+        st->bytes_d2h = (uint64_t)rank * ncr * 4;
+        st->kernel_launches = ctx->launches - launches0;
+        st->rank = rank;
+    }
+    return F4LA_OK;
+}
+
+int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r)
+{
+    const uint64_t n = (uint64_t)in->nru + in->nrl;
+    if (in->fc < 2 || in->fc >= 0x80000000u)
+        return fail(ctx, F4LA_ERR_ARG, "field characteristic %u out of range (need 2 <= p < 2^31)", in->fc);
+    if (in->cf_bytes != 1 && in->cf_bytes != 2 && in->cf_bytes != 4)
+        return fail(ctx, F4LA_ERR_ARG, "cf_bytes must be 1, 2 or 4");
+    r->dims = *in;
+    r->nnz = n ? in->row_ptr[n] : 0;
+    r->ncoef = in->ncf ? in->cf_ptr[in->ncf] : 0;
+    CU(cudaMalloc(&r->row_ptr, (n + 1) * 8));
+    CU(cudaMalloc(&r->cols, (r->nnz + 1) * 4));
+    CU(cudaMalloc(&r->row_cf, (n + 1) * 4));
+    CU(cudaMalloc(&r->cf_ptr, ((uint64_t)in->ncf + 1) * 8));
+    CU(cudaMalloc(&r->cf, (r->ncoef + 1) * in->cf_bytes));
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(r->row_ptr, in->row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (r->nnz) CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(r->row_cf, in->row_cf, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(r->cf_ptr, in->cf_ptr, ((uint64_t)in->ncf + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (r->ncoef) CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
+    r->bytes = (n + 1) * 8 + r->nnz * 4 + n * 4 + ((uint64_t)in->ncf + 1) * 8 + r->ncoef * in->cf_bytes;
+    return F4LA_OK;
+}
+
+void release_resident(f4la_resident *r)
+{
+    if (!r) return;
+    cudaFree(r->row_ptr); cudaFree(r->cols); cudaFree(r->row_cf); cudaFree(r->cf_ptr); cudaFree(r->cf);
+    delete r;
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ */
+/* C ABI                                                               */
+/* ------------------------------------------------------------------ */
+
+extern "C" {
+
+const char *f4la_b200_version(void) { return "f4la_b200 0.1.0 (sm_100a)"; }
+
+int f4la_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+f4la_ctx *f4la_b200_create(int device)
+{
+    int n = f4la_b200_device_count();
+    if (n <= 0) {
+        fprintf(stderr, "[f4la_b200] no CUDA device available; this library has no CPU fallback\n");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fprintf(stderr, "[f4la_b200] device %d out of range (0..%d)\n", device, n - 1);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        fprintf(stderr, "[f4la_b200] device %d is not an sm_100 class GPU (found sm_%d%d); kernels are built "
+                        "for sm_100a only\n", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    f4la_ctx *ctx = new f4la_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    return ctx;
+}
+
+void f4la_b200_destroy(f4la_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
+                      &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
+                      &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out};
+    for (auto b : bufs) free_dev(*b);
+    if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
+    if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
+    for (auto &e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *f4la_b200_last_error(const f4la_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+void *f4la_b200_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void f4la_b200_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in)
+{
+    if (!ctx || !in) return nullptr;
+    cudaSetDevice(ctx->device);
+    f4la_resident *r = new f4la_resident();
+    if (upload(ctx, in, r) != F4LA_OK) { release_resident(r); return nullptr; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { release_resident(r); return nullptr; }
+    return r;
+}
+
+void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m)
+{
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    release_resident(m);
+}
+
+int f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m, f4la_flat_result *out, f4la_stats *stats)
+{
+    if (!ctx || !m || !out) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const double t0 = now_ms();
+    int rc = run_pipeline(ctx, m, out, stats);
+    if (stats) stats->ms_total = now_ms() - t0;
+    return rc;
+}
+
+int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result *out, f4la_stats *stats)
+{
+    if (!ctx || !in || !out) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const double t0 = now_ms();
+    f4la_resident *r = new f4la_resident();
+    int rc = upload(ctx, in, r);
+    if (rc == F4LA_OK) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, F4LA_ERR_CUDA, "upload failed");
+    }
+    const double t1 = now_ms();
+    if (rc == F4LA_OK) rc = run_pipeline(ctx, r, out, stats);
+    if (stats) {
+        stats->ms_h2d = t1 - t0;
+        stats->bytes_h2d = r->bytes;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    release_resident(r);
+    if (stats) stats->ms_total = now_ms() - t0;
+    return rc;
+}
+
+void f4la_b200_free_result(f4la_flat_result *res)
+{
+    if (!res) return;
+    free(res->row_ptr); free(res->cols); free(res->cf); free(res->src_row);
+    memset(res, 0, sizeof(*res));
+}
+
+} /* extern "C" */

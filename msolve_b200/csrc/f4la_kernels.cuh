@@ -1,0 +1,553 @@
+/* f4la_kernels.cuh -- sm_100a kernels of the F4 GF(p) linear algebra.
+ *
+ * Device algorithm (see DESIGN.md for the derivation and the roofline):
+ *
+ *   The reference reduces every lower row r by the known pivots with a
+ *   left-to-right chain of sparse AXPYs into a dense int64 accumulator
+ *   (reference src/neogb/la_ff_32.c:965-1242, driven by :2637-2698).  The
+ *   multiplier of pivot i in row r, m[r][i], and the remainder of row r in the
+ *   non-pivot columns, D'[r][:], satisfy
+ *
+ *        V[j][r] = X[r][j] - sum_{i<j, a_ij != 0} a_ij * V[i][r]        (*)
+ *
+ *   where X = [C D] are the lower rows, a_ij the entries of the (unit upper
+ *   triangular) pivot rows, V[j] = m[:,j] for j < ncl and V[j] = D'[:,j-ncl]
+ *   for j >= ncl.  (*) is a sparse triangular solve with nrl right-hand
+ *   sides.  We run it TRANSPOSED: V[j] is a dense vector over the lower rows,
+ *   a column j pulls the vectors of its source pivots (CSC of the pivot
+ *   rows), so every memory access is a coalesced dense vector load, there is
+ *   no scatter and no atomics in the hot loop.  Columns are level-scheduled
+ *   (level[j] = 1 + max level of its sources).  The lower rows are split into
+ *   chunks of 128*T rows so that the V block of the chunks in flight stays
+ *   L2-resident (126 MB on B200).
+ *
+ *   The Schur complement D' (ncr x nrl, column major) is then brought to
+ *   reduced row echelon form by Gauss-Jordan elimination (trailing block,
+ *   reference la_ff_32.c:3390-3500 + :3354-3388 compute the same unique RREF).
+ *
+ * Arithmetic is exact: residues are kept canonical in [0,p) as uint32, sums of
+ * products are accumulated in uint64 with the coefficient split in two 16-bit
+ * halves (v * c_lo < 2^47, v * c_hi < 2^46: 2^16 terms cannot overflow), and
+ * reduced with a Barrett step (floor(2^64/p)) once per column.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace f4la {
+
+constexpr int kSolveThreads   = 256;   /* 8 warps */
+constexpr int kWarpsPerBlock  = kSolveThreads / 32;
+constexpr int kRowsPerT       = 128;   /* rows covered by one uint4 per lane */
+constexpr int kMaxT           = 4;     /* chunk = 128*T rows, T in 1..4      */
+constexpr uint32_t kFoldEvery = 1u << 15; /* entries between overflow folds  */
+constexpr uint32_t kLongColumn = 48;   /* >= this many entries: one CTA/col  */
+
+/* x mod p for any 64-bit x, pinv = floor((2^64-1)/p).  The quotient estimate
+ * is short by at most 2, the loop repairs it. */
+__device__ __forceinline__ uint32_t mod_u64(uint64_t x, uint32_t p, uint64_t pinv)
+{
+    const uint64_t q = __umul64hi(x, pinv);
+    uint64_t r = x - q * (uint64_t)p;
+    while (r >= p) r -= p;
+    return (uint32_t)r;
+}
+
+__device__ __forceinline__ uint32_t mulmod(uint32_t a, uint32_t b, uint32_t p, uint64_t pinv)
+{
+    return mod_u64((uint64_t)a * b, p, pinv);
+}
+
+/* Modular inverse by extended Euclid (same recurrence as the reference's
+ * mod_p_inverse_32, tools.h:95-122). */
+__device__ __forceinline__ uint32_t modinv(uint32_t val, uint32_t p)
+{
+    int64_t a = p, b = val % p, c = 1, d = 0;
+    while (b != 0) {
+        const int64_t e = a / b;
+        int64_t f = b; b = a - e * f; a = f;
+        f = c; c = d - e * f; d = f;
+    }
+    if (d < 0) d += p;
+    return (uint32_t)d;
+}
+
+__device__ __forceinline__ uint32_t load_cf(const void *cf, uint32_t cf_bytes, uint64_t idx)
+{
+    if (cf_bytes == 4) return ((const uint32_t *)cf)[idx];
+    if (cf_bytes == 2) return ((const uint16_t *)cf)[idx];
+    return ((const uint8_t *)cf)[idx];
+}
+
+/* ------------------------------------------------------------------ */
+/* layout kernels                                                      */
+/* ------------------------------------------------------------------ */
+
+/* error bits written by the layout kernels */
+constexpr uint32_t kErrLeadNotFirst  = 1u;  /* pivot row i does not start with column i */
+constexpr uint32_t kErrNotTriangular = 2u;  /* pivot entry left of / on its lead        */
+constexpr uint32_t kErrColumnRange   = 4u;  /* column id >= nc                          */
+constexpr uint32_t kErrLeadNotOne    = 8u;  /* pivot row not monic                      */
+
+/* Pass 1 over the pivot rows: histogram of the target columns of all
+ * non-lead entries.  One warp per pivot row. */
+__global__ void k_pull_count(const uint64_t *__restrict__ row_ptr,
+                             const uint32_t *__restrict__ cols,
+                             const uint32_t *__restrict__ row_cf,
+                             const uint64_t *__restrict__ cf_ptr,
+                             const void *__restrict__ cf, uint32_t cf_bytes,
+                             uint32_t nru, uint32_t ncl, uint32_t nc,
+                             uint32_t *__restrict__ col_cnt, uint32_t *__restrict__ err)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < nru; i += nwarps) {
+        const uint64_t a = row_ptr[i], b = row_ptr[i + 1];
+        if (lane == 0) {
+            if (b == a || cols[a] != i) atomicOr(err, kErrLeadNotFirst);
+            else if (load_cf(cf, cf_bytes, cf_ptr[row_cf[i]]) != 1) atomicOr(err, kErrLeadNotOne);
+        }
+        for (uint64_t k = a + 1 + lane; k < b; k += 32) {
+            const uint32_t j = cols[k];
+            if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
+            if (j <= i)  { atomicOr(err, kErrNotTriangular); continue; }
+            atomicAdd(&col_cnt[j], 1u);
+        }
+    }
+}
+
+/* Exclusive prefix sum of n counters into out[0..n] (out[n] = total), one
+ * block.  n is at most a few 10^5, this is not a hot kernel. */
+__global__ void k_exclusive_scan(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint32_t s = 0;
+    for (uint32_t k = lo; k < hi; ++k) s += in[k];
+    part[t] = s;
+    __syncthreads();
+    for (uint32_t off = 1; off < nt; off <<= 1) {
+        const uint32_t v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (uint32_t k = lo; k < hi; ++k) { const uint32_t c = in[k]; out[k] = run; run += c; }
+    if (t == nt - 1) out[n] = part[t];
+}
+
+/* Pass 2: fill the pull lists.  Entry = { source pivot i, p - a_ij }. */
+__global__ void k_pull_fill(const uint64_t *__restrict__ row_ptr,
+                            const uint32_t *__restrict__ cols,
+                            const uint32_t *__restrict__ row_cf,
+                            const uint64_t *__restrict__ cf_ptr,
+                            const void *__restrict__ cf, uint32_t cf_bytes,
+                            uint32_t nru, uint32_t nc, uint32_t p,
+                            const uint32_t *__restrict__ col_ptr,
+                            uint32_t *__restrict__ cursor, uint2 *__restrict__ ent)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < nru; i += nwarps) {
+        const uint64_t a = row_ptr[i], b = row_ptr[i + 1];
+        const uint64_t c0 = cf_ptr[row_cf[i]];
+        for (uint64_t k = a + 1 + lane; k < b; k += 32) {
+            const uint32_t j = cols[k];
+            if (j >= nc || j <= i) continue;
+            const uint32_t v = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
+            const uint32_t pos = col_ptr[j] + atomicAdd(&cursor[j], 1u);
+            ent[pos] = make_uint2(i, v == 0 ? 0u : p - v);
+        }
+    }
+}
+
+/* Level relaxation, in place and monotone: level[j] = max(level[j],
+ * 1 + max_i level[src]).  Converges to the longest-path levels. */
+__global__ void k_level_relax(const uint32_t *__restrict__ col_ptr, const uint2 *__restrict__ ent,
+                              uint32_t ncl, uint32_t *level, uint32_t *__restrict__ changed)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = warp; j < ncl; j += nwarps) {
+        const uint32_t a = col_ptr[j], b = col_ptr[j + 1];
+        uint32_t m = 0;
+        for (uint32_t k = a + lane; k < b; k += 32) {
+            const uint32_t l = ((volatile uint32_t *)level)[ent[k].x] + 1;
+            m = max(m, l);
+        }
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > level[j]) { level[j] = m; *changed = 1; }
+    }
+}
+
+/* Histogram of (level, long/short) classes: slot = 2*level + (short ? 1 : 0). */
+__global__ void k_level_count(const uint32_t *__restrict__ level, const uint32_t *__restrict__ col_ptr,
+                              uint32_t ncl, uint32_t *__restrict__ slot_cnt, uint32_t *__restrict__ max_level)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncl) return;
+    const uint32_t len = col_ptr[j + 1] - col_ptr[j];
+    atomicAdd(&slot_cnt[2 * level[j] + (len >= kLongColumn ? 0 : 1)], 1u);
+    atomicMax(max_level, level[j]);
+}
+
+__global__ void k_level_fill(const uint32_t *__restrict__ level, const uint32_t *__restrict__ col_ptr,
+                             uint32_t ncl, const uint32_t *__restrict__ slot_ptr,
+                             uint32_t *__restrict__ cursor, uint32_t *__restrict__ order)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncl) return;
+    const uint32_t len = col_ptr[j + 1] - col_ptr[j];
+    const uint32_t s = 2 * level[j] + (len >= kLongColumn ? 0 : 1);
+    order[slot_ptr[s] + atomicAdd(&cursor[s], 1u)] = j;
+}
+
+/* Scatter the lower rows of the chunks [chunk0, chunk0+nchunks) into V.
+ * V layout: [chunk][column][Rc].  One warp per lower row. */
+__global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
+                                const uint32_t *__restrict__ cols,
+                                const uint32_t *__restrict__ row_cf,
+                                const uint64_t *__restrict__ cf_ptr,
+                                const void *__restrict__ cf, uint32_t cf_bytes,
+                                uint32_t nru, uint32_t nrl, uint32_t nc, uint32_t p,
+                                uint32_t chunk0, uint32_t nchunks, uint32_t Rc,
+                                uint32_t *__restrict__ V, uint32_t *__restrict__ err)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t r0 = chunk0 * Rc;
+    const uint32_t r1 = min(nrl, (chunk0 + nchunks) * Rc);
+    for (uint32_t r = r0 + warp; r < r1; r += nwarps) {
+        const uint64_t a = row_ptr[nru + r], b = row_ptr[nru + r + 1];
+        const uint64_t c0 = cf_ptr[row_cf[nru + r]];
+        const uint32_t lc = (r - r0) / Rc, lr = (r - r0) % Rc;
+        uint32_t *Vc = V + (size_t)lc * nc * Rc;
+        for (uint64_t k = a + lane; k < b; k += 32) {
+            const uint32_t j = cols[k];
+            if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
+            Vc[(size_t)j * Rc + lr] = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* the hot kernel: pull-solve of a set of columns                      */
+/* ------------------------------------------------------------------ */
+
+struct SolveArgs {
+    const uint32_t *col_ptr;   /* pull lists                                  */
+    const uint2    *ent;
+    uint32_t       *V;         /* [nchunks][nc][Rc] of the chunk group        */
+    uint32_t        nc;
+    uint32_t        Rc;        /* 128*T                                       */
+    const uint32_t *long_cols; /* columns solved by a whole CTA               */
+    uint32_t        n_long;
+    const uint32_t *short_cols;/* columns solved by one warp each             */
+    uint32_t        n_short;
+    uint32_t        col_base;  /* when the lists are NULL: columns col_base+k */
+    uint32_t       *out;       /* != NULL: results go to out instead of V     */
+    uint64_t        out_ld;    /* out[(j-out_col0)*out_ld + chunk*Rc + row]   */
+    uint32_t        out_col0;
+    uint32_t        chunk0;    /* first chunk of the group (for out)          */
+    uint32_t        p;
+    uint64_t        pinv;
+};
+
+/* Accumulate entries [e0,e1) with stride `step` of column j into acc.
+ * Lane owns rows 4*lane + 128*t + {0,1,2,3}. */
+template <int T, bool WIDE>
+__device__ __forceinline__ void pull_accumulate(const SolveArgs &A, const uint32_t *__restrict__ Vc,
+                                                uint32_t e0, uint32_t e1, uint32_t step, uint32_t lane,
+                                                uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
+{
+    constexpr int U = (T <= 2) ? 4 : 2;       /* entries in flight per warp */
+    const uint2 *__restrict__ ent = A.ent;
+    const uint32_t Rc = A.Rc;
+    uint32_t since_fold = 0;
+    uint32_t e = e0;
+    for (; e + (U - 1) * step < e1; e += U * step) {
+        uint2 en[U];
+        uint4 v[U][T];
+#pragma unroll
+        for (int u = 0; u < U; ++u) en[u] = __ldg(&ent[e + u * step]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(Vc + (size_t)en[u].x * Rc) + lane;
+#pragma unroll
+            for (int t = 0; t < T; ++t) v[u][t] = src[t * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t cl = WIDE ? (en[u].y & 0xffffu) : en[u].y;
+            const uint32_t ch = en[u].y >> 16;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                lo[t][0] += (uint64_t)v[u][t].x * cl; lo[t][1] += (uint64_t)v[u][t].y * cl;
+                lo[t][2] += (uint64_t)v[u][t].z * cl; lo[t][3] += (uint64_t)v[u][t].w * cl;
+                if (WIDE) {
+                    hi[t][0] += (uint64_t)v[u][t].x * ch; hi[t][1] += (uint64_t)v[u][t].y * ch;
+                    hi[t][2] += (uint64_t)v[u][t].z * ch; hi[t][3] += (uint64_t)v[u][t].w * ch;
+                }
+            }
+        }
+        since_fold += U;
+        if (since_fold >= kFoldEvery) {
+            since_fold = 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
+                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
+                }
+        }
+    }
+    for (; e < e1; e += step) {               /* tail, < U entries */
+        const uint2 en = __ldg(&ent[e]);
+        const uint4 *src = reinterpret_cast<const uint4 *>(Vc + (size_t)en.x * Rc) + lane;
+        const uint32_t cl = WIDE ? (en.y & 0xffffu) : en.y;
+        const uint32_t ch = en.y >> 16;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint4 v = src[t * 32];
+            lo[t][0] += (uint64_t)v.x * cl; lo[t][1] += (uint64_t)v.y * cl;
+            lo[t][2] += (uint64_t)v.z * cl; lo[t][3] += (uint64_t)v.w * cl;
+            if (WIDE) {
+                hi[t][0] += (uint64_t)v.x * ch; hi[t][1] += (uint64_t)v.y * ch;
+                hi[t][2] += (uint64_t)v.z * ch; hi[t][3] += (uint64_t)v.w * ch;
+            }
+        }
+    }
+}
+
+/* canonical residue of lo + 2^16 * hi */
+template <bool WIDE>
+__device__ __forceinline__ uint32_t fold_lohi(uint64_t lo, uint64_t hi, uint32_t p, uint64_t pinv)
+{
+    uint64_t x = mod_u64(lo, p, pinv);
+    if (WIDE) x += (uint64_t)mod_u64(hi, p, pinv) << 16;
+    return mod_u64(x, p, pinv);
+}
+
+template <int T, bool WIDE>
+__global__ void __launch_bounds__(kSolveThreads)
+k_pull_solve(const SolveArgs A)
+{
+    __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];   /* long columns only */
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.y;
+    uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
+    const bool is_long = blockIdx.x < A.n_long;
+
+    uint32_t j;
+    if (is_long) {
+        j = A.long_cols ? A.long_cols[blockIdx.x] : A.col_base + blockIdx.x;
+    } else {
+        const uint32_t k = (blockIdx.x - A.n_long) * kWarpsPerBlock + warp;
+        if (k >= A.n_short) return;
+        j = A.short_cols ? A.short_cols[k] : A.col_base + A.n_long + k;
+    }
+    const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
+
+    uint64_t lo[T][4], hi[T][4];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lo[t][k] = 0; hi[t][k] = 0; }
+
+    uint32_t *dst = A.out ? A.out + (size_t)(j - A.out_col0) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
+                          : Vc + (size_t)j * A.Rc;
+    const uint4 *init = reinterpret_cast<const uint4 *>(Vc + (size_t)j * A.Rc) + lane;
+
+    if (!is_long) {
+        pull_accumulate<T, WIDE>(A, Vc, e0, e1, 1, lane, lo, hi);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint4 x = init[t * 32];
+            uint4 r;
+            r.x = fold_lohi<WIDE>(lo[t][0] + x.x, hi[t][0], A.p, A.pinv);
+            r.y = fold_lohi<WIDE>(lo[t][1] + x.y, hi[t][1], A.p, A.pinv);
+            r.z = fold_lohi<WIDE>(lo[t][2] + x.z, hi[t][2], A.p, A.pinv);
+            r.w = fold_lohi<WIDE>(lo[t][3] + x.w, hi[t][3], A.p, A.pinv);
+            reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
+        }
+        return;
+    }
+
+    /* long column: the 8 warps take interleaved entries, then reduce */
+    pull_accumulate<T, WIDE>(A, Vc, e0 + warp, e1, kWarpsPerBlock, lane, lo, hi);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        uint4 r;
+        r.x = fold_lohi<WIDE>(lo[t][0], hi[t][0], A.p, A.pinv);
+        r.y = fold_lohi<WIDE>(lo[t][1], hi[t][1], A.p, A.pinv);
+        r.z = fold_lohi<WIDE>(lo[t][2], hi[t][2], A.p, A.pinv);
+        r.w = fold_lohi<WIDE>(lo[t][3], hi[t][3], A.p, A.pinv);
+        reinterpret_cast<uint4 *>(&part[warp][t * kRowsPerT])[lane] = r;
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < (uint32_t)(T * kRowsPerT); r += kSolveThreads) {
+        uint64_t s = Vc[(size_t)j * A.Rc + r];
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w][r];
+        dst[r] = mod_u64(s, A.p, A.pinv);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* trailing block: Gauss-Jordan on D' (column major, ld rows per col)   */
+/* ------------------------------------------------------------------ */
+
+struct GEState {
+    uint32_t next_col;   /* first column not yet examined                    */
+    uint32_t rank;
+    uint32_t done;
+    uint32_t cur_col;    /* pivot of the current elimination step            */
+    uint32_t cur_row;
+    uint32_t cur_inv;
+    uint32_t active;     /* 1 when cur_* describe a pivot to be eliminated   */
+    uint32_t pad;
+};
+
+/* colflag[c] = 1 iff column c has a non-zero entry in a row that is not a
+ * pivot row yet.  Initially: any non-zero. */
+__global__ void k_ge_init_flags(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows,
+                                uint32_t ncr, uint8_t *__restrict__ colflag)
+{
+    const uint32_t c = blockIdx.x;
+    if (c >= ncr) return;
+    int any = 0;
+    for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) any |= D[(size_t)c * ld + r] != 0;
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) colflag[c] = (uint8_t)(any != 0);
+}
+
+/* Next pivot: first flagged column >= next_col, in it the first row that is
+ * not yet a pivot row and non-zero.  One block. */
+__global__ void k_ge_find(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t ncr,
+                          const uint8_t *__restrict__ colflag, uint8_t *__restrict__ used,
+                          uint8_t *__restrict__ ispiv, GEState *st,
+                          uint32_t *__restrict__ pivcol, uint32_t *__restrict__ pivrow,
+                          uint32_t *__restrict__ pivinv, uint32_t p)
+{
+    __shared__ uint32_t s_min;
+    if (st->done) return;
+    uint32_t c = st->next_col;
+    __syncthreads();                      /* everybody has read the state */
+    for (;;) {
+        /* first flagged column at or after c */
+        uint32_t cand = 0xffffffffu;
+        for (uint32_t base = c; base < ncr; base += blockDim.x) {
+            const uint32_t k = base + threadIdx.x;
+            const int hit = k < ncr && colflag[k];
+            if (threadIdx.x == 0) s_min = 0xffffffffu;
+            __syncthreads();
+            if (hit) atomicMin(&s_min, k);
+            __syncthreads();
+            cand = s_min;
+            __syncthreads();
+            if (cand != 0xffffffffu) break;
+        }
+        if (cand == 0xffffffffu) {
+            if (threadIdx.x == 0) { st->done = 1; st->active = 0; st->next_col = ncr; }
+            return;
+        }
+        c = cand;
+        if (threadIdx.x == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x)
+            if (!used[r] && D[(size_t)c * ld + r] != 0) { atomicMin(&s_min, r); break; }
+        __syncthreads();
+        const uint32_t piv = s_min;
+        __syncthreads();
+        if (piv != 0xffffffffu) {
+            if (threadIdx.x == 0) {
+                const uint32_t k = st->rank;
+                const uint32_t inv = modinv(D[(size_t)c * ld + piv], p);
+                pivcol[k] = c; pivrow[k] = piv; pivinv[k] = inv;
+                used[piv] = 1; ispiv[c] = 1;
+                st->rank = k + 1; st->cur_col = c; st->cur_row = piv; st->cur_inv = inv;
+                st->active = 1; st->next_col = c + 1;
+            }
+            return;
+        }
+        c = c + 1;                        /* stale flag (cannot happen, but be safe) */
+    }
+}
+
+/* Eliminate the current pivot from every other row, columns right of it.
+ * One block per column.  Also refreshes colflag for the touched columns. */
+__global__ void k_ge_eliminate(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t ncr,
+                               uint8_t *__restrict__ colflag, const uint8_t *__restrict__ used,
+                               const GEState *__restrict__ st, uint32_t p, uint64_t pinv)
+{
+    if (st->done || !st->active) return;
+    const uint32_t c = st->cur_col, piv = st->cur_row;
+    const uint32_t cc = blockIdx.x;
+    if (cc <= c || cc >= ncr) return;
+    uint32_t *col = D + (size_t)cc * ld;
+    const uint32_t *fcol = D + (size_t)c * ld;
+    const uint32_t s = mulmod(col[piv], st->cur_inv, p, pinv);
+    if (s == 0) return;                   /* column untouched, flag still valid */
+    int any = 0;
+    for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
+        uint32_t v = col[r];
+        if (r != piv) {
+            const uint32_t f = fcol[r];
+            if (f) {
+                const uint32_t t = mulmod(f, s, p, pinv);
+                v = v >= t ? v - t : v + p - t;
+                col[r] = v;
+            }
+            any |= (v != 0) && !used[r];
+        }
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) colflag[cc] = (uint8_t)(any != 0);
+}
+
+/* Reduced echelon rows, dense: row t = pivot rank-1-t (decreasing lead). */
+__global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t rank,
+                             const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,
+                             const uint32_t *__restrict__ pivinv, const uint8_t *__restrict__ ispiv,
+                             uint32_t *__restrict__ out, uint32_t p, uint64_t pinv)
+{
+    const uint32_t t = blockIdx.y;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rank || c >= ncr) return;
+    const uint32_t k = rank - 1 - t;
+    const uint32_t ck = pivcol[k];
+    uint32_t v;
+    if (c < ck) v = 0;
+    else if (c == ck) v = 1;
+    else if (ispiv[c]) v = 0;
+    else v = mulmod(D[(size_t)c * ld + pivrow[k]], pivinv[k], p, pinv);
+    out[(size_t)t * ncr + c] = v;
+}
+
+/* Normal-form mode: row r of D' as is (no elimination). */
+__global__ void k_transpose_rows(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t nrows,
+                                 uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t tile[32][33];
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+    for (uint32_t k = ty; k < 32; k += blockDim.y) {
+        const uint32_t c = c0 + k, r = r0 + tx;
+        tile[k][tx] = (c < ncr && r < nrows) ? D[(size_t)c * ld + r] : 0;
+    }
+    __syncthreads();
+    for (uint32_t k = ty; k < 32; k += blockDim.y) {
+        const uint32_t r = r0 + k, c = c0 + tx;
+        if (r < nrows && c < ncr) out[(size_t)r * ncr + c] = tile[tx][k];
+    }
+}
+
+} /* namespace f4la */

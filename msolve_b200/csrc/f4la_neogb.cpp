@@ -1,0 +1,277 @@
+/* f4la_neogb.cpp -- neogb-level drop-in entry points (include/f4la_b200_neogb.h).
+ *
+ * Mirrors the wrapper + body pair exact_sparse_linear_algebra_ff_32 /
+ * exact_sparse_reduced_echelon_form_ff_32 of the reference
+ * (src/neogb/la_ff_32.c:3961-3990 and :2595-2770; 16/8-bit twins in
+ * la_ff_16.c:2011/1046, la_ff_8.c:2203/1319) on the host side:
+ *   - same inputs consumed (every tr[i] and rr[i] is free()d, :2666/:2718-2721),
+ *   - same outputs produced (individually malloc()ed rows with the 6-word
+ *     prelude and individually malloc()ed coefficient arrays, :1223-1240;
+ *     rows by decreasing lead column, :2732-2762),
+ *   - same side channels (st->np, mat->np/nr/sz, num_zerored, la_ctime,
+ *     la_rtime, the info_level > 1 print, :3968-3989).
+ * The arithmetic happens on the GPU (f4la_device.cu); there is no CPU path.
+ */
+#include <sys/time.h>
+#include <time.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "f4la_b200.h"
+#include "f4la_b200_neogb.h"
+
+namespace {
+
+f4la_neogb_layout L;
+bool g_configured = false;
+
+struct ThreadState {
+    f4la_ctx *ctx = nullptr;
+    int device = -1;
+    /* pinned staging for the flat matrix (grow-only) */
+    void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[5] = {0, 0, 0, 0, 0};
+    f4la_neogb_totals tot = {};
+    ~ThreadState()
+    {
+        for (auto &b : buf) if (b) f4la_b200_pinned_free(b);
+        if (ctx) f4la_b200_destroy(ctx);
+    }
+};
+
+thread_local ThreadState T;
+
+template <typename V> V &fld(void *base, uint32_t off) { return *reinterpret_cast<V *>((char *)base + off); }
+template <typename V> const V &fld(const void *base, uint32_t off) { return *reinterpret_cast<const V *>((const char *)base + off); }
+
+double wall_s() { struct timeval t; gettimeofday(&t, nullptr); return t.tv_sec + 1e-6 * t.tv_usec; }
+double cpu_s() { return (double)clock() / CLOCKS_PER_SEC; }
+double now_ms()
+{
+    using clk = std::chrono::steady_clock;
+    return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count();
+}
+
+[[noreturn]] void die(const char *msg)
+{
+    fprintf(stderr, "[f4la_b200] fatal: %s\n", msg);
+    exit(1);                       /* same style as the reference, f4.c:828-830 */
+}
+
+void *stage(int k, size_t bytes)
+{
+    if (bytes > T.cap[k]) {
+        if (T.buf[k]) f4la_b200_pinned_free(T.buf[k]);
+        size_t want = bytes + bytes / 2 + 4096;
+        T.buf[k] = f4la_b200_pinned_alloc(want);
+        if (!T.buf[k]) die("pinned host allocation failed");
+        T.cap[k] = want;
+    }
+    return T.buf[k];
+}
+
+f4la_ctx *ctx()
+{
+    if (!T.ctx) {
+        if (T.device < 0) {
+            const char *e = getenv("F4LA_B200_DEVICE");
+            T.device = e ? atoi(e) : 0;
+        }
+        T.ctx = f4la_b200_create(T.device);
+        if (!T.ctx) die("no usable B200 device for the linear algebra backend (there is no CPU fallback)");
+    }
+    return T.ctx;
+}
+
+/* Echelon form of mat->tr modulo mat->rr; the body shared by both pointers. */
+void echelon(void *mat, const void *tbr, const void *bs, void *st)
+{
+    if (!g_configured) die("f4la_b200_neogb_configure() was not called");
+    const double ct0 = cpu_s(), rt0 = wall_s();
+    const double t_begin = now_ms();
+
+    const int32_t ff_bits = fld<int32_t>(st, L.md_ff_bits);
+    const uint32_t fc = fld<uint32_t>(st, L.md_fc);
+    const int32_t trace_level = fld<int32_t>(st, L.md_trace_level);
+    const uint32_t w = ff_bits == 8 ? 1 : ff_bits == 16 ? 2 : 4;
+    if (ff_bits != 8 && ff_bits != 16 && ff_bits != 32) die("unsupported field (ff_bits must be 8, 16 or 32)");
+    if (fld<int32_t>(st, L.md_nf) > 0 || fld<int32_t>(st, L.md_in_final_reduction_step))
+        die("normal-form / final-reduction mode is not served by this backend yet: leave exact_linear_algebra "
+            "on the reference's dispatcher");
+    if (trace_level == 1 /* LEARN_TRACER */)
+        die("LEARN_TRACER is not served by this backend yet");
+
+    const uint32_t nru = fld<uint32_t>(mat, L.mat_nru), nrl = fld<uint32_t>(mat, L.mat_nrl);
+    const uint32_t ncl = fld<uint32_t>(mat, L.mat_ncl), ncr = fld<uint32_t>(mat, L.mat_ncr);
+    uint32_t **rr = fld<uint32_t **>(mat, L.mat_rr);
+    uint32_t **tr = fld<uint32_t **>(mat, L.mat_tr);
+    const uint32_t n = nru + nrl;
+    const uint32_t cf_off = w == 1 ? L.mat_cf_8 : w == 2 ? L.mat_cf_16 : L.mat_cf_32;
+    const uint32_t bcf_off = w == 1 ? L.bs_cf_8 : w == 2 ? L.bs_cf_16 : L.bs_cf_32;
+
+    /* la_ff_32.c:3975: room for one coefficient array pointer per row */
+    void **&mcf = fld<void **>(mat, cf_off);
+    mcf = (void **)realloc(mcf, (size_t)fld<uint32_t>(mat, L.mat_nr) * sizeof(void *));
+
+    /* ---- flatten into pinned staging ---- */
+    uint64_t *row_ptr = (uint64_t *)stage(0, ((size_t)n + 1) * 8);
+    uint32_t *row_cf = (uint32_t *)stage(2, ((size_t)n + 1) * 4);
+    uint64_t nnz = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+        row_ptr[r] = nnz; nnz += row[L.row_length];
+    }
+    row_ptr[n] = nnz;
+    uint32_t *cols = (uint32_t *)stage(1, (nnz + 1) * 4);
+    void *const *bs_cf = fld<void *const *>(bs, bcf_off);
+    void *const *tbr_cf = fld<void *const *>(tbr, bcf_off);
+    const uint32_t bs_ld = fld<uint32_t>(bs, L.bs_ld), tbr_ld = fld<uint32_t>(tbr, L.bs_ld);
+    std::vector<int32_t> map_bs(bs_ld + 1, -1), map_tbr_v;
+    if (tbr != bs) map_tbr_v.assign(tbr_ld + 1, -1);
+    std::vector<int32_t> &map_tbr = (tbr == bs) ? map_bs : map_tbr_v;
+    std::vector<const void *> cfsrc; cfsrc.reserve(1024);
+    std::vector<uint64_t> cfp; cfp.reserve(1025);
+    std::vector<uint32_t> src_bindex(nrl), src_mult(nrl);
+    uint64_t ncoef = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+        const uint32_t len = row[L.row_length];
+        memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)len * 4);
+        std::vector<int32_t> &map = r < nru ? map_bs : map_tbr;
+        const uint32_t ci = row[L.row_coeffs];
+        if ((size_t)ci >= map.size()) die("row refers to a coefficient array beyond the basis load");
+        if (map[ci] < 0) {
+            map[ci] = (int32_t)cfsrc.size();
+            cfp.push_back(ncoef);
+            cfsrc.push_back((r < nru ? bs_cf : tbr_cf)[ci]);
+            ncoef += len;
+        }
+        row_cf[r] = (uint32_t)map[ci];
+        if (r >= nru) { src_bindex[r - nru] = row[L.row_bindex]; src_mult[r - nru] = row[L.row_mult]; }
+    }
+    cfp.push_back(ncoef);
+    const uint32_t ncf = (uint32_t)cfsrc.size();
+    uint64_t *cf_ptr = (uint64_t *)stage(3, ((size_t)ncf + 1) * 8);
+    memcpy(cf_ptr, cfp.data(), ((size_t)ncf + 1) * 8);
+    unsigned char *pool = (unsigned char *)stage(4, (ncoef + 1) * w);
+    for (uint32_t c = 0; c < ncf; ++c)
+        memcpy(pool + cfp[c] * w, cfsrc[c], (size_t)(cfp[c + 1] - cfp[c]) * w);
+
+    f4la_flat_matrix fm;
+    memset(&fm, 0, sizeof(fm));
+    fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
+    fm.flags = F4LA_FLAG_NONE;
+    fm.row_ptr = row_ptr; fm.cols = cols; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = pool;
+    const double t_flat = now_ms();
+
+    /* ---- device ---- */
+    f4la_flat_result res;
+    f4la_stats stats;
+    const int rc = f4la_b200_reduce(ctx(), &fm, &res, &stats);
+    if (rc != F4LA_OK) die(f4la_b200_last_error(ctx()));
+    const double t_dev = now_ms();
+
+    /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
+    for (uint32_t i = 0; i < nrl; ++i) { free(tr[i]); tr[i] = nullptr; }
+    for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
+
+    uint32_t np = res.nrows;
+    if (trace_level == 2 /* APPLY_TRACER */ && np != nrl) {
+        /* a row reduced to zero while applying the tracer: bad prime
+         * (la_ff_32.c:2679-2683, 2700-2709) */
+        np = 0;
+        if (fld<int32_t>(st, L.md_info_level) > 0)
+            fprintf(stderr, "Zero reduction while applying tracer, bad prime.\n");
+        fld<uint32_t>(mat, L.mat_np) = 0;
+        f4la_b200_free_result(&res);
+    } else {
+        /* ---- materialise the new pivots as neogb rows (la_ff_32.c:1223-1240) ---- */
+        tr = (uint32_t **)realloc(tr, (size_t)(np ? np : 1) * sizeof(uint32_t *));
+        fld<uint32_t **>(mat, L.mat_tr) = tr;
+        for (uint32_t t = 0; t < np; ++t) {
+            const uint64_t a = res.row_ptr[t];
+            const uint32_t len = (uint32_t)(res.row_ptr[t + 1] - a);
+            uint32_t *row = (uint32_t *)malloc(((size_t)len + L.row_offset) * sizeof(uint32_t));
+            void *cf = malloc((size_t)(len ? len : 1) * w);
+            memcpy(row + L.row_offset, res.cols + a, (size_t)len * 4);
+            memcpy(cf, (unsigned char *)res.cf + a * w, (size_t)len * w);
+            const uint32_t src = res.src_row[t];
+            row[L.row_deg] = 0;
+            row[L.row_bindex] = src_bindex[src];
+            row[L.row_mult] = src_mult[src];
+            row[L.row_coeffs] = t;
+            row[L.row_preloop] = len % L.unroll;
+            row[L.row_length] = len;
+            mcf[t] = cf;
+            tr[t] = row;
+        }
+        f4la_b200_free_result(&res);
+        fld<uint32_t>(st, L.md_np) = np;
+        fld<uint32_t>(mat, L.mat_np) = np;
+        fld<uint32_t>(mat, L.mat_nr) = np;
+        fld<uint32_t>(mat, L.mat_sz) = np;
+    }
+    const double t_end = now_ms();
+
+    /* ---- side channels of the wrapper (la_ff_32.c:3978-3989) ---- */
+    fld<double>(st, L.md_la_ctime) += cpu_s() - ct0;
+    fld<double>(st, L.md_la_rtime) += wall_s() - rt0;
+    fld<int64_t>(st, L.md_num_zerored) += (int64_t)nrl - (int64_t)np;
+    fld<double>(st, L.md_application_nr_mult) += (double)stats.units / 1000.0;
+    fld<double>(st, L.md_application_nr_add) += (double)stats.units / 1000.0;
+    fld<uint64_t>(st, L.md_application_nr_red) += stats.pivot_applications;
+    if (fld<int32_t>(st, L.md_info_level) > 1) {
+        fprintf(stderr, "%9d new %7d zero", (int)np, (int)(nrl - np));
+        fflush(stderr);
+    }
+
+    f4la_neogb_totals &t = T.tot;
+    t.calls++;
+    t.ms_total += t_end - t_begin; t.ms_flatten += t_flat - t_begin; t.ms_materialize += t_end - t_dev;
+    t.ms_h2d += stats.ms_h2d; t.ms_prep += stats.ms_prep; t.ms_reduce += stats.ms_reduce;
+    t.ms_echelon += stats.ms_echelon; t.ms_d2h += stats.ms_d2h;
+    t.units += stats.units; t.bytes_h2d += stats.bytes_h2d; t.bytes_d2h += stats.bytes_d2h;
+    t.kernel_launches += stats.kernel_launches;
+}
+
+} // namespace
+
+extern "C" {
+
+int f4la_b200_neogb_configure(const f4la_neogb_layout *layout)
+{
+    if (!layout || layout->struct_size != sizeof(f4la_neogb_layout)) {
+        fprintf(stderr, "[f4la_b200] layout descriptor has the wrong size (header / library mismatch)\n");
+        return F4LA_ERR_ARG;
+    }
+    L = *layout;
+    g_configured = true;
+    return F4LA_OK;
+}
+
+void f4la_b200_neogb_set_device(int device)
+{
+    if (T.ctx && T.device != device) { f4la_b200_destroy(T.ctx); T.ctx = nullptr; }
+    T.device = device;
+}
+
+void f4la_b200_linear_algebra(void *mat, const void *tbr, const void *bs, void *st)
+{
+    echelon(mat, tbr, bs, st);
+}
+
+void f4la_b200_exact_linear_algebra(void *mat, const void *tbr, const void *bs, void *st)
+{
+    echelon(mat, tbr, bs, st);
+}
+
+void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset)
+{
+    if (t) *t = T.tot;
+    if (reset) T.tot = f4la_neogb_totals{};
+}
+
+} /* extern "C" */

@@ -26,6 +26,7 @@
 
 #include "gb.c"                 /* the reference, unmodified (-I at build) */
 #include "f4la_b200.h"          /* flat exchange format only               */
+#include "f4la_b200_neogb.h"    /* layout descriptor of the drop-in ABI    */
 
 /* ------------------------------------------------------------------ */
 /* records                                                             */
@@ -486,4 +487,31 @@ int refh_struct_layout(uint64_t *o, int cap)
     PUSH(OFFSET); PUSH(LENGTH); PUSH(PRELOOP); PUSH(COEFFS); PUSH(MULT); PUSH(BINDEX); PUSH(DEG);
 #undef PUSH
     return k;
+}
+
+/* The reference-side half of the drop-in binding: describe mat_t/bs_t/md_t to
+ * the backend with this compiler's offsetof. */
+void refh_fill_layout(f4la_neogb_layout *l)
+{
+    memset(l, 0, sizeof(*l));
+    l->struct_size = sizeof(*l);
+    l->mat_tr = offsetof(mat_t, tr); l->mat_rba = offsetof(mat_t, rba); l->mat_rr = offsetof(mat_t, rr);
+    l->mat_cf_8 = offsetof(mat_t, cf_8); l->mat_cf_16 = offsetof(mat_t, cf_16); l->mat_cf_32 = offsetof(mat_t, cf_32);
+    l->mat_sz = offsetof(mat_t, sz); l->mat_np = offsetof(mat_t, np); l->mat_nr = offsetof(mat_t, nr);
+    l->mat_nc = offsetof(mat_t, nc); l->mat_nru = offsetof(mat_t, nru); l->mat_nrl = offsetof(mat_t, nrl);
+    l->mat_ncl = offsetof(mat_t, ncl); l->mat_ncr = offsetof(mat_t, ncr); l->mat_rbal = offsetof(mat_t, rbal);
+    l->bs_ld = offsetof(bs_t, ld); l->bs_cf_8 = offsetof(bs_t, cf_8); l->bs_cf_16 = offsetof(bs_t, cf_16);
+    l->bs_cf_32 = offsetof(bs_t, cf_32);
+    l->md_trace_level = offsetof(md_t, trace_level); l->md_np = offsetof(md_t, np);
+    l->md_la_ctime = offsetof(md_t, la_ctime); l->md_la_rtime = offsetof(md_t, la_rtime);
+    l->md_num_zerored = offsetof(md_t, num_zerored); l->md_fc = offsetof(md_t, fc);
+    l->md_laopt = offsetof(md_t, laopt); l->md_nthrds = offsetof(md_t, nthrds);
+    l->md_ff_bits = offsetof(md_t, ff_bits); l->md_nf = offsetof(md_t, nf);
+    l->md_in_final_reduction_step = offsetof(md_t, in_final_reduction_step);
+    l->md_info_level = offsetof(md_t, info_level);
+    l->md_application_nr_mult = offsetof(md_t, application_nr_mult);
+    l->md_application_nr_add = offsetof(md_t, application_nr_add);
+    l->md_application_nr_red = offsetof(md_t, application_nr_red);
+    l->row_offset = OFFSET; l->row_length = LENGTH; l->row_preloop = PRELOOP; l->row_coeffs = COEFFS;
+    l->row_mult = MULT; l->row_bindex = BINDEX; l->row_deg = DEG; l->unroll = UNROLL;
 }

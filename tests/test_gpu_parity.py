@@ -1,0 +1,137 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes
+through the C ABI of csrc/libf4la_b200.so; the oracle / compiled reference are
+only the checkers."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+from msolve_b200 import systems
+from msolve_b200.flat import FlatMatrix
+from oracle import oracle
+from oracle import refharness as rh
+
+pytestmark = pytest.mark.gpu
+
+P31, P16, P8 = 1073741827, 65521, 251
+
+
+@pytest.mark.parametrize("path", golden_io.fixture_files(), ids=os.path.basename)
+def test_gpu_matches_reference_fixtures(backend, path):
+    n = 0
+    for m, ref, meta in golden_io.load_cases(path):
+        if meta["kind"] != 0 or m.flags != 0:
+            continue
+        out, st = backend.reduce(m)
+        assert out.same_rows(ref), f"{path}: {m.nru}+{m.nrl} rows x {m.ncl}+{m.ncr} cols"
+        assert st["kernel_launches"] > 0
+        n += 1
+    assert n > 0
+
+
+def test_gpu_edge_cases(backend):
+    p = P31
+    # no lower rows
+    m = FlatMatrix(p, 1, 0, 1, 1, np.array([0, 2]), np.array([0, 1]), np.array([0]),
+                   np.array([0, 2]), np.array([1, 5], dtype=np.uint32))
+    out, _ = backend.reduce(m)
+    assert out.nrows == 0
+    # dependent lower rows -> one new pivot
+    m = FlatMatrix(p, 1, 2, 1, 1, np.array([0, 2, 4, 6]), np.array([0, 1, 0, 1, 0, 1]), np.array([0, 1, 2]),
+                   np.array([0, 2, 4, 6]), np.array([1, 5, 2, 3, 4, 20], dtype=np.uint32))
+    out, _ = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref) and out.nrows == 1
+    # a lower row equal to a pivot row reduces to zero
+    m = FlatMatrix(p, 1, 1, 1, 1, np.array([0, 2, 4]), np.array([0, 1, 0, 1]), np.array([0, 0]),
+                   np.array([0, 2]), np.array([1, 5], dtype=np.uint32))
+    out, _ = backend.reduce(m)
+    assert out.nrows == 0
+    # no pivots at all: plain echelon form of the lower rows
+    m = FlatMatrix(p, 0, 2, 0, 3, np.array([0, 2, 4]), np.array([0, 2, 0, 1]), np.array([0, 1]),
+                   np.array([0, 2, 4]), np.array([3, 7, 6, 1], dtype=np.uint32))
+    out, _ = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref) and out.nrows == 2
+
+
+def test_gpu_rejects_malformed_input(backend):
+    from msolve_b200.backend import F4LAError
+    p = P31
+    # pivot row 0 does not start with column 0
+    m = FlatMatrix(p, 1, 1, 1, 1, np.array([0, 2, 4]), np.array([1, 0, 0, 1]), np.array([0, 0]),
+                   np.array([0, 2]), np.array([1, 5], dtype=np.uint32))
+    with pytest.raises(F4LAError):
+        backend.reduce(m)
+
+
+def random_matrix(rng, p, nru, nrl, ncr, density, cf_dtype):
+    """Random [A B; C D] with unit upper triangular A, ragged row lengths."""
+    nc = nru + ncr
+    rows, cfs = [], []
+    for i in range(nru):
+        k = rng.integers(0, max(1, int(density * (nc - i - 1)) + 1))
+        others = rng.choice(np.arange(i + 1, nc), size=min(k, nc - i - 1), replace=False) if nc - i - 1 > 0 else np.zeros(0, int)
+        rng.shuffle(others)
+        rows.append(np.concatenate([[i], others]))
+        cfs.append(np.concatenate([[1], rng.integers(1, p, size=len(others))]))
+    for r in range(nrl):
+        k = int(rng.integers(0, max(2, int(density * nc) + 2)))
+        c = rng.choice(nc, size=min(k, nc), replace=False)
+        if len(c) == 0 and r % 3:
+            c = np.array([rng.integers(0, nc)])
+        c = np.sort(c)
+        rows.append(c)
+        cfs.append(rng.integers(1, p, size=len(c)))
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    return FlatMatrix(p, nru, nrl, nru, ncr, row_ptr, np.concatenate(rows) if rows else np.zeros(0),
+                      np.arange(nru + nrl), row_ptr.copy(), np.concatenate(cfs).astype(cf_dtype))
+
+
+@pytest.mark.parametrize("p,dt", [(P31, np.uint32), (2147483629, np.uint32), (P16, np.uint16), (P8, np.uint8),
+                                  (65537, np.uint32), (3, np.uint8)])
+def test_gpu_vs_oracle_random_ragged(backend, p, dt):
+    rng = np.random.default_rng(1234 + p % 1000)
+    for nru, nrl, ncr, dens in [(40, 17, 9, 0.2), (300, 150, 70, 0.05), (257, 129, 33, 0.3), (1000, 520, 130, 0.02),
+                                (64, 700, 40, 0.1)]:
+        m = random_matrix(rng, p, nru, nrl, ncr, dens, dt)
+        out, st = backend.reduce(m)
+        ref, units, apps = oracle.reduce(m)
+        assert out.same_rows(ref), (p, nru, nrl, ncr)
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+@pytest.mark.parametrize("name,p", [("cyclic-7", P31), ("cyclic-7", P16), ("cyclic-7", P8), ("katsura-8", P31),
+                                    ("katsura-8", P16), ("eco-9", P31), ("randquad-6", P31)])
+def test_gpu_vs_reference_every_f4_step(backend, name, p):
+    """Per-F4-step parity: identical reduced row echelon rows on every matrix
+    the reference's F4 builds (the reference's own LA output is the checker)."""
+    gb, recs = rh.record_f4(systems.by_name(name, p), p, threads=4)
+    n = 0
+    for r in recs:
+        if r.kind != 0:
+            continue
+        out, st = backend.reduce(r.matrix)
+        assert out.same_rows(r.result), (name, p, r.matrix.nru, r.matrix.nrl)
+        n += 1
+    assert n > 5
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+@pytest.mark.parametrize("name,p", [("cyclic-7", P31), ("cyclic-7", P8), ("katsura-8", P16), ("cyclic-8", P31),
+                                    ("cyclic-8", P16), ("cyclic-8", P8), ("katsura-10", P31)])
+def test_gpu_backend_inside_reference_f4(name, p):
+    """Drop-in test: neogb's F4 with `linear_algebra` pointing at the GPU
+    backend returns the reference's reduced Groebner basis bit for bit."""
+    import gpu_helpers
+    L = gpu_helpers.install_backend()
+    try:
+        gb = rh.run_f4(systems.by_name(name, p), p, threads=4, laopt=2)
+        tot = gpu_helpers.neogb_totals(L)
+    finally:
+        gpu_helpers.uninstall_backend()
+    want = golden_io.gb_digests()[f"{name}@{p}"]
+    assert len(gb.lens) == want["nelts"] and int(gb.lens.sum()) == want["nterms"]
+    assert gb.digest() == want["digest"]
+    assert tot["calls"] > 0 and tot["kernel_launches"] > 0
