@@ -54,7 +54,7 @@ static refh_record *g_rec   = NULL;
 static int          g_nrec  = 0;
 static int          g_caprec = 0;
 
-static int    g_mode        = 0;   /* 0 ref, 1 backend, 2 shadow, 3 record */
+static int    g_mode        = 0;   /* 0 ref, 1 backend, 2 shadow, 3 record (reference serves), 4 record (backend serves) */
 static int    g_max_records = 1 << 30;
 static int64_t g_shadow_mismatch = 0;
 static int64_t g_shadow_calls    = 0;
@@ -263,7 +263,7 @@ static void hook_common(int kind, mat_t *mat, const bs_t *tbr, const bs_t *bs, m
     la_fn_t be_fn  = kind == 0 ? g_backend_la : g_backend_exact_la;
     const double t0 = realtime();
     g_la_calls++;
-    if (g_mode == 1 && be_fn) {
+    if ((g_mode == 1 || (g_mode == 4 && g_nrec >= g_max_records)) && be_fn) {
         be_fn(mat, tbr, bs, st);
         g_la_seconds += realtime() - t0;
         return;
@@ -288,7 +288,8 @@ static void hook_common(int kind, mat_t *mat, const bs_t *tbr, const bs_t *bs, m
         free_clone_after_la(c, &stc);
         return;
     }
-    if (g_mode == 3 && g_nrec < g_max_records) {
+    if ((g_mode == 3 || (g_mode == 4 && be_fn)) && g_nrec < g_max_records) {
+        if (g_mode == 4) ref_fn = be_fn;      /* record the inputs, serve with the backend */
         refh_record *rec = new_record();
         flatten_input(rec, mat, tbr, bs, st, 0);
         rec->kind = kind; rec->laopt = st->laopt; rec->ff_bits = st->ff_bits;

@@ -24,7 +24,7 @@ from msolve_b200.flat import CFlatMatrix, CFlatResult, FlatMatrix, FlatResult, _
 
 LIB_PATH = os.path.join(_HERE, "_ref", "libneogb_ref.so")
 
-MODE_REFERENCE, MODE_BACKEND, MODE_SHADOW, MODE_RECORD = 0, 1, 2, 3
+MODE_REFERENCE, MODE_BACKEND, MODE_SHADOW, MODE_RECORD, MODE_RECORD_BACKEND = 0, 1, 2, 3, 4
 
 
 class _CRecord(C.Structure):
