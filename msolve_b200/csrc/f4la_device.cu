@@ -27,7 +27,7 @@ struct HostBuf {            /* pinned */
     size_t cap = 0;
 };
 
-constexpr size_t kL2Budget = (size_t)88 << 20;   /* bytes of V kept in flight */
+constexpr size_t kL2BudgetDefault = (size_t)88 << 20;   /* bytes of V kept in flight */
 
 double now_ms()
 {
@@ -47,6 +47,10 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
+    DevBuf sched, items, flowflags;
+    int           flow_blocks_per_sm[2][kMaxT + 1] = {};
+    int           use_levels = 0;       /* F4LA_B200_SCHED=levels: one launch per level (debug / A-B) */
+    size_t        l2_budget = 0;
     HostBuf h_small, h_dense;
 };
 
@@ -140,6 +144,48 @@ void launch_solve_T(f4la_ctx *ctx, int T, const SolveArgs &a, unsigned nchunks, 
         case 3: launch_solve<3>(ctx, a, nchunks, wide); break;
         default: launch_solve<4>(ctx, a, nchunks, wide); break;
     }
+}
+
+template <int T, bool WIDE>
+int flow_occupancy()
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pull_flow<T, WIDE>, kSolveThreads, 0) != cudaSuccess) n = 2;
+    return n < 1 ? 1 : n;
+}
+
+int flow_blocks(f4la_ctx *ctx, int T, bool wide)
+{
+    int &c = ctx->flow_blocks_per_sm[wide ? 1 : 0][T];
+    if (c == 0) {
+        switch (T) {
+            case 1: c = wide ? flow_occupancy<1, true>() : flow_occupancy<1, false>(); break;
+            case 2: c = wide ? flow_occupancy<2, true>() : flow_occupancy<2, false>(); break;
+            case 3: c = wide ? flow_occupancy<3, true>() : flow_occupancy<3, false>(); break;
+            default: c = wide ? flow_occupancy<4, true>() : flow_occupancy<4, false>(); break;
+        }
+    }
+    return c;
+}
+
+void launch_flow(f4la_ctx *ctx, int T, const FlowArgs &a, bool wide)
+{
+    const uint64_t total = (uint64_t)a.n_items * a.G;
+    if (total == 0) return;
+    uint64_t g = (uint64_t)ctx->sm_count * flow_blocks(ctx, T, wide);
+    if (g > total) g = total;
+    const unsigned grid = (unsigned)g;
+#define FLOW(TT)                                                                                   \
+    if (wide) k_pull_flow<TT, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);                    \
+    else      k_pull_flow<TT, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a)
+    switch (T) {
+        case 1: FLOW(1); break;
+        case 2: FLOW(2); break;
+        case 3: FLOW(3); break;
+        default: FLOW(4); break;
+    }
+#undef FLOW
+    ctx->launches++;
 }
 
 void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
@@ -258,6 +304,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     /* ---- 3. chunking of the lower rows ---- */
     int T = (int)((nrl + kRowsPerT - 1) / kRowsPerT);
     if (T > kMaxT) T = kMaxT;
+    const size_t kL2Budget = ctx->l2_budget;
     while (T > 1 && (size_t)nc * kRowsPerT * T * 4 > kL2Budget) --T;
     const uint32_t Rc = kRowsPerT * T;
     const uint32_t nchunks = (nrl + Rc - 1) / Rc;
@@ -275,6 +322,40 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     a.V = as<uint32_t>(ctx->V);
     a.nc = nc; a.Rc = Rc; a.p = p; a.pinv = pinv;
 
+    /* dataflow schedule: items in level order, then the non-pivot columns */
+    uint32_t n_items = 0;
+    if (!ctx->use_levels) {
+        const uint32_t first = nlev ? slot_ptr_h[2] : ncl;      /* columns of level 0 have no sources */
+        const uint32_t na = ncl - first;
+        std::vector<uint32_t> items;
+        items.reserve((size_t)na / 4 + ncr + 16);
+        for (uint32_t l = 1; l < nlev; ++l) {
+            for (uint32_t q = slot_ptr_h[2 * l]; q < slot_ptr_h[2 * l + 1]; ++q)
+                items.push_back(((q - first) << 5) | (1u << 1) | 1u);
+            for (uint32_t q = slot_ptr_h[2 * l + 1]; q < slot_ptr_h[2 * l + 2]; q += kWarpsPerBlock) {
+                const uint32_t cnt = slot_ptr_h[2 * l + 2] - q < (uint32_t)kWarpsPerBlock
+                                         ? slot_ptr_h[2 * l + 2] - q : (uint32_t)kWarpsPerBlock;
+                items.push_back(((q - first) << 5) | (cnt << 1));
+            }
+        }
+        for (uint32_t k = 0; k < ncr; ++k) items.push_back(((na + k) << 5) | (1u << 1) | 1u);
+        n_items = (uint32_t)items.size();
+        OK(ensure(ctx, ctx->sched, ((size_t)na + ncr + 1) * 4));
+        OK(ensure(ctx, ctx->items, ((size_t)n_items + 1) * 4));
+        OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
+        OK(ensure_host(ctx, ctx->h_dense, (size_t)n_items * 4 + 64));
+        memcpy(ctx->h_dense.p, items.data(), (size_t)n_items * 4);
+        CU(cudaMemcpyAsync(ctx->items.p, ctx->h_dense.p, (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+        k_flow_sched<<<(na + ncr + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->order), first, ncl, ncr,
+                                                           as<uint32_t>(ctx->sched));
+        k_flow_init_flags<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), ncl, nc, G,
+                                                          as<uint32_t>(ctx->flowflags));
+        ctx->launches += 2;
+        /* the staging buffer is reused for the result later: the copy must be done first */
+        CU(cudaStreamSynchronize(s));
+    }
+
+    uint32_t epoch = 0;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
@@ -283,6 +364,21 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                                                                     d.cf_bytes, nru, nrl, nc, p, c0, g, Rc,
                                                                     as<uint32_t>(ctx->V), d_err);
         ctx->launches++;
+        if (!ctx->use_levels) {
+            FlowArgs f;
+            memset(&f, 0, sizeof(f));
+            f.col_ptr = as<uint32_t>(ctx->col_ptr); f.ent = as<uint2>(ctx->ent);
+            f.V = as<uint32_t>(ctx->V); f.nc = nc; f.Rc = Rc;
+            f.sched = as<uint32_t>(ctx->sched); f.items = as<uint32_t>(ctx->items);
+            f.n_items = n_items; f.G = g;
+            f.flags = as<uint32_t>(ctx->flowflags); f.epoch = ++epoch;
+            f.counter = d_err + 4; f.err = d_err;
+            f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
+            f.p = p; f.pinv = pinv;
+            CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
+            launch_flow(ctx, T, f, wide);
+            continue;
+        }
         /* level 0 columns have no sources: V[j] already final */
         for (uint32_t l = 1; l < nlev; ++l) {
             SolveArgs b = a;
@@ -337,6 +433,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
     }
     const uint32_t rank = h_state->rank;
+    {
+        uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
+        CU(cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (*h_err)
+            return fail(ctx, F4LA_ERR_CUDA, "device pipeline reported error bits 0x%x (4: column out of range in a lower "
+                        "row, 16: dataflow watchdog expired)", *h_err);
+    }
     CU(cudaEventRecord(ctx->ev[3], s));
 
     /* ---- 5. reduced rows back to the host ---- */
@@ -475,6 +579,10 @@ f4la_ctx *f4la_b200_create(int device)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    const char *sched = getenv("F4LA_B200_SCHED");
+    ctx->use_levels = sched && !strcmp(sched, "levels");
+    const char *bud = getenv("F4LA_B200_L2_MB");
+    ctx->l2_budget = bud && atoi(bud) > 0 ? (size_t)atoi(bud) << 20 : kL2BudgetDefault;
     return ctx;
 }
 
@@ -485,7 +593,8 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
-                      &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out};
+                      &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
+                      &ctx->sched, &ctx->items, &ctx->flowflags};
     for (auto b : bufs) free_dev(*b);
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);

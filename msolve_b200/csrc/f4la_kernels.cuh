@@ -402,6 +402,249 @@ k_pull_solve(const SolveArgs A)
 }
 
 /* ------------------------------------------------------------------ */
+/* the hot kernel, dataflow-scheduled (one launch per chunk group)      */
+/* ------------------------------------------------------------------ */
+
+/* Instead of one launch per dependency level, a persistent grid pulls work
+ * items from an atomic counter in topological (level) order and waits per
+ * SOURCE COLUMN on a ready flag, as in synchronisation-free sparse triangular
+ * solves.  An item is one long column (whole CTA) or up to 8 short columns
+ * (one warp each).  Items are handed out in increasing order, a column only
+ * depends on columns of earlier items, hence the oldest unfinished item never
+ * waits: no deadlock whatever the number of resident CTAs. */
+
+constexpr uint32_t kFlagAlways = 0xffffffffu;   /* column without sources: V[j] = X[j] */
+constexpr uint32_t kSpinLimit  = 1u << 24;      /* polls before the watchdog gives up (seconds) */
+constexpr uint32_t kErrWatchdog = 16u;
+
+struct FlowArgs {
+    const uint32_t *col_ptr;
+    const uint2    *ent;
+    uint32_t       *V;          /* [G][nc][Rc]                                   */
+    uint32_t        nc, Rc;
+    const uint32_t *sched;      /* column ids in schedule order                   */
+    const uint32_t *items;      /* (pos << 5) | (count << 1) | is_long            */
+    uint32_t        n_items, G;
+    uint32_t       *flags;      /* [G][nc] ready epoch of each column             */
+    uint32_t        epoch;
+    uint32_t       *counter;    /* work counter, zeroed before the launch         */
+    uint32_t       *err;        /* error bits (kErrWatchdog)                      */
+    uint32_t        ncl;        /* columns >= ncl go to out                       */
+    uint32_t       *out;
+    uint64_t        out_ld;
+    uint32_t        chunk0;
+    uint32_t        p;
+    uint64_t        pinv;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *ptr)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release(uint32_t *ptr, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(ptr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4 *ptr)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+
+/* Entries [e0,e1) of one column, taken in batches of 32 with stride
+ * `nslots` batches starting at batch `slot`; waits for every source. */
+template <int T, bool WIDE>
+__device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_t *__restrict__ Vc,
+                                                const uint32_t *__restrict__ flagc,
+                                                uint32_t e0, uint32_t e1, uint32_t slot, uint32_t nslots,
+                                                uint32_t lane, uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
+{
+    constexpr int U = (T <= 2) ? 4 : 2;
+    const uint32_t Rc = A.Rc;
+    uint32_t since_fold = 0;
+    for (uint32_t b = e0 + 32 * slot; b < e1; b += 32 * nslots) {
+        const uint32_t n = min(32u, e1 - b);
+        uint2 en = make_uint2(0, 0);
+        bool ready = true;
+        if (lane < n) {
+            en = __ldg(&A.ent[b + lane]);
+            const uint32_t f = ld_acquire(&flagc[en.x]);
+            ready = (f == A.epoch) || (f == kFlagAlways);
+        }
+        uint32_t spins = 0;
+        while (!__all_sync(0xffffffffu, ready)) {
+            if (!ready) {
+                __nanosleep(64);
+                const uint32_t f = ld_acquire(&flagc[en.x]);
+                ready = (f == A.epoch) || (f == kFlagAlways);
+                if (++spins > kSpinLimit) {          /* watchdog: never hang the GPU */
+                    atomicOr(A.err, kErrWatchdog);
+                    ready = true;
+                }
+            }
+        }
+        __syncwarp();       /* order every lane's V loads after the lanes' acquires */
+        for (uint32_t u0 = 0; u0 < n; u0 += U) {
+            uint32_t src[U], cf[U];
+            uint4 v[U][T];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                /* lanes beyond n hold {0,0}: a zero coefficient, source column 0 (always valid) */
+                src[u] = __shfl_sync(0xffffffffu, en.x, (u0 + u) & 31);
+                cf[u]  = __shfl_sync(0xffffffffu, en.y, (u0 + u) & 31);
+                if (u0 + u >= n) cf[u] = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint4 *sp = reinterpret_cast<const uint4 *>(Vc + (size_t)src[u] * Rc) + lane;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    if (u0 + u < n) v[u][t] = ld_cg_u4(sp + t * 32);
+                    else v[u][t] = make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t cl = WIDE ? (cf[u] & 0xffffu) : cf[u];
+                const uint32_t ch = cf[u] >> 16;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    lo[t][0] += (uint64_t)v[u][t].x * cl; lo[t][1] += (uint64_t)v[u][t].y * cl;
+                    lo[t][2] += (uint64_t)v[u][t].z * cl; lo[t][3] += (uint64_t)v[u][t].w * cl;
+                    if (WIDE) {
+                        hi[t][0] += (uint64_t)v[u][t].x * ch; hi[t][1] += (uint64_t)v[u][t].y * ch;
+                        hi[t][2] += (uint64_t)v[u][t].z * ch; hi[t][3] += (uint64_t)v[u][t].w * ch;
+                    }
+                }
+            }
+        }
+        since_fold += 32;
+        if (since_fold >= kFoldEvery) {
+            since_fold = 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
+                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
+                }
+        }
+    }
+}
+
+template <int T, bool WIDE>
+__global__ void __launch_bounds__(kSolveThreads)
+k_pull_flow(const FlowArgs A)
+{
+    __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];
+    __shared__ uint32_t s_id;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t total = A.n_items * A.G;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_id = atomicAdd(A.counter, 1u);
+        __syncthreads();
+        const uint32_t id = s_id;
+        __syncthreads();
+        if (id >= total) return;
+        const uint32_t chunk = id % A.G;
+        const uint32_t it = A.items[id / A.G];
+        const uint32_t pos = it >> 5, cnt = (it >> 1) & 15u;
+        const bool is_long = it & 1u;
+        uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
+        uint32_t *flagc = A.flags + (size_t)chunk * A.nc;
+
+        uint64_t lo[T][4], hi[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lo[t][k] = 0; hi[t][k] = 0; }
+
+        if (!is_long) {
+            if (warp < cnt) {
+                const uint32_t j = A.sched[pos + warp];
+                const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
+                flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, 0, 1, lane, lo, hi);
+                const bool to_out = j >= A.ncl;
+                uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
+                                       : Vc + (size_t)j * A.Rc;
+                const uint4 *init = reinterpret_cast<const uint4 *>(Vc + (size_t)j * A.Rc) + lane;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint4 x = init[t * 32];
+                    uint4 r;
+                    r.x = fold_lohi<WIDE>(lo[t][0] + x.x, hi[t][0], A.p, A.pinv);
+                    r.y = fold_lohi<WIDE>(lo[t][1] + x.y, hi[t][1], A.p, A.pinv);
+                    r.z = fold_lohi<WIDE>(lo[t][2] + x.z, hi[t][2], A.p, A.pinv);
+                    r.w = fold_lohi<WIDE>(lo[t][3] + x.w, hi[t][3], A.p, A.pinv);
+                    reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
+                }
+                if (!to_out) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) st_release(&flagc[j], A.epoch);
+                }
+            }
+            continue;       /* the two barriers at the loop head keep the CTA together */
+        }
+
+        const uint32_t j = A.sched[pos];
+        const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
+        flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, warp, kWarpsPerBlock, lane, lo, hi);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            uint4 r;
+            r.x = fold_lohi<WIDE>(lo[t][0], hi[t][0], A.p, A.pinv);
+            r.y = fold_lohi<WIDE>(lo[t][1], hi[t][1], A.p, A.pinv);
+            r.z = fold_lohi<WIDE>(lo[t][2], hi[t][2], A.p, A.pinv);
+            r.w = fold_lohi<WIDE>(lo[t][3], hi[t][3], A.p, A.pinv);
+            reinterpret_cast<uint4 *>(&part[warp][t * kRowsPerT])[lane] = r;
+        }
+        __syncthreads();
+        const bool to_out = j >= A.ncl;
+        uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
+                               : Vc + (size_t)j * A.Rc;
+        for (uint32_t r = threadIdx.x; r < (uint32_t)(T * kRowsPerT); r += kSolveThreads) {
+            uint64_t s = Vc[(size_t)j * A.Rc + r];
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w][r];
+            dst[r] = mod_u64(s, A.p, A.pinv);
+        }
+        if (!to_out) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release(&flagc[j], A.epoch);
+        }
+    }
+}
+
+/* flags of the columns without sources, for all G chunk slots */
+__global__ void k_flow_init_flags(const uint32_t *__restrict__ col_ptr, uint32_t ncl, uint32_t nc, uint32_t G,
+                                  uint32_t *__restrict__ flags)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nc) return;
+    const uint32_t f = (j < ncl && col_ptr[j + 1] == col_ptr[j]) ? kFlagAlways : 0u;
+    for (uint32_t g = 0; g < G; ++g) flags[(size_t)g * nc + j] = f;
+}
+
+/* schedule = pivot columns with sources in level order, then the non-pivot columns */
+__global__ void k_flow_sched(const uint32_t *__restrict__ order, uint32_t first, uint32_t ncl, uint32_t ncr,
+                             uint32_t *__restrict__ sched)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t na = ncl - first;
+    if (k < na) sched[k] = order[first + k];
+    else if (k < na + ncr) sched[k] = ncl + (k - na);
+}
+
+/* ------------------------------------------------------------------ */
 /* trailing block: Gauss-Jordan on D' (column major, ld rows per col)   */
 /* ------------------------------------------------------------------ */
 
