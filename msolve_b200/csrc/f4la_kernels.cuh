@@ -490,24 +490,23 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
             }
         }
         __syncwarp();       /* order every lane's V loads after the lanes' acquires */
-        for (uint32_t u0 = 0; u0 < n; u0 += U) {
+        /* Lanes >= n hold the entry {source 0, coefficient 0}: it is loaded and
+         * multiplied like any other (column 0 always exists) and adds nothing,
+         * which keeps the loop free of predicates. */
+        const uint32_t nu = (n + U - 1) / U * U;
+        for (uint32_t u0 = 0; u0 < nu; u0 += U) {
             uint32_t src[U], cf[U];
             uint4 v[U][T];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                /* lanes beyond n hold {0,0}: a zero coefficient, source column 0 (always valid) */
                 src[u] = __shfl_sync(0xffffffffu, en.x, (u0 + u) & 31);
                 cf[u]  = __shfl_sync(0xffffffffu, en.y, (u0 + u) & 31);
-                if (u0 + u >= n) cf[u] = 0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint4 *sp = reinterpret_cast<const uint4 *>(Vc + (size_t)src[u] * Rc) + lane;
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    if (u0 + u < n) v[u][t] = ld_cg_u4(sp + t * 32);
-                    else v[u][t] = make_uint4(0, 0, 0, 0);
-                }
+                for (int t = 0; t < T; ++t) v[u][t] = __ldcg(sp + t * 32);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
