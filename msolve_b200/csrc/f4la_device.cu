@@ -48,6 +48,7 @@ struct f4la_ctx {
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
     DevBuf sched, items, flowflags;
+    DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     int           use_levels = 0;       /* F4LA_B200_SCHED=levels: one launch per level (debug / A-B) */
     size_t        l2_budget = 0;
@@ -63,6 +64,7 @@ struct f4la_resident {
     void     *cf = nullptr;
     uint64_t  nnz = 0, ncoef = 0;
     uint64_t  bytes = 0;
+    bool      owned = true;
 };
 
 namespace {
@@ -257,19 +259,15 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     std::vector<uint32_t> slot_ptr_h;
     if (ncl) {
         OK(ensure(ctx, ctx->level, (size_t)ncl * 4));
-        CU(cudaMemsetAsync(ctx->level.p, 0, (size_t)ncl * 4, s));
-        for (int it = 0;; ++it) {
-            CU(cudaMemsetAsync(d_err + 1, 0, 4, s));
-            for (int k = 0; k < 4; ++k) {
-                k_level_relax<<<blocks_for_warps(ncl), 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), as<uint2>(ctx->ent),
-                                                                    ncl, as<uint32_t>(ctx->level), d_err + 1);
-                ctx->launches++;
-            }
-            CU(cudaMemcpyAsync(h_small, d_err + 1, 4, cudaMemcpyDeviceToHost, s));
-            CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
-            if (!h_small[0]) break;
-            if (it > (int)ncl) return fail(ctx, F4LA_ERR_ARG, "level relaxation does not converge (cyclic pivots?)");
+        CU(cudaMemsetAsync(ctx->level.p, 0xff, (size_t)ncl * 4, s));      /* kLevelUnset */
+        CU(cudaMemsetAsync(d_err + 1, 0, 4, s));
+        {
+            unsigned g = (ncl + 7) / 8;
+            const unsigned gmax = (unsigned)ctx->sm_count * 8;
+            if (g > gmax) g = gmax;
+            k_level_flow<<<g, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), as<uint2>(ctx->ent), ncl,
+                                           as<uint32_t>(ctx->level), d_err + 1, d_err);
+            ctx->launches++;
         }
         /* class histogram: slot 2l = long columns of level l, 2l+1 = short ones */
         OK(ensure(ctx, ctx->slots, ((size_t)2 * ncl + 4) * 4));
@@ -507,7 +505,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     return F4LA_OK;
 }
 
-int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r)
+/* Copies the flat arrays to the device.  own == true: fresh allocations that
+ * belong to the resident handle; own == false: the context's grow-only staging
+ * buffers (no cudaMalloc/cudaFree on the per-call path). */
+int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own)
 {
     const uint64_t n = (uint64_t)in->nru + in->nrl;
     if (in->fc < 2 || in->fc >= 0x80000000u)
@@ -515,13 +516,24 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r)
     if (in->cf_bytes != 1 && in->cf_bytes != 2 && in->cf_bytes != 4)
         return fail(ctx, F4LA_ERR_ARG, "cf_bytes must be 1, 2 or 4");
     r->dims = *in;
+    r->owned = own;
     r->nnz = n ? in->row_ptr[n] : 0;
     r->ncoef = in->ncf ? in->cf_ptr[in->ncf] : 0;
-    CU(cudaMalloc(&r->row_ptr, (n + 1) * 8));
-    CU(cudaMalloc(&r->cols, (r->nnz + 1) * 4));
-    CU(cudaMalloc(&r->row_cf, (n + 1) * 4));
-    CU(cudaMalloc(&r->cf_ptr, ((uint64_t)in->ncf + 1) * 8));
-    CU(cudaMalloc(&r->cf, (r->ncoef + 1) * in->cf_bytes));
+    if (own) {
+        CU(cudaMalloc(&r->row_ptr, (n + 1) * 8));
+        CU(cudaMalloc(&r->cols, (r->nnz + 1) * 4));
+        CU(cudaMalloc(&r->row_cf, (n + 1) * 4));
+        CU(cudaMalloc(&r->cf_ptr, ((uint64_t)in->ncf + 1) * 8));
+        CU(cudaMalloc(&r->cf, (r->ncoef + 1) * in->cf_bytes));
+    } else {
+        OK(ensure(ctx, ctx->in_row_ptr, (n + 1) * 8));
+        OK(ensure(ctx, ctx->in_cols, (r->nnz + 1) * 4));
+        OK(ensure(ctx, ctx->in_row_cf, (n + 1) * 4));
+        OK(ensure(ctx, ctx->in_cf_ptr, ((uint64_t)in->ncf + 1) * 8));
+        OK(ensure(ctx, ctx->in_cf, (r->ncoef + 1) * in->cf_bytes));
+        r->row_ptr = as<uint64_t>(ctx->in_row_ptr); r->cols = as<uint32_t>(ctx->in_cols);
+        r->row_cf = as<uint32_t>(ctx->in_row_cf); r->cf_ptr = as<uint64_t>(ctx->in_cf_ptr); r->cf = ctx->in_cf.p;
+    }
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(r->row_ptr, in->row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     if (r->nnz) CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
@@ -535,7 +547,7 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r)
 void release_resident(f4la_resident *r)
 {
     if (!r) return;
-    cudaFree(r->row_ptr); cudaFree(r->cols); cudaFree(r->row_cf); cudaFree(r->cf_ptr); cudaFree(r->cf);
+    if (r->owned) { cudaFree(r->row_ptr); cudaFree(r->cols); cudaFree(r->row_cf); cudaFree(r->cf_ptr); cudaFree(r->cf); }
     delete r;
 }
 
@@ -594,7 +606,8 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags};
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf};
     for (auto b : bufs) free_dev(*b);
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
@@ -619,7 +632,7 @@ f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in)
     if (!ctx || !in) return nullptr;
     cudaSetDevice(ctx->device);
     f4la_resident *r = new f4la_resident();
-    if (upload(ctx, in, r) != F4LA_OK) { release_resident(r); return nullptr; }
+    if (upload(ctx, in, r, true) != F4LA_OK) { release_resident(r); return nullptr; }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { release_resident(r); return nullptr; }
     return r;
 }
@@ -647,20 +660,20 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result
     cudaSetDevice(ctx->device);
     if (stats) memset(stats, 0, sizeof(*stats));
     const double t0 = now_ms();
-    f4la_resident *r = new f4la_resident();
-    int rc = upload(ctx, in, r);
-    if (rc == F4LA_OK) {
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, F4LA_ERR_CUDA, "upload failed");
-    }
-    const double t1 = now_ms();
-    if (rc == F4LA_OK) rc = run_pipeline(ctx, r, out, stats);
-    if (stats) {
-        stats->ms_h2d = t1 - t0;
-        stats->bytes_h2d = r->bytes;
-    }
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    f4la_resident r;
+    int rc = upload(ctx, in, &r, false);
+    /* the pipeline runs on the same stream: no synchronisation needed before it;
+     * the H2D time is measured with events */
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    if (rc == F4LA_OK) rc = run_pipeline(ctx, &r, out, stats);
     cudaStreamSynchronize(ctx->stream);
-    release_resident(r);
-    if (stats) stats->ms_total = now_ms() - t0;
+    if (stats) {
+        float ms = 0;
+        if (rc == F4LA_OK && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[5]) == cudaSuccess) stats->ms_h2d = ms;
+        stats->bytes_h2d = r.bytes;
+        stats->ms_total = now_ms() - t0;
+    }
     return rc;
 }
 

@@ -186,6 +186,49 @@ __global__ void k_level_relax(const uint32_t *__restrict__ col_ptr, const uint2 
     }
 }
 
+/* Exact longest-path levels in ONE pass: a persistent grid hands out the
+ * columns in increasing order (a topological order, sources are always to the
+ * left), a warp waits until the levels of its sources have been published.
+ * level[] must be pre-set to kLevelUnset.  Same no-deadlock argument as the
+ * dataflow solve below: the oldest unfinished column never waits. */
+constexpr uint32_t kLevelUnset = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *ptr)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+
+__global__ void k_level_flow(const uint32_t *__restrict__ col_ptr, const uint2 *__restrict__ ent,
+                             uint32_t ncl, uint32_t *level, uint32_t *__restrict__ counter,
+                             uint32_t *__restrict__ err)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(counter, 1u);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= ncl) return;
+        const uint32_t a = col_ptr[j], b = col_ptr[j + 1];
+        uint32_t m = 0;
+        for (uint32_t k = a + lane; k < b; k += 32) {
+            const uint32_t src = __ldg(&ent[k]).x;
+            uint32_t l = ld_acquire_u32(&level[src]);
+            uint32_t spins = 0;
+            while (l == kLevelUnset) {
+                __nanosleep(32);
+                l = ld_acquire_u32(&level[src]);
+                if (++spins > (1u << 24)) { atomicOr(err, 16u); l = 0; }
+            }
+            m = max(m, l + 1);
+        }
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(level + j), "r"(m) : "memory");
+    }
+}
+
 /* Histogram of (level, long/short) classes: slot = 2*level + (short ? 1 : 0). */
 __global__ void k_level_count(const uint32_t *__restrict__ level, const uint32_t *__restrict__ col_ptr,
                               uint32_t ncl, uint32_t *__restrict__ slot_cnt, uint32_t *__restrict__ max_level)

@@ -65,7 +65,7 @@ void *stage(int k, size_t bytes)
 {
     if (bytes > T.cap[k]) {
         if (T.buf[k]) f4la_b200_pinned_free(T.buf[k]);
-        size_t want = bytes + bytes / 2 + 4096;
+        size_t want = 2 * bytes + ((size_t)1 << 20);      /* geometric growth: few re-pinnings per run */
         T.buf[k] = f4la_b200_pinned_alloc(want);
         if (!T.buf[k]) die("pinned host allocation failed");
         T.cap[k] = want;
@@ -136,10 +136,17 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     std::vector<uint64_t> cfp; cfp.reserve(1025);
     std::vector<uint32_t> src_bindex(nrl), src_mult(nrl);
     uint64_t ncoef = 0;
+    const int nthr = fld<int32_t>(st, L.md_nthrds) > 1 ? fld<int32_t>(st, L.md_nthrds) : 1;
+    /* the bulk copy of the column indices is row-parallel (st->nthrds host
+     * threads, like the reference's own row loops, e.g. convert.c:365-397) */
+#pragma omp parallel for num_threads(nthr) schedule(dynamic, 256)
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+        memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)row[L.row_length] * 4);
+    }
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
         const uint32_t len = row[L.row_length];
-        memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)len * 4);
         std::vector<int32_t> &map = r < nru ? map_bs : map_tbr;
         const uint32_t ci = row[L.row_coeffs];
         if ((size_t)ci >= map.size()) die("row refers to a coefficient array beyond the basis load");
@@ -175,7 +182,9 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     const double t_dev = now_ms();
 
     /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
+#pragma omp parallel for num_threads(nthr) schedule(static)
     for (uint32_t i = 0; i < nrl; ++i) { free(tr[i]); tr[i] = nullptr; }
+#pragma omp parallel for num_threads(nthr) schedule(static)
     for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
 
     uint32_t np = res.nrows;
