@@ -49,6 +49,7 @@ struct f4la_ctx {
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
     DevBuf sched, items, flowflags;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
+    DevBuf is_piv, pividx, colmap, invmap, leads;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     int           use_levels = 0;       /* F4LA_B200_SCHED=levels: one launch per level (debug / A-B) */
     size_t        l2_budget = 0;
@@ -204,20 +205,39 @@ void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
 int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f4la_stats *st)
 {
     const f4la_flat_matrix &d = m->dims;
-    const uint32_t nru = d.nru, nrl = d.nrl, ncl = d.ncl, ncr = d.ncr, p = d.fc;
-    const uint32_t nc = ncl + ncr;
+    const uint32_t nru = d.nru, nrl = d.nrl, p = d.fc;
+    const uint32_t nc = d.ncl + d.ncr;
+    const bool by_lead = (d.flags & F4LA_FLAG_PIVOT_BY_LEAD) != 0;
+    const bool nf_mode = (d.flags & F4LA_FLAG_NORMALFORM) != 0;
+    /* effective split: with pivots keyed by lead column the columns are renumbered
+     * (pivot columns first), so that ncl == nru holds for the rest of the pipeline */
+    const uint32_t ncl = by_lead ? nru : d.ncl;
+    const uint32_t ncr = nc - ncl;
     const uint64_t pinv = ~0ULL / p;
     const bool wide = p >= 65536u;
     cudaStream_t s = ctx->stream;
     const uint32_t launches0 = ctx->launches;
 
-    if (d.flags != F4LA_FLAG_NONE)
-        return fail(ctx, F4LA_ERR_ARG, "flags 0x%x not supported by the device pipeline yet", d.flags);
-    if (nru != ncl)
-        return fail(ctx, F4LA_ERR_ARG, "echelon mode needs nru == ncl (got %u, %u)", nru, ncl);
+    if (d.flags & ~(F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_NORMALFORM))
+        return fail(ctx, F4LA_ERR_ARG, "unknown flags 0x%x", d.flags);
+    if (by_lead && nf_mode)
+        return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD and F4LA_FLAG_NORMALFORM cannot be combined");
+    if (!by_lead && nru != d.ncl)
+        return fail(ctx, F4LA_ERR_ARG, "pivots keyed by row index need nru == ncl (got %u, %u)", nru, d.ncl);
+    if (nru > nc)
+        return fail(ctx, F4LA_ERR_ARG, "more pivot rows (%u) than columns (%u)", nru, nc);
     if (m->nnz >= 0xfffffff0ull)
         return fail(ctx, F4LA_ERR_ARG, "matrix too large: %llu non-zeros", (unsigned long long)m->nnz);
-    if (nrl == 0 || ncr == 0) { empty_result(out, d.cf_bytes); return F4LA_OK; }
+    if (nrl == 0 || (ncr == 0 && !by_lead && !nf_mode)) { empty_result(out, d.cf_bytes); return F4LA_OK; }
+    if (ncr == 0) {                       /* every lower row reduces to zero */
+        empty_result(out, d.cf_bytes);
+        free(out->row_ptr); free(out->src_row);
+        out->nrows = nrl;
+        out->row_ptr = (uint64_t *)calloc((size_t)nrl + 1, sizeof(uint64_t));
+        out->src_row = (uint32_t *)malloc((size_t)nrl * sizeof(uint32_t));
+        for (uint32_t i = 0; i < nrl; ++i) out->src_row[i] = i;
+        return F4LA_OK;
+    }
 
     CU(cudaEventRecord(ctx->ev[0], s));
 
@@ -230,9 +250,24 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint32_t *d_err = as<uint32_t>(ctx->flags32);           /* [0] err, [1] changed, [2] max level */
     CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));
     CU(cudaMemsetAsync(d_err, 0, 64, s));
+    const uint32_t *colmap = nullptr;
+    if (by_lead) {
+        OK(ensure(ctx, ctx->is_piv, ((size_t)nc + 2) * 4));
+        OK(ensure(ctx, ctx->pividx, ((size_t)nc + 2) * 4));
+        OK(ensure(ctx, ctx->colmap, ((size_t)nc + 2) * 4));
+        OK(ensure(ctx, ctx->invmap, ((size_t)nc + 2) * 4));
+        CU(cudaMemsetAsync(ctx->is_piv.p, 0, ((size_t)nc + 2) * 4, s));
+        if (nru) k_mark_leads<<<(nru + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nc, as<uint32_t>(ctx->is_piv), d_err);
+        k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc);
+        k_build_colmap<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc, nru,
+                                                       as<uint32_t>(ctx->colmap), as<uint32_t>(ctx->invmap));
+        ctx->launches += 3;
+        colmap = as<uint32_t>(ctx->colmap);
+    }
     if (nru) {
         k_pull_count<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
-                                                           d.cf_bytes, nru, ncl, nc, as<uint32_t>(ctx->col_cnt), d_err);
+                                                           d.cf_bytes, nru, ncl, nc, colmap,
+                                                           as<uint32_t>(ctx->col_cnt), d_err);
         ctx->launches++;
     }
     k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->col_cnt), as<uint32_t>(ctx->col_ptr), nc);
@@ -244,12 +279,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     const uint32_t nnz_pull = h_small[0];
     if (h_small[1])
         return fail(ctx, F4LA_ERR_ARG, "malformed pivot rows (error bits 0x%x: 1 lead not first, 2 not upper "
-                    "triangular, 4 column out of range, 8 lead coefficient != 1)", h_small[1]);
+                    "triangular, 4 column out of range, 8 lead coefficient != 1, 32 duplicate pivot column)", h_small[1]);
     OK(ensure(ctx, ctx->ent, ((size_t)nnz_pull + 1) * sizeof(uint2)));
     CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));   /* reuse as cursor */
     if (nru) {
         k_pull_fill<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
-                                                          nru, nc, p, as<uint32_t>(ctx->col_ptr),
+                                                          nru, nc, p, colmap, as<uint32_t>(ctx->col_ptr),
                                                           as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent));
         ctx->launches++;
     }
@@ -359,7 +394,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
         k_scatter_lower<<<blocks_for_warps(rows_here), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
-                                                                    d.cf_bytes, nru, nrl, nc, p, c0, g, Rc,
+                                                                    d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
                                                                     as<uint32_t>(ctx->V), d_err);
         ctx->launches++;
         if (!ctx->use_levels) {
@@ -396,41 +431,45 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     }
     CU(cudaEventRecord(ctx->ev[2], s));
 
-    /* ---- 4. Gauss-Jordan on the trailing block ---- */
+    /* ---- 4. Gauss-Jordan on the trailing block (not in normal-form mode) ---- */
     const uint32_t maxrank = nrl < ncr ? nrl : ncr;
-    OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
-    OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
-    OK(ensure(ctx, ctx->used, (size_t)ld + 16));
-    OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
-    OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
-    OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
-    OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
-    CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
-    CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
-    CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
     uint32_t *Dm = as<uint32_t>(ctx->D);
-    k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-    ctx->launches++;
-    GEState *h_state = (GEState *)ctx->h_small.p;
-    for (uint32_t done_steps = 0;;) {
-        const int batch = 16;
-        for (int k = 0; k < batch; ++k) {
-            k_ge_find<<<1, 1024, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                                         as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
-                                         as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p);
-            k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                                               as<GEState>(ctx->gestate), p, pinv);
-            ctx->launches += 2;
+    uint32_t rank = 0;
+    if (!nf_mode) {
+        OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
+        OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
+        OK(ensure(ctx, ctx->used, (size_t)ld + 16));
+        OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
+        OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
+        OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
+        OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
+        CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
+        CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
+        CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
+        k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+        ctx->launches++;
+        GEState *h_state = (GEState *)ctx->h_small.p;
+        for (uint32_t done_steps = 0;;) {
+            const int batch = 16;
+            for (int k = 0; k < batch; ++k) {
+                k_ge_find<<<1, 1024, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                             as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate),
+                                             as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                             as<uint32_t>(ctx->pivinv), p);
+                k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                                   as<GEState>(ctx->gestate), p, pinv);
+                ctx->launches += 2;
+            }
+            done_steps += batch;
+            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s));
+            if (h_state->done) break;
+            if (done_steps > maxrank + 2 * batch)
+                return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
         }
-        done_steps += batch;
-        CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
-        CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
-        if (h_state->done) break;
-        if (done_steps > maxrank + 2 * batch)
-            return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+        rank = h_state->rank;
     }
-    const uint32_t rank = h_state->rank;
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
         CU(cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
@@ -441,45 +480,91 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     }
     CU(cudaEventRecord(ctx->ev[3], s));
 
-    /* ---- 5. reduced rows back to the host ---- */
-    if (rank == 0) {
+    /* ---- 5. result rows back to the host ---- */
+    const uint32_t ndense = nf_mode ? nrl : rank;       /* dense rows produced on the device */
+    const uint32_t nout = (nf_mode || by_lead) ? nrl : rank;
+    uint64_t d2h_bytes = 0;
+    if (nout == 0) {
         empty_result(out, d.cf_bytes);
     } else {
-        const size_t dense_bytes = (size_t)rank * ncr * 4;
-        OK(ensure(ctx, ctx->dense_out, dense_bytes));
-        OK(ensure_host(ctx, ctx->h_dense, dense_bytes + (size_t)rank * 8));
-        dim3 grid((ncr + 255) / 256, rank);
-        k_ge_extract<<<grid, 256, 0, s>>>(Dm, ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
-                                          as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
-                                          as<uint32_t>(ctx->dense_out), p, pinv);
-        ctx->launches++;
-        uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
-        uint32_t *h_pivrow = h_dense + (size_t)rank * ncr;
-        CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(h_pivrow, ctx->pivrow.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
-        memset(out, 0, sizeof(*out));
-        out->nrows = rank; out->cf_bytes = d.cf_bytes;
-        out->row_ptr = (uint64_t *)malloc(((size_t)rank + 1) * sizeof(uint64_t));
-        out->src_row = (uint32_t *)malloc((size_t)rank * sizeof(uint32_t));
-        uint64_t nnz = 0;
-        for (uint32_t t = 0; t < rank; ++t) {
-            out->row_ptr[t] = nnz;
-            const uint32_t *row = h_dense + (size_t)t * ncr;
-            for (uint32_t c = 0; c < ncr; ++c) nnz += row[c] != 0;
-            out->src_row[t] = h_pivrow[rank - 1 - t];
+        const size_t dense_bytes = (size_t)ndense * ncr * 4;
+        const size_t aux_words = 2 * (size_t)rank + (by_lead ? 2 * (size_t)nc + nrl : 0) + 16;
+        OK(ensure(ctx, ctx->dense_out, dense_bytes + 16));
+        OK(ensure_host(ctx, ctx->h_dense, dense_bytes + aux_words * 4));
+        if (nf_mode) {
+            dim3 grid((ncr + 31) / 32, (nrl + 31) / 32), block(32, 8);
+            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, as<uint32_t>(ctx->dense_out));
+            ctx->launches++;
+        } else if (rank) {
+            dim3 grid((ncr + 255) / 256, rank);
+            k_ge_extract<<<grid, 256, 0, s>>>(Dm, ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                              as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
+                                              as<uint32_t>(ctx->dense_out), p, pinv);
+            ctx->launches++;
         }
-        out->row_ptr[rank] = nnz;
+        uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
+        uint32_t *h_pivrow = h_dense + (size_t)ndense * ncr;
+        uint32_t *h_pivcol = h_pivrow + rank;
+        uint32_t *h_colmap = h_pivcol + rank, *h_invmap = h_colmap + (by_lead ? nc : 0);
+        uint32_t *h_leads = h_invmap + (by_lead ? nc : 0);
+        if (dense_bytes) CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
+        if (rank) {
+            CU(cudaMemcpyAsync(h_pivrow, ctx->pivrow.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(h_pivcol, ctx->pivcol.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (by_lead) {
+            OK(ensure(ctx, ctx->leads, (size_t)nrl * 4 + 16));
+            k_lower_leads<<<(nrl + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, as<uint32_t>(ctx->leads));
+            ctx->launches++;
+            CU(cudaMemcpyAsync(h_colmap, ctx->colmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(h_invmap, ctx->invmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        d2h_bytes = dense_bytes + aux_words * 4;
+
+        /* which dense row answers output row i (or -1: the row is zero) */
+        std::vector<int64_t> pick(nout, -1);
+        if (nf_mode) {
+            for (uint32_t i = 0; i < nrl; ++i) pick[i] = i;
+        } else if (by_lead) {
+            std::vector<int32_t> row_of_col(ncr, -1);
+            for (uint32_t k = 0; k < rank; ++k) row_of_col[h_pivcol[k]] = (int32_t)(rank - 1 - k);
+            for (uint32_t i = 0; i < nrl; ++i) {
+                if (h_leads[i] >= nc) continue;                    /* empty input row */
+                const uint32_t nid = h_colmap[h_leads[i]];
+                if (nid >= ncl) pick[i] = row_of_col[nid - ncl];
+                if (pick[i] < 0)
+                    return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD needs lower rows with distinct lead columns "
+                                "that are not pivot columns and that are linearly independent (row %u violates this)", i);
+            }
+        } else {
+            for (uint32_t t = 0; t < rank; ++t) pick[t] = t;
+        }
+        memset(out, 0, sizeof(*out));
+        out->nrows = nout; out->cf_bytes = d.cf_bytes;
+        out->row_ptr = (uint64_t *)malloc(((size_t)nout + 1) * sizeof(uint64_t));
+        out->src_row = (uint32_t *)malloc((size_t)nout * sizeof(uint32_t));
+        uint64_t nnz = 0;
+        for (uint32_t t = 0; t < nout; ++t) {
+            out->row_ptr[t] = nnz;
+            out->src_row[t] = (nf_mode || by_lead) ? t : h_pivrow[rank - 1 - t];
+            if (pick[t] < 0) continue;
+            const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
+            for (uint32_t c = 0; c < ncr; ++c) nnz += row[c] != 0;
+        }
+        out->row_ptr[nout] = nnz;
         out->cols = (uint32_t *)malloc((nnz ? nnz : 1) * sizeof(uint32_t));
         out->cf = malloc((nnz ? nnz : 1) * (size_t)d.cf_bytes);
         uint64_t k = 0;
-        for (uint32_t t = 0; t < rank; ++t) {
-            const uint32_t *row = h_dense + (size_t)t * ncr;
+        for (uint32_t t = 0; t < nout; ++t) {
+            if (pick[t] < 0) continue;
+            const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
             for (uint32_t c = 0; c < ncr; ++c) {
                 const uint32_t v = row[c];
                 if (!v) continue;
-                out->cols[k] = ncl + c;
+                out->cols[k] = by_lead ? h_invmap[ncl + c] : ncl + c;
                 if (d.cf_bytes == 4) ((uint32_t *)out->cf)[k] = v;
                 else if (d.cf_bytes == 2) ((uint16_t *)out->cf)[k] = (uint16_t)v;
                 else ((uint8_t *)out->cf)[k] = (uint8_t)v;
@@ -498,7 +583,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_d2h = ms;
         st->units = (uint64_t)nnz_pull * nrl;
         st->pivot_applications = (uint64_t)nnz_pull;
-        st->bytes_d2h = (uint64_t)rank * ncr * 4;
+        st->bytes_d2h = d2h_bytes;
         st->kernel_launches = ctx->launches - launches0;
         st->rank = rank;
     }
@@ -607,7 +692,8 @@ void f4la_b200_destroy(f4la_ctx *ctx)
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
                       &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
-                      &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf};
+                      &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
+                      &ctx->invmap, &ctx->leads};
     for (auto b : bufs) free_dev(*b);
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);

@@ -88,6 +88,7 @@ constexpr uint32_t kErrLeadNotFirst  = 1u;  /* pivot row i does not start with c
 constexpr uint32_t kErrNotTriangular = 2u;  /* pivot entry left of / on its lead        */
 constexpr uint32_t kErrColumnRange   = 4u;  /* column id >= nc                          */
 constexpr uint32_t kErrLeadNotOne    = 8u;  /* pivot row not monic                      */
+constexpr uint32_t kErrDuplicatePivot = 32u; /* two pivot rows with the same lead column */
 
 /* Pass 1 over the pivot rows: histogram of the target columns of all
  * non-lead entries.  One warp per pivot row. */
@@ -97,6 +98,7 @@ __global__ void k_pull_count(const uint64_t *__restrict__ row_ptr,
                              const uint64_t *__restrict__ cf_ptr,
                              const void *__restrict__ cf, uint32_t cf_bytes,
                              uint32_t nru, uint32_t ncl, uint32_t nc,
+                             const uint32_t *__restrict__ colmap,
                              uint32_t *__restrict__ col_cnt, uint32_t *__restrict__ err)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -104,14 +106,23 @@ __global__ void k_pull_count(const uint64_t *__restrict__ row_ptr,
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = warp; i < nru; i += nwarps) {
         const uint64_t a = row_ptr[i], b = row_ptr[i + 1];
+        /* pivot id = (renumbered) lead column; without a column map it must equal the row index */
+        uint32_t id = i;
+        if (b == a) { if (lane == 0) atomicOr(err, kErrLeadNotFirst); continue; }
+        if (colmap) {
+            const uint32_t lead = cols[a];
+            if (lead >= nc) { if (lane == 0) atomicOr(err, kErrColumnRange); continue; }
+            id = colmap[lead];
+        }
         if (lane == 0) {
-            if (b == a || cols[a] != i) atomicOr(err, kErrLeadNotFirst);
+            if (!colmap && cols[a] != i) atomicOr(err, kErrLeadNotFirst);
             else if (load_cf(cf, cf_bytes, cf_ptr[row_cf[i]]) != 1) atomicOr(err, kErrLeadNotOne);
         }
         for (uint64_t k = a + 1 + lane; k < b; k += 32) {
-            const uint32_t j = cols[k];
+            uint32_t j = cols[k];
             if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
-            if (j <= i)  { atomicOr(err, kErrNotTriangular); continue; }
+            if (colmap) j = colmap[j];
+            if (j <= id) { atomicOr(err, kErrNotTriangular); continue; }
             atomicAdd(&col_cnt[j], 1u);
         }
     }
@@ -147,6 +158,7 @@ __global__ void k_pull_fill(const uint64_t *__restrict__ row_ptr,
                             const uint64_t *__restrict__ cf_ptr,
                             const void *__restrict__ cf, uint32_t cf_bytes,
                             uint32_t nru, uint32_t nc, uint32_t p,
+                            const uint32_t *__restrict__ colmap,
                             const uint32_t *__restrict__ col_ptr,
                             uint32_t *__restrict__ cursor, uint2 *__restrict__ ent)
 {
@@ -155,35 +167,51 @@ __global__ void k_pull_fill(const uint64_t *__restrict__ row_ptr,
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = warp; i < nru; i += nwarps) {
         const uint64_t a = row_ptr[i], b = row_ptr[i + 1];
+        if (b == a) continue;
+        uint32_t id = i;
+        if (colmap) {
+            const uint32_t lead = cols[a];
+            if (lead >= nc) continue;
+            id = colmap[lead];
+        }
         const uint64_t c0 = cf_ptr[row_cf[i]];
         for (uint64_t k = a + 1 + lane; k < b; k += 32) {
-            const uint32_t j = cols[k];
-            if (j >= nc || j <= i) continue;
+            uint32_t j = cols[k];
+            if (j >= nc) continue;
+            if (colmap) j = colmap[j];
+            if (j <= id) continue;
             const uint32_t v = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
             const uint32_t pos = col_ptr[j] + atomicAdd(&cursor[j], 1u);
-            ent[pos] = make_uint2(i, v == 0 ? 0u : p - v);
+            ent[pos] = make_uint2(id, v == 0 ? 0u : p - v);
         }
     }
 }
 
-/* Level relaxation, in place and monotone: level[j] = max(level[j],
- * 1 + max_i level[src]).  Converges to the longest-path levels. */
-__global__ void k_level_relax(const uint32_t *__restrict__ col_ptr, const uint2 *__restrict__ ent,
-                              uint32_t ncl, uint32_t *level, uint32_t *__restrict__ changed)
+/* Column renumbering for matrices whose known pivots are keyed by their lead
+ * column (F4LA_FLAG_PIVOT_BY_LEAD): pivot columns first, both groups in their
+ * original relative order, so the pivot rows stay upper triangular. */
+__global__ void k_mark_leads(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
+                             uint32_t nru, uint32_t nc, uint32_t *__restrict__ is_piv, uint32_t *__restrict__ err)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t j = warp; j < ncl; j += nwarps) {
-        const uint32_t a = col_ptr[j], b = col_ptr[j + 1];
-        uint32_t m = 0;
-        for (uint32_t k = a + lane; k < b; k += 32) {
-            const uint32_t l = ((volatile uint32_t *)level)[ent[k].x] + 1;
-            m = max(m, l);
-        }
-        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && m > level[j]) { level[j] = m; *changed = 1; }
-    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nru) return;
+    const uint64_t a = row_ptr[i];
+    if (row_ptr[i + 1] == a) { atomicOr(err, kErrLeadNotFirst); return; }
+    const uint32_t lead = cols[a];
+    if (lead >= nc) { atomicOr(err, kErrColumnRange); return; }
+    if (atomicExch(&is_piv[lead], 1u)) atomicOr(err, kErrDuplicatePivot);
+}
+
+/* pividx = exclusive scan of is_piv; colmap[c] = new id, invmap[new id] = c */
+__global__ void k_build_colmap(const uint32_t *__restrict__ is_piv, const uint32_t *__restrict__ pividx,
+                               uint32_t nc, uint32_t npiv, uint32_t *__restrict__ colmap,
+                               uint32_t *__restrict__ invmap)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const uint32_t k = is_piv[c] ? pividx[c] : npiv + (c - pividx[c]);
+    colmap[c] = k;
+    invmap[k] = c;
 }
 
 /* Exact longest-path levels in ONE pass: a persistent grid hands out the
@@ -260,6 +288,7 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
                                 const void *__restrict__ cf, uint32_t cf_bytes,
                                 uint32_t nru, uint32_t nrl, uint32_t nc, uint32_t p,
                                 uint32_t chunk0, uint32_t nchunks, uint32_t Rc,
+                                const uint32_t *__restrict__ colmap,
                                 uint32_t *__restrict__ V, uint32_t *__restrict__ err)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -273,8 +302,9 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
         const uint32_t lc = (r - r0) / Rc, lr = (r - r0) % Rc;
         uint32_t *Vc = V + (size_t)lc * nc * Rc;
         for (uint64_t k = a + lane; k < b; k += 32) {
-            const uint32_t j = cols[k];
+            uint32_t j = cols[k];
             if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
+            if (colmap) j = colmap[j];
             Vc[(size_t)j * Rc + lr] = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
         }
     }
@@ -815,6 +845,16 @@ __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32
     else if (ispiv[c]) v = 0;
     else v = mulmod(D[(size_t)c * ld + pivrow[k]], pivinv[k], p, pinv);
     out[(size_t)t * ncr + c] = v;
+}
+
+/* Lead (first stored) column of every lower row; 0xffffffff for an empty row. */
+__global__ void k_lower_leads(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
+                              uint32_t nru, uint32_t nrl, uint32_t *__restrict__ leads)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrl) return;
+    const uint64_t a = row_ptr[nru + i];
+    leads[i] = row_ptr[nru + i + 1] > a ? cols[a] : 0xffffffffu;
 }
 
 /* Normal-form mode: row r of D' as is (no elimination). */

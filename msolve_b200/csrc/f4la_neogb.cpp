@@ -98,10 +98,10 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     const int32_t trace_level = fld<int32_t>(st, L.md_trace_level);
     const uint32_t w = ff_bits == 8 ? 1 : ff_bits == 16 ? 2 : 4;
     if (ff_bits != 8 && ff_bits != 16 && ff_bits != 32) die("unsupported field (ff_bits must be 8, 16 or 32)");
-    if (fld<int32_t>(st, L.md_nf) > 0 || fld<int32_t>(st, L.md_in_final_reduction_step))
-        die("normal-form / final-reduction mode is not served by this backend yet: leave exact_linear_algebra "
-            "on the reference's dispatcher");
-    if (trace_level == 1 /* LEARN_TRACER */)
+    const bool nf_mode = fld<int32_t>(st, L.md_nf) > 0;
+    const bool final_step = fld<int32_t>(st, L.md_in_final_reduction_step) != 0;
+    /* the reference records no trace in the final reduction step (la_ff_32.c:2713) */
+    if (trace_level == 1 /* LEARN_TRACER */ && !final_step)
         die("LEARN_TRACER is not served by this backend yet");
 
     const uint32_t nru = fld<uint32_t>(mat, L.mat_nru), nrl = fld<uint32_t>(mat, L.mat_nrl);
@@ -170,7 +170,7 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     f4la_flat_matrix fm;
     memset(&fm, 0, sizeof(fm));
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
-    fm.flags = F4LA_FLAG_NONE;
+    fm.flags = nf_mode ? F4LA_FLAG_NORMALFORM : final_step ? F4LA_FLAG_PIVOT_BY_LEAD : F4LA_FLAG_NONE;
     fm.row_ptr = row_ptr; fm.cols = cols; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = pool;
     const double t_flat = now_ms();
 
@@ -188,7 +188,33 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
 
     uint32_t np = res.nrows;
-    if (trace_level == 2 /* APPLY_TRACER */ && np != nrl) {
+    if (nf_mode || final_step) {
+        /* rows are returned in place, one per input row, NULL when it vanished;
+         * np = nrl (la_ff_32.c:2672-2684, 2764-2766) */
+        for (uint32_t t = 0; t < nrl; ++t) {
+            const uint64_t a = res.row_ptr[t];
+            const uint32_t len = (uint32_t)(res.row_ptr[t + 1] - a);
+            if (len == 0) { tr[t] = nullptr; continue; }
+            uint32_t *row = (uint32_t *)malloc(((size_t)len + L.row_offset) * sizeof(uint32_t));
+            void *cf = malloc((size_t)len * w);
+            memcpy(row + L.row_offset, res.cols + a, (size_t)len * 4);
+            memcpy(cf, (unsigned char *)res.cf + a * w, (size_t)len * w);
+            row[L.row_deg] = 0;
+            row[L.row_bindex] = src_bindex[t];
+            row[L.row_mult] = src_mult[t];
+            row[L.row_coeffs] = t;
+            row[L.row_preloop] = len % L.unroll;
+            row[L.row_length] = len;
+            mcf[t] = cf;
+            tr[t] = row;
+        }
+        f4la_b200_free_result(&res);
+        np = nrl;
+        fld<uint32_t>(st, L.md_np) = np;
+        fld<uint32_t>(mat, L.mat_np) = np;
+        fld<uint32_t>(mat, L.mat_nr) = np;
+        fld<uint32_t>(mat, L.mat_sz) = np;
+    } else if (trace_level == 2 /* APPLY_TRACER */ && np != nrl) {
         /* a row reduced to zero while applying the tracer: bad prime
          * (la_ff_32.c:2679-2683, 2700-2709) */
         np = 0;

@@ -15,7 +15,8 @@ def install_backend(mode=rh.MODE_BACKEND, verbose=0):
     rh.lib().refh_fill_layout(lay)
     assert L.f4la_b200_neogb_configure(lay) == 0
     la = C.cast(L.f4la_b200_linear_algebra, C.c_void_p).value
-    rh.set_backend(la, None, None)
+    ela = C.cast(L.f4la_b200_exact_linear_algebra, C.c_void_p).value
+    rh.set_backend(la, ela, None)
     rh.reset()
     rh.set_mode(mode, 0, verbose)
     return L

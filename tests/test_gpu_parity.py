@@ -21,9 +21,7 @@ P31, P16, P8 = 1073741827, 65521, 251
 def test_gpu_matches_reference_fixtures(backend, path):
     n = 0
     for m, ref, meta in golden_io.load_cases(path):
-        if meta["kind"] != 0 or m.flags != 0:
-            continue
-        out, st = backend.reduce(m)
+        out, st = backend.reduce(m)       # F4 rounds and the final reduction step (pivots keyed by lead)
         assert out.same_rows(ref), f"{path}: {m.nru}+{m.nrl} rows x {m.ncl}+{m.ncr} cols"
         assert st["kernel_launches"] > 0
         n += 1
@@ -110,12 +108,31 @@ def test_gpu_vs_reference_every_f4_step(backend, name, p):
     gb, recs = rh.record_f4(systems.by_name(name, p), p, threads=4)
     n = 0
     for r in recs:
-        if r.kind != 0:
-            continue
         out, st = backend.reduce(r.matrix)
-        assert out.same_rows(r.result), (name, p, r.matrix.nru, r.matrix.nrl)
+        assert out.same_rows(r.result), (name, p, r.kind, r.matrix.nru, r.matrix.nrl)
         n += 1
-    assert n > 5
+    assert n > 5 and any(r.kind == 1 for r in recs)
+
+
+@pytest.mark.parametrize("path", [f for f in golden_io.fixture_files() if "cyclic-6" in f or "katsura-5_p65521" in f
+                                  or "eco-6_p251" in f], ids=os.path.basename)
+def test_gpu_normal_form_mode(backend, path):
+    """nf > 0 contract (la_ff_32.c:2672-2684): every lower row comes back as its own
+    normal form modulo the known pivots, not normalised, not inter-reduced."""
+    from msolve_b200.flat import FLAG_NORMALFORM
+    n = 0
+    for m, ref, meta in golden_io.load_cases(path):
+        if meta["kind"] != 0:
+            continue
+        m.flags = FLAG_NORMALFORM
+        out, st = backend.reduce(m)
+        chk, _, _ = oracle.reduce(m)
+        assert out.nrows == m.nrl and out.same_rows(chk)
+        if rh.available():
+            again, _, _, _ = rh.reference_la(m, laopt=2, threads=1)
+            assert out.same_rows(again)
+        n += 1
+    assert n > 3
 
 
 @pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
