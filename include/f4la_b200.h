@@ -73,6 +73,10 @@ typedef struct f4la_flat_matrix {
 /* known pivots are keyed by their lead column instead of by row index
  * (in_final_reduction_step, la_ff_32.c:2618-2622) */
 #define F4LA_FLAG_PIVOT_BY_LEAD 2u
+/* also return, for every lower row, the bit set of known pivots that were
+ * applied to it (non-zero multipliers): the `rba` arrays the reference fills
+ * while learning a trace (la_ff_32.c:1027-1036, data.h:209-213). */
+#define F4LA_FLAG_WANT_RBA    4u
 
 /* Result: rows of the reduced row echelon form, as CSR over ALL columns
  * (column ids in 0..ncl+ncr-1, ascending inside a row).  In echelon mode the
@@ -87,6 +91,10 @@ typedef struct f4la_flat_result {
     void     *cf;        /* [row_ptr[nrows]] coefficients, cf_bytes wide      */
     uint32_t *src_row;   /* [nrows] index of an input lower row whose
                             reduction produced this pivot (BINDEX/MULT donor) */
+    uint32_t *rba;       /* F4LA_FLAG_WANT_RBA: [nrl][rba_words] bit i%32 of
+                            word i/32 set iff pivot i was used; else NULL     */
+    uint32_t  rba_words; /* ceil(nru / 32)                                    */
+    uint32_t  reserved;
 } f4la_flat_result;
 
 /* Per-call measurements (device times from CUDA events on the ctx stream). */

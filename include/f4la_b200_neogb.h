@@ -35,6 +35,7 @@ typedef struct f4la_neogb_layout {
     uint32_t md_trace_level, md_np, md_la_ctime, md_la_rtime, md_num_zerored;
     uint32_t md_fc, md_laopt, md_nthrds, md_ff_bits, md_nf, md_in_final_reduction_step;
     uint32_t md_info_level, md_application_nr_mult, md_application_nr_add, md_application_nr_red;
+    uint32_t md_tr;             /* trace_t *tr, data.h:330 */
     /* row prelude, data.h:49-59 */
     uint32_t row_offset, row_length, row_preloop, row_coeffs, row_mult, row_bindex, row_deg;
     uint32_t unroll;            /* UNROLL (data.h:47), PRELOOP = len % UNROLL */
@@ -42,6 +43,11 @@ typedef struct f4la_neogb_layout {
 
 /* Must be called once before any of the entry points below; copies *layout. */
 int f4la_b200_neogb_configure(const f4la_neogb_layout *layout);
+
+/* Learning a trace (LEARN_TRACER, f4.c:360-369) needs the reference's own
+ * construct_trace(trace_t *, mat_t *) (tools.c:63-183, static in the unity
+ * build): the stub hands its address over.  Without it LEARN_TRACER aborts. */
+void f4la_b200_neogb_set_construct_trace(void (*fn)(void *trace, void *mat));
 
 /* CUDA device used by the calling host thread (default: $F4LA_B200_DEVICE or
  * 0).  The QQ multi-modular loop runs one F4 instance per OpenMP thread

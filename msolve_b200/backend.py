@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "f4la_b200_reduce", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
     "f4la_b200_free_result",
     # include/f4la_b200_neogb.h
-    "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_linear_algebra",
+    "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",
     "f4la_b200_exact_linear_algebra", "f4la_b200_neogb_get_totals",
 ]
 
@@ -131,6 +131,7 @@ class Backend:
         cm, res, st = m.c_struct(), CFlatResult(), CStats()
         self._check(self.lib.f4la_b200_reduce(self.ctx, C.byref(cm), C.byref(res), C.byref(st)))
         out = FlatResult.from_c(res)
+        out.attach_rba(res, m.nrl)
         self.lib.f4la_b200_free_result(C.byref(res))
         return out, st.as_dict()
 

@@ -49,7 +49,7 @@ struct f4la_ctx {
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
     DevBuf sched, items, flowflags;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
-    DevBuf is_piv, pividx, colmap, invmap, leads;
+    DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     int           use_levels = 0;       /* F4LA_B200_SCHED=levels: one launch per level (debug / A-B) */
     size_t        l2_budget = 0;
@@ -218,7 +218,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     cudaStream_t s = ctx->stream;
     const uint32_t launches0 = ctx->launches;
 
-    if (d.flags & ~(F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_NORMALFORM))
+    const bool want_rba = (d.flags & F4LA_FLAG_WANT_RBA) != 0;
+    if (want_rba && by_lead)
+        return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_WANT_RBA needs pivots keyed by row index");
+    if (d.flags & ~(F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_NORMALFORM | F4LA_FLAG_WANT_RBA))
         return fail(ctx, F4LA_ERR_ARG, "unknown flags 0x%x", d.flags);
     if (by_lead && nf_mode)
         return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD and F4LA_FLAG_NORMALFORM cannot be combined");
@@ -388,6 +391,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaStreamSynchronize(s));
     }
 
+    const uint32_t rba_words = (nru + 31) / 32;
+    if (want_rba && rba_words) OK(ensure(ctx, ctx->rba, (size_t)nrl * rba_words * 4 + 16));
+
     uint32_t epoch = 0;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
@@ -410,6 +416,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             f.p = p; f.pinv = pinv;
             CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
             launch_flow(ctx, T, f, wide);
+            if (want_rba && rba_words) {
+                dim3 grid(rba_words, g * (Rc / 128));
+                k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
+                                                as<uint32_t>(ctx->rba));
+                ctx->launches++;
+            }
             continue;
         }
         /* level 0 columns have no sources: V[j] already final */
@@ -572,6 +584,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             }
         }
     }
+    if (want_rba && rba_words) {
+        if (ctx->use_levels) return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_WANT_RBA is not available with F4LA_B200_SCHED=levels");
+        out->rba_words = rba_words;
+        out->rba = (uint32_t *)malloc((size_t)nrl * rba_words * 4);
+        CU(cudaMemcpyAsync(out->rba, ctx->rba.p, (size_t)nrl * rba_words * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        d2h_bytes += (uint64_t)nrl * rba_words * 4;
+    }
     CU(cudaEventRecord(ctx->ev[4], s));
     CU(cudaEventSynchronize(ctx->ev[4]));
 
@@ -693,7 +713,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
                       &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
-                      &ctx->invmap, &ctx->leads};
+                      &ctx->invmap, &ctx->leads, &ctx->rba};
     for (auto b : bufs) free_dev(*b);
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
@@ -766,7 +786,7 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result
 void f4la_b200_free_result(f4la_flat_result *res)
 {
     if (!res) return;
-    free(res->row_ptr); free(res->cols); free(res->cf); free(res->src_row);
+    free(res->row_ptr); free(res->cols); free(res->cf); free(res->src_row); free(res->rba);
     memset(res, 0, sizeof(*res));
 }
 

@@ -847,6 +847,26 @@ __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32
     out[(size_t)t * ncr + c] = v;
 }
 
+/* Reducer bit arrays (trace learning): bit (i % 32) of rba[row][i / 32] is set
+ * iff pivot i was applied to the row, i.e. its multiplier V[i][row] != 0.
+ * grid = (words, chunks * Rc / 128), block = 128 rows. */
+__global__ void k_rba_bits(const uint32_t *__restrict__ V, uint32_t nc, uint32_t Rc, uint32_t ncl,
+                           uint32_t chunk0, uint32_t nrl, uint32_t words, uint32_t *__restrict__ rba)
+{
+    const uint32_t w = blockIdx.x;
+    const uint32_t per = Rc / 128;
+    const uint32_t lc = blockIdx.y / per, lr = (blockIdx.y % per) * 128 + threadIdx.x;
+    const uint32_t row = (chunk0 + lc) * Rc + lr;
+    if (row >= nrl) return;
+    const uint32_t *Vc = V + (size_t)lc * nc * Rc;
+    uint32_t bits = 0;
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t col = 32 * w + b;
+        if (col < ncl && Vc[(size_t)col * Rc + lr] != 0) bits |= 1u << b;
+    }
+    rba[(size_t)row * words + w] = bits;
+}
+
 /* Lead (first stored) column of every lower row; 0xffffffff for an empty row. */
 __global__ void k_lower_leads(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
                               uint32_t nru, uint32_t nrl, uint32_t *__restrict__ leads)

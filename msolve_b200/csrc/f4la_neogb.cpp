@@ -27,6 +27,7 @@ namespace {
 
 f4la_neogb_layout L;
 bool g_configured = false;
+void (*g_construct_trace)(void *, void *) = nullptr;
 
 struct ThreadState {
     f4la_ctx *ctx = nullptr;
@@ -101,8 +102,9 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     const bool nf_mode = fld<int32_t>(st, L.md_nf) > 0;
     const bool final_step = fld<int32_t>(st, L.md_in_final_reduction_step) != 0;
     /* the reference records no trace in the final reduction step (la_ff_32.c:2713) */
-    if (trace_level == 1 /* LEARN_TRACER */ && !final_step)
-        die("LEARN_TRACER is not served by this backend yet");
+    const bool learn = trace_level == 1 /* LEARN_TRACER */ && !final_step && !nf_mode;
+    if (learn && !g_construct_trace)
+        die("LEARN_TRACER needs f4la_b200_neogb_set_construct_trace() (see INTEGRATION.md)");
 
     const uint32_t nru = fld<uint32_t>(mat, L.mat_nru), nrl = fld<uint32_t>(mat, L.mat_nrl);
     const uint32_t ncl = fld<uint32_t>(mat, L.mat_ncl), ncr = fld<uint32_t>(mat, L.mat_ncr);
@@ -171,6 +173,7 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     memset(&fm, 0, sizeof(fm));
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
     fm.flags = nf_mode ? F4LA_FLAG_NORMALFORM : final_step ? F4LA_FLAG_PIVOT_BY_LEAD : F4LA_FLAG_NONE;
+    if (learn) fm.flags |= F4LA_FLAG_WANT_RBA;
     fm.row_ptr = row_ptr; fm.cols = cols; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = pool;
     const double t_flat = now_ms();
 
@@ -180,6 +183,25 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     const int rc = f4la_b200_reduce(ctx(), &fm, &res, &stats);
     if (rc != F4LA_OK) die(f4la_b200_last_error(ctx()));
     const double t_dev = now_ms();
+
+    /* ---- learning: hand the reference's trace builder what it reads -------------
+     * construct_trace() (tools.c:63-183) looks at mat->tr[i] == NULL (row vanished),
+     * tr[i][BINDEX/MULT], rr[i][BINDEX/MULT] and the reducer bit arrays mat->rba[i].
+     * A lower row is kept iff it became a pivot row of the trailing block: these
+     * rows are linearly independent modulo the known pivots and span the new
+     * elements, which is all the application phase relies on (any maximal
+     * independent subset gives the same reduced rows). */
+    if (learn) {
+        std::vector<char> kept(nrl, 0);
+        for (uint32_t t = 0; t < res.nrows; ++t) kept[res.src_row[t]] = 1;
+        uint32_t **rba = fld<uint32_t **>(mat, L.mat_rba);
+        const uint32_t words = res.rba_words;
+        for (uint32_t i = 0; i < nrl; ++i) {
+            if (rba && rba[i] && res.rba) memcpy(rba[i], res.rba + (size_t)i * words, (size_t)words * 4);
+            if (!kept[i]) { free(tr[i]); tr[i] = nullptr; }
+        }
+        g_construct_trace(fld<void *>(st, L.md_tr), mat);
+    }
 
     /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
 #pragma omp parallel for num_threads(nthr) schedule(static)
@@ -286,6 +308,8 @@ int f4la_b200_neogb_configure(const f4la_neogb_layout *layout)
     g_configured = true;
     return F4LA_OK;
 }
+
+void f4la_b200_neogb_set_construct_trace(void (*fn)(void *trace, void *mat)) { g_construct_trace = fn; }
 
 void f4la_b200_neogb_set_device(int device)
 {

@@ -17,6 +17,7 @@ import numpy as np
 
 FLAG_NORMALFORM = 1
 FLAG_PIVOT_BY_LEAD = 2
+FLAG_WANT_RBA = 4
 
 _CF_DTYPE = {1: np.uint8, 2: np.uint16, 4: np.uint32}
 
@@ -36,7 +37,7 @@ class CFlatResult(C.Structure):
     _fields_ = [
         ("nrows", C.c_uint32), ("cf_bytes", C.c_uint32),
         ("row_ptr", C.c_void_p), ("cols", C.c_void_p), ("cf", C.c_void_p),
-        ("src_row", C.c_void_p),
+        ("src_row", C.c_void_p), ("rba", C.c_void_p), ("rba_words", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -141,6 +142,7 @@ class FlatResult:
     cols: np.ndarray      # uint32
     cf: np.ndarray
     src_row: Optional[np.ndarray] = None
+    rba: Optional[np.ndarray] = None      # uint32 [nrl, rba_words] when FLAG_WANT_RBA was set
 
     @property
     def nrows(self) -> int:
@@ -153,6 +155,10 @@ class FlatResult:
         src = _np_from_ptr(r.src_row, r.nrows, np.uint32) if r.src_row else None
         return cls(row_ptr, _np_from_ptr(r.cols, nnz, np.uint32),
                    _np_from_ptr(r.cf, nnz, _CF_DTYPE[r.cf_bytes]), src)
+
+    def attach_rba(self, r: CFlatResult, nrl: int) -> None:
+        if r.rba and r.rba_words:
+            self.rba = _np_from_ptr(r.rba, nrl * r.rba_words, np.uint32).reshape(nrl, r.rba_words)
 
     def same_rows(self, other: "FlatResult") -> bool:
         """Bit-exact equality of the echelon rows (columns and coefficients)."""

@@ -40,6 +40,18 @@ class PolySystem:
                 np.asarray(cfs, dtype=np.int32))
 
 
+def encode_integers(system: "PolySystem"):
+    """Signed integer coefficients as they stand (rational input of the QQ flow)."""
+    lens, exps, cfs = [], [], []
+    for f in system.polys:
+        lens.append(len(f))
+        for m, c in f.items():
+            exps.extend(m)
+            cfs.append(c)
+    return (np.asarray(lens, dtype=np.int32), np.asarray(exps, dtype=np.int32),
+            np.asarray(cfs, dtype=np.int32))
+
+
 def _add(f: Poly, m: Monomial, c: int) -> None:
     v = f.get(m, 0) + c
     if v:

@@ -513,6 +513,150 @@ void refh_fill_layout(f4la_neogb_layout *l)
     l->md_application_nr_mult = offsetof(md_t, application_nr_mult);
     l->md_application_nr_add = offsetof(md_t, application_nr_add);
     l->md_application_nr_red = offsetof(md_t, application_nr_red);
+    l->md_tr = offsetof(md_t, tr);
     l->row_offset = OFFSET; l->row_length = LENGTH; l->row_preloop = PRELOOP; l->row_coeffs = COEFFS;
     l->row_mult = MULT; l->row_bindex = BINDEX; l->row_deg = DEG; l->unroll = UNROLL;
+}
+
+/* construct_trace() is static in the reference's unity build; the drop-in
+ * stub passes its address to the backend. */
+static void construct_trace_thunk(void *trace, void *mat) { construct_trace((trace_t *)trace, (mat_t *)mat); }
+void *refh_construct_trace_ptr(void) { return (void *)construct_trace_thunk; }
+
+/* ------------------------------------------------------------------ */
+/* QQ multi-modular tracer flow (learn once, apply per prime)          */
+/* ------------------------------------------------------------------ */
+/* This is what msolve does for rational input (src/msolve/msolve.c:2145 ff.):
+ *   setup   : validate_input_data, check_and_set_meta_data_trace,
+ *             initialize_basis, import_input_data, calculate_divmask, sort,
+ *             remove_content_of_initial_basis          (msolve.c:2189-2240)
+ *   learn   : st->f4_qq_round = 1; core_gba(bs_qq, st, &err, p0)   (msolve.c:1628-1632)
+ *   apply   : st->f4_qq_round = 2; st->nthrds = 1; one core_gba per prime,
+ *             primes in parallel on OpenMP threads          (msolve.c:1815-1824)
+ * FGLM / CRT (which need FLINT) are not part of it. */
+
+static md_t *g_qq_st = NULL;
+static bs_t *g_qq_bs = NULL;
+static int   g_qq_nvars = 0;
+static void (*g_set_device)(int) = NULL;
+
+void refh_set_device_callback(void *fn) { g_set_device = (void (*)(int))fn; }
+
+/* FNV-1a over the reduced basis of a modular F4 run: lengths, coefficients, exponents */
+static uint64_t basis_digest(const bs_t *bs, int32_t *nelts, int64_t *nterms)
+{
+    uint64_t h = 1469598103934665603ULL;
+#define MIX(v) do { uint64_t x_ = (uint64_t)(v); for (int b_ = 0; b_ < 8; ++b_) { h ^= (x_ >> (8 * b_)) & 0xff; h *= 1099511628211ULL; } } while (0)
+    const ht_t *ht = bs->ht;
+    int64_t nt = 0;
+    for (bl_t i = 0; i < bs->lml; ++i) {
+        const hm_t *hm = bs->hm[bs->lmps[i]];
+        const cf32_t *cf = bs->cf_32[hm[COEFFS]];
+        MIX(hm[LENGTH]);
+        for (len_t k = 0; k < hm[LENGTH]; ++k) {
+            MIX(cf[k]);
+            const exp_t *e = ht->ev[hm[OFFSET + k]];
+            for (len_t v = 0; v < ht->evl; ++v) MIX(e[v]);
+        }
+        nt += hm[LENGTH];
+    }
+#undef MIX
+    if (nelts) *nelts = (int32_t)bs->lml;
+    if (nterms) *nterms = nt;
+    return h;
+}
+
+int refh_qq_setup(const int32_t *lens, const int32_t *exps, const int32_t *icfs,
+                  int32_t nvars, int32_t ngens, int32_t threads, int32_t laopt, int32_t info_level)
+{
+    int64_t nterms = 0;
+    for (int i = 0; i < ngens; ++i) nterms += lens[i];
+    /* rational coefficients: numerator, denominator per term (io.c:380-405) */
+    mpz_t **cfs = malloc((size_t)(2 * nterms) * sizeof(mpz_t *));
+    for (int64_t k = 0; k < nterms; ++k) {
+        cfs[2 * k] = malloc(sizeof(mpz_t)); cfs[2 * k + 1] = malloc(sizeof(mpz_t));
+        mpz_init(*cfs[2 * k]); mpz_set_si(*cfs[2 * k], icfs[k]);
+        mpz_init(*cfs[2 * k + 1]); mpz_set_si(*cfs[2 * k + 1], 1);
+    }
+    uint32_t field_char = 0;
+    int32_t mon_order = 0, elim_block_len = 0, nr_vars = nvars, nr_gens = ngens, nr_nf = 0, ht_size = 17;
+    int32_t nr_threads = threads, max_nr_pairs = 0, reset_ht = 0, la_option = laopt, use_signatures = 0;
+    int32_t reduce_gb = 1, truncate_lifting = 0, info = info_level;
+    int *invalid_gens = NULL;
+    if (validate_input_data(&invalid_gens, cfs, lens, &field_char, &mon_order, &elim_block_len, &nr_vars,
+                            &nr_gens, &nr_nf, &ht_size, &nr_threads, &max_nr_pairs, &reset_ht, &la_option,
+                            &use_signatures, &reduce_gb, &truncate_lifting, &info) == -1) return -1;
+    md_t *st = allocate_meta_data();
+    if (check_and_set_meta_data_trace(st, lens, exps, cfs, invalid_gens, field_char, mon_order, elim_block_len,
+                                      nr_vars, nr_gens, nr_nf, ht_size, nr_threads, max_nr_pairs, reset_ht,
+                                      la_option, use_signatures, reduce_gb, (uint32_t)1 << 30, nr_threads,
+                                      0, 0, info)) { free(st); return -2; }
+    bs_t *bs = initialize_basis(st, NULL);
+    import_input_data(bs, st, 0, st->ngens_input, lens, exps, cfs, invalid_gens);
+    calculate_divmask(bs->ht);
+    sort_r(bs->hm, (unsigned long)bs->ld, sizeof(hm_t *), initial_input_cmp, bs->ht);
+    remove_content_of_initial_basis(bs);
+    for (int64_t k = 0; k < 2 * nterms; ++k) { mpz_clear(*cfs[k]); free(cfs[k]); }
+    free(cfs); free(invalid_gens);
+    g_qq_st = st; g_qq_bs = bs; g_qq_nvars = nvars;
+    return 0;
+}
+
+typedef struct refh_qq_result {
+    uint64_t digest;
+    int32_t  nelts;
+    int64_t  nterms;
+    int32_t  err;
+    double   seconds;
+    double   la_seconds;
+} refh_qq_result;
+
+/* learning phase with prime p0 (all st->nthrds threads inside F4) */
+int refh_qq_learn(uint32_t p0, refh_qq_result *res)
+{
+    if (!g_qq_st) return -1;
+    memset(res, 0, sizeof(*res));
+    g_la_seconds = 0.0; g_la_calls = 0;
+    g_qq_st->f4_qq_round = 1;
+    int32_t err = 0;
+    const double t0 = realtime();
+    bs_t *bs = core_gba(g_qq_bs, g_qq_st, &err, p0);
+    res->seconds = realtime() - t0;
+    res->la_seconds = g_la_seconds;
+    res->err = err;
+    if (err || !bs) return 1;
+    res->digest = basis_digest(bs, &res->nelts, &res->nterms);
+    /* in the learning round the modular basis shares bs_qq's hash table
+     * (basis.c:398-402), which the application rounds still need */
+    free_basis_without_hash_table(&bs);
+    return 0;
+}
+
+/* application phase: one F4 replay per prime, `threads` primes at a time, host
+ * thread t bound to GPU t % ngpus when a backend with a device callback is installed */
+int refh_qq_apply(const uint32_t *primes, int32_t nprimes, int32_t threads, int32_t ngpus,
+                  refh_qq_result *res, double *wall_seconds)
+{
+    if (!g_qq_st || g_qq_st->trace_level != APPLY_TRACER) return -1;
+    g_qq_st->f4_qq_round = 2;
+    const int32_t old_thr = g_qq_st->nthrds, old_info = g_qq_st->info_level;
+    g_qq_st->nthrds = 1; g_qq_st->info_level = 0;
+    const double t0 = realtime();
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (int32_t i = 0; i < nprimes; ++i) {
+        if (g_set_device && ngpus > 0) g_set_device(omp_get_thread_num() % ngpus);
+        int32_t err = 0;
+        const double t1 = realtime();
+        bs_t *bs = core_gba(g_qq_bs, g_qq_st, &err, primes[i]);
+        memset(&res[i], 0, sizeof(res[i]));
+        res[i].err = err;
+        if (!err && bs) res[i].digest = basis_digest(bs, &res[i].nelts, &res[i].nterms);
+        res[i].seconds = realtime() - t1;
+        if (bs) {
+            if (err) free(bs); else free_basis_and_only_local_hash_table_data(&bs);
+        }
+    }
+    if (wall_seconds) *wall_seconds = realtime() - t0;
+    g_qq_st->nthrds = old_thr; g_qq_st->info_level = old_info;
+    return 0;
 }

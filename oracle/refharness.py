@@ -182,6 +182,66 @@ def reference_la(m: FlatMatrix, laopt: int = 2, threads: int = 1):
     return out, sec.value, units.value, apps.value
 
 
+class QQResult(C.Structure):
+    _fields_ = [("digest", C.c_uint64), ("nelts", C.c_int32), ("nterms", C.c_int64), ("err", C.c_int32),
+                ("seconds", C.c_double), ("la_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def qq_setup(system, threads: int = 1, laopt: int = 2, info_level: int = 0) -> None:
+    """Rational input (integer coefficients of the formula) for the tracer flow."""
+    from msolve_b200.systems import encode_integers
+    lens, exps, cfs = encode_integers(system)
+    L = lib()
+    L.refh_qq_setup.restype = C.c_int
+    L.refh_qq_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    rc = L.refh_qq_setup(lens.ctypes.data, exps.ctypes.data, cfs.ctypes.data, system.nvars, len(lens),
+                         threads, laopt, info_level)
+    if rc != 0:
+        raise RuntimeError(f"refh_qq_setup failed: {rc}")
+
+
+def qq_learn(p0: int) -> dict:
+    L = lib()
+    L.refh_qq_learn.restype = C.c_int
+    L.refh_qq_learn.argtypes = [C.c_uint32, C.POINTER(QQResult)]
+    r = QQResult()
+    rc = L.refh_qq_learn(p0, C.byref(r))
+    d = r.as_dict(); d["rc"] = rc
+    return d
+
+
+def qq_apply(primes, threads: int = 1, ngpus: int = 0):
+    """-> (list of per-prime dicts, wall seconds)"""
+    L = lib()
+    L.refh_qq_apply.restype = C.c_int
+    L.refh_qq_apply.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(QQResult), C.POINTER(C.c_double)]
+    arr = np.asarray(primes, dtype=np.uint32)
+    res = (QQResult * len(arr))()
+    wall = C.c_double()
+    rc = L.refh_qq_apply(arr.ctypes.data, len(arr), threads, ngpus, res, C.byref(wall))
+    if rc != 0:
+        raise RuntimeError(f"refh_qq_apply failed: {rc} (learn first)")
+    return [r.as_dict() for r in res], wall.value
+
+
+def set_device_callback(fn) -> None:
+    lib().refh_set_device_callback.argtypes = [C.c_void_p]
+    lib().refh_set_device_callback(C.cast(fn, C.c_void_p).value if fn is not None else None)
+
+
+def primes_above(start: int, n: int):
+    """n successive primes > start (trial division; 31-bit)."""
+    out, c = [], start + 1
+    while len(out) < n:
+        if c % 2 and all(c % d for d in range(3, int(c ** 0.5) + 1, 2)):
+            out.append(c)
+        c += 1
+    return out
+
+
 def struct_layout() -> List[int]:
     buf = (C.c_uint64 * 128)()
     n = lib().refh_struct_layout(buf, 128)

@@ -14,6 +14,10 @@ def install_backend(mode=rh.MODE_BACKEND, verbose=0):
     lay = (C.c_uint32 * 64)()
     rh.lib().refh_fill_layout(lay)
     assert L.f4la_b200_neogb_configure(lay) == 0
+    rh.lib().refh_construct_trace_ptr.restype = C.c_void_p
+    L.f4la_b200_neogb_set_construct_trace.argtypes = [C.c_void_p]
+    L.f4la_b200_neogb_set_construct_trace(rh.lib().refh_construct_trace_ptr())
+    rh.set_device_callback(L.f4la_b200_neogb_set_device)
     la = C.cast(L.f4la_b200_linear_algebra, C.c_void_p).value
     ela = C.cast(L.f4la_b200_exact_linear_algebra, C.c_void_p).value
     rh.set_backend(la, ela, None)

@@ -60,5 +60,5 @@ def test_layout_descriptor_matches_reference_when_available():
     rh.lib().refh_fill_layout(buf)
     L = backend.load_library()
     assert L.f4la_b200_neogb_configure(buf) == 0
-    assert buf[0] == 43 * 4          # sizeof(f4la_neogb_layout): 43 uint32 fields
-    assert list(buf[36:43]) == [6, 5, 4, 3, 2, 1, 0] or buf[35] == 6
+    assert buf[0] == 44 * 4          # sizeof(f4la_neogb_layout): 44 uint32 fields
+    assert list(buf[36:43]) == [6, 5, 4, 3, 2, 1, 0]
