@@ -241,6 +241,20 @@ def run_gpu(args, rank, world):
     el_v, aggs_v, clocks = timed(pass_resident, "device-resident")
     el_e, aggs_e, _ = timed(lambda: pass_host()[0], "host buffers (e2e)")
 
+    # the matrices are not needed any more
+    for rm in resident:
+        rm.release()
+    for pm in pinned:
+        pm.free()
+    be.close()
+    qq = None
+    if not args.no_qq:
+        try:
+            qq = run_qq(args, rank, world, local, dist, torch)
+        except Exception as e:          # the headline number must survive a failure of the extra block
+            qq = {"error": repr(e)}
+            log(f"[bench] rank {rank}: QQ block failed: {e!r}")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -283,6 +297,7 @@ def run_gpu(args, rank, world):
                      "bytes_per_unit": bytes_per_unit, "kernel_ms_per_step": ms_reduce},
         "cpu_baseline": cpu,
         "f4_total_seconds_with_gpu_la": f4_s,
+        "qq": qq,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -300,6 +315,66 @@ def cpu_sample(recs, units_per):
             break
         idx.append(i); cum += units_per[i]
     return idx, cum
+
+
+def run_qq(args, rank, world, local, dist, torch):
+    """QQ multi-modular tracer loop (BASELINE config 5): learn once, then replay the
+    trace for independent primes.  Primes are sharded over the ranks (GPU = rank),
+    every rank drives its GPU with a fixed number of host threads; the only
+    collective is the gather of the per-prime results (here: 64-bit digests of the
+    modular bases; msolve gathers residues for CRT, msolve.c:2694-2712)."""
+    import gpu_helpers
+    from msolve_b200 import systems
+    from oracle import refharness as rh
+    system = systems.by_name(args.qq_system)
+    threads = max(1, (os.cpu_count() or 8) // 8)          # fixed per GPU, whatever N is
+    per_rank = args.qq_primes_per_thread * threads
+    all_primes = rh.primes_above(1 << 30, 1 + per_rank * world)
+    from msolve_b200 import sharding
+    p0, mine = all_primes[0], sharding.shard(all_primes[1:], rank, world)[:per_rank]
+    L = gpu_helpers.install_backend()
+    try:
+        rh.qq_setup(system, threads=threads)
+        learn = rh.qq_learn(p0)
+        assert learn["rc"] == 0
+        gpu_helpers.neogb_totals(L)                       # reset
+        rh.qq_apply(mine[:threads], threads=threads, ngpus=1)    # warm-up
+        gpu_helpers.neogb_totals(L)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res, wall = rh.qq_apply(mine, threads=threads, ngpus=1)
+        # NCCL all-gather of the per-prime results (msolve: residues for CRT on the host)
+        parts = sharding.gather_uint64([r["digest"] for r in res], dist if world > 1 else None, device="cuda")
+        torch.cuda.synchronize()
+        assert sum(len(x) for x in parts) == per_rank * world
+        el = time.perf_counter() - t0
+        tot = gpu_helpers.neogb_totals(L)
+    finally:
+        gpu_helpers.uninstall_backend()
+    assert all(r["err"] == 0 and r["nelts"] == learn["nelts"] for r in res)
+    if world > 1:
+        t = torch.tensor([el], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    out = {"metric": "QQ primes/s (F4 tracer application phase)", "system": f"{args.qq_system} over QQ",
+           "value": per_rank * world / el, "unit": "primes/s", "n_gpus": world, "primes": per_rank * world,
+           "host_threads_per_gpu": threads, "seconds": el, "scaling": "weak",
+           "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"],
+           "la_share_of_host_thread_time": tot["ms_total"] / 1e3 / max(1e-9, sum(r["seconds"] for r in res)),
+           "la_ms_per_prime": tot["ms_total"] / max(1, len(res)),
+           "collective": "nccl all_gather of per-prime results" if world > 1 else "none (1 GPU)"}
+    if rank == 0 and not args.no_qq_cpu:
+        rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
+        rh.qq_setup(system, threads=os.cpu_count() or 1)
+        rh.qq_learn(p0)
+        ncpu = os.cpu_count() or 1
+        sample = all_primes[1:1 + 2 * ncpu]
+        _, wall_cpu = rh.qq_apply(sample, threads=ncpu)
+        out["cpu_baseline"] = {"value": len(sample) / wall_cpu, "unit": "primes/s", "cores": ncpu, "kind": "reference",
+                               "sample": f"{len(sample)} primes, reference core_gba apply, one prime per thread"}
+    return out
 
 
 def cpu_baseline(recs, units_per, threads, repeats):
@@ -377,6 +452,10 @@ def main():
     ap.add_argument("--workload", default="katsura-12")
     ap.add_argument("--prime", type=int, default=P31)
     ap.add_argument("--per-matrix", action="store_true", help="log per-matrix phase times (stderr)")
+    ap.add_argument("--no-qq", action="store_true", help="skip the QQ multi-modular block")
+    ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
+    ap.add_argument("--qq-system", default="katsura-10")
+    ap.add_argument("--qq-primes-per-thread", type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

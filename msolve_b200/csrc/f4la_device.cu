@@ -47,7 +47,9 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf sched, items, flowflags;
+    DevBuf sched, items, flowflags, nzflags, mailbox;
+    size_t        panel_smem_optin = 0;
+    int           ge_panel = 0;         /* F4LA_B200_GE=panel: cluster/shared-memory panels (experimental, slower on low-rank blocks) */
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
@@ -379,6 +381,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         OK(ensure(ctx, ctx->sched, ((size_t)na + ncr + 1) * 4));
         OK(ensure(ctx, ctx->items, ((size_t)n_items + 1) * 4));
         OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
+        OK(ensure(ctx, ctx->nzflags, (size_t)G * nc + 16));
         OK(ensure_host(ctx, ctx->h_dense, (size_t)n_items * 4 + 64));
         memcpy(ctx->h_dense.p, items.data(), (size_t)n_items * 4);
         CU(cudaMemcpyAsync(ctx->items.p, ctx->h_dense.p, (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
@@ -398,9 +401,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
+        if (!ctx->use_levels) CU(cudaMemsetAsync(ctx->nzflags.p, 0, (size_t)g * nc, s));
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
         k_scatter_lower<<<blocks_for_warps(rows_here), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
                                                                     d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
+                                                                    ctx->use_levels ? nullptr : as<uint8_t>(ctx->nzflags),
                                                                     as<uint32_t>(ctx->V), d_err);
         ctx->launches++;
         if (!ctx->use_levels) {
@@ -411,6 +416,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             f.sched = as<uint32_t>(ctx->sched); f.items = as<uint32_t>(ctx->items);
             f.n_items = n_items; f.G = g;
             f.flags = as<uint32_t>(ctx->flowflags); f.epoch = ++epoch;
+            f.nz = as<uint8_t>(ctx->nzflags);
             f.counter = d_err + 4; f.err = d_err;
             f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
             f.p = p; f.pinv = pinv;
@@ -458,9 +464,42 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
         CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
         CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
+        GEState *h_state = (GEState *)ctx->h_small.p;
+        /* blocked path when a panel of at least 8 columns fits the cluster's shared memory */
+        const size_t smem_cap = (size_t)216 * 1024;
+        const size_t fixed = (size_t)nrl * 4 + nrl + 64;
+        uint32_t slots = fixed < smem_cap ? (uint32_t)((smem_cap - fixed) / ((size_t)nrl * 4)) : 0;
+        if (slots > (uint32_t)(kPanelMaxCols / kPanelCluster)) slots = kPanelMaxCols / kPanelCluster;
+        if (slots >= 1 && ctx->ge_panel) {
+            const uint32_t B = slots * kPanelCluster;
+            const size_t panel_smem = (size_t)slots * nrl * 4 + fixed;
+            const size_t upd_smem = (size_t)nrl * 4;
+            if (panel_smem > ctx->panel_smem_optin) {
+                CU(cudaFuncSetAttribute(k_ge_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                CU(cudaFuncSetAttribute(k_ge_block_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                ctx->panel_smem_optin = smem_cap;
+            }
+            OK(ensure(ctx, ctx->mailbox, 2 * kPanelMaxCols * 4));
+            for (uint32_t c0 = 0; c0 < ncr; c0 += B) {
+                const uint32_t c1 = c0 + B < ncr ? c0 + B : ncr;
+                k_ge_panel_smem<<<kPanelCluster, kPanelThreads, panel_smem, s>>>(
+                    Dm, ld, nrl, c0, c1, slots, as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
+                    as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                    as<uint32_t>(ctx->pivinv), as<uint32_t>(ctx->mailbox), p, pinv);
+                ctx->launches++;
+                if (c1 < ncr) {
+                    k_ge_block_update<<<ncr - c1, kUpdateThreads, upd_smem, s>>>(
+                        Dm, ld, nrl, c1, ncr, as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
+                    ctx->launches++;
+                }
+            }
+            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s));
+        } else {
         k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
         ctx->launches++;
-        GEState *h_state = (GEState *)ctx->h_small.p;
         for (uint32_t done_steps = 0;;) {
             const int batch = 16;
             for (int k = 0; k < batch; ++k) {
@@ -479,6 +518,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             if (h_state->done) break;
             if (done_steps > maxrank + 2 * batch)
                 return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+        }
         }
         rank = h_state->rank;
     }
@@ -698,6 +738,8 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     const char *sched = getenv("F4LA_B200_SCHED");
     ctx->use_levels = sched && !strcmp(sched, "levels");
+    const char *ge = getenv("F4LA_B200_GE");
+    ctx->ge_panel = ge && !strcmp(ge, "panel");
     const char *bud = getenv("F4LA_B200_L2_MB");
     ctx->l2_budget = bud && atoi(bud) > 0 ? (size_t)atoi(bud) << 20 : kL2BudgetDefault;
     return ctx;
@@ -711,7 +753,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->nzflags, &ctx->mailbox, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba};
     for (auto b : bufs) free_dev(*b);

@@ -62,11 +62,15 @@ __device__ __forceinline__ uint32_t mulmod(uint32_t a, uint32_t b, uint32_t p, u
  * mod_p_inverse_32, tools.h:95-122). */
 __device__ __forceinline__ uint32_t modinv(uint32_t val, uint32_t p)
 {
-    int64_t a = p, b = val % p, c = 1, d = 0;
+    /* p < 2^31: remainders fit 32 bits (cheap divisions), Bezout coefficients fit int64 */
+    uint32_t a = p, b = val % p;
+    int64_t c = 1, d = 0;
     while (b != 0) {
-        const int64_t e = a / b;
-        int64_t f = b; b = a - e * f; a = f;
-        f = c; c = d - e * f; d = f;
+        const uint32_t e = a / b;
+        const uint32_t r = a - e * b;
+        a = b; b = r;
+        const int64_t f = d - (int64_t)e * c;
+        d = c; c = f;
     }
     if (d < 0) d += p;
     return (uint32_t)d;
@@ -288,7 +292,7 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
                                 const void *__restrict__ cf, uint32_t cf_bytes,
                                 uint32_t nru, uint32_t nrl, uint32_t nc, uint32_t p,
                                 uint32_t chunk0, uint32_t nchunks, uint32_t Rc,
-                                const uint32_t *__restrict__ colmap,
+                                const uint32_t *__restrict__ colmap, uint8_t *__restrict__ nz,
                                 uint32_t *__restrict__ V, uint32_t *__restrict__ err)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -305,7 +309,9 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
             uint32_t j = cols[k];
             if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
             if (colmap) j = colmap[j];
-            Vc[(size_t)j * Rc + lr] = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
+            const uint32_t v = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
+            Vc[(size_t)j * Rc + lr] = v;
+            if (nz && v) nz[(size_t)lc * nc + j] = 1;     /* columns without sources keep this flag */
         }
     }
 }
@@ -499,6 +505,7 @@ struct FlowArgs {
     const uint32_t *items;      /* (pos << 5) | (count << 1) | is_long            */
     uint32_t        n_items, G;
     uint32_t       *flags;      /* [G][nc] ready epoch of each column             */
+    uint8_t        *nz;         /* [G][nc] 1 iff the column's vector is non-zero   */
     uint32_t        epoch;
     uint32_t       *counter;    /* work counter, zeroed before the launch         */
     uint32_t       *err;        /* error bits (kErrWatchdog)                      */
@@ -535,6 +542,7 @@ __device__ __forceinline__ uint4 ld_cg_u4(const uint4 *ptr)
 template <int T, bool WIDE>
 __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_t *__restrict__ Vc,
                                                 const uint32_t *__restrict__ flagc,
+                                                const uint8_t *__restrict__ nzc,
                                                 uint32_t e0, uint32_t e1, uint32_t slot, uint32_t nslots,
                                                 uint32_t lane, uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
 {
@@ -563,17 +571,24 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
             }
         }
         __syncwarp();       /* order every lane's V loads after the lanes' acquires */
-        /* Lanes >= n hold the entry {source 0, coefficient 0}: it is loaded and
-         * multiplied like any other (column 0 always exists) and adds nothing,
-         * which keeps the loop free of predicates. */
-        const uint32_t nu = (n + U - 1) / U * U;
-        for (uint32_t u0 = 0; u0 < nu; u0 += U) {
+        /* Sources whose vector is entirely zero in this chunk contribute nothing:
+         * the lower rows come clustered, 15-60 % of the (pivot, chunk) vectors are
+         * zero, so their loads and multiplies are skipped altogether. */
+        uint32_t live = __ballot_sync(0xffffffffu, lane < n && __ldcg(&nzc[en.x]) != 0);
+        since_fold += __popc(live);
+        while (live) {
             uint32_t src[U], cf[U];
             uint4 v[U][T];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                src[u] = __shfl_sync(0xffffffffu, en.x, (u0 + u) & 31);
-                cf[u]  = __shfl_sync(0xffffffffu, en.y, (u0 + u) & 31);
+                /* next live entry; when the group runs out, repeat the last one with coefficient 0 */
+                const bool ok = live != 0;
+                const uint32_t idx = ok ? (uint32_t)__ffs(live) - 1 : 0;
+                live &= live - (ok ? 1u : 0u);
+                const uint32_t sx = __shfl_sync(0xffffffffu, en.x, idx);
+                const uint32_t sy = __shfl_sync(0xffffffffu, en.y, idx);
+                src[u] = ok ? sx : (u ? src[u - 1] : 0u);
+                cf[u]  = ok ? sy : 0u;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -596,7 +611,6 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                 }
             }
         }
-        since_fold += 32;
         if (since_fold >= kFoldEvery) {
             since_fold = 0;
 #pragma unroll
@@ -631,6 +645,7 @@ k_pull_flow(const FlowArgs A)
         const bool is_long = it & 1u;
         uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
         uint32_t *flagc = A.flags + (size_t)chunk * A.nc;
+        uint8_t *nzc = A.nz + (size_t)chunk * A.nc;
 
         uint64_t lo[T][4], hi[T][4];
 #pragma unroll
@@ -642,11 +657,12 @@ k_pull_flow(const FlowArgs A)
             if (warp < cnt) {
                 const uint32_t j = A.sched[pos + warp];
                 const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-                flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, 0, 1, lane, lo, hi);
+                flow_accumulate<T, WIDE>(A, Vc, flagc, nzc, e0, e1, 0, 1, lane, lo, hi);
                 const bool to_out = j >= A.ncl;
                 uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                        : Vc + (size_t)j * A.Rc;
                 const uint4 *init = reinterpret_cast<const uint4 *>(Vc + (size_t)j * A.Rc) + lane;
+                uint32_t nonzero = 0;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
                     const uint4 x = init[t * 32];
@@ -656,11 +672,13 @@ k_pull_flow(const FlowArgs A)
                     r.z = fold_lohi<WIDE>(lo[t][2] + x.z, hi[t][2], A.p, A.pinv);
                     r.w = fold_lohi<WIDE>(lo[t][3] + x.w, hi[t][3], A.p, A.pinv);
                     reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
+                    nonzero |= r.x | r.y | r.z | r.w;
                 }
                 if (!to_out) {
+                    const bool any = __any_sync(0xffffffffu, nonzero != 0);
                     __threadfence();
                     __syncwarp();
-                    if (lane == 0) st_release(&flagc[j], A.epoch);
+                    if (lane == 0) { nzc[j] = any ? 1 : 0; st_release(&flagc[j], A.epoch); }
                 }
             }
             continue;       /* the two barriers at the loop head keep the CTA together */
@@ -668,7 +686,7 @@ k_pull_flow(const FlowArgs A)
 
         const uint32_t j = A.sched[pos];
         const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-        flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, warp, kWarpsPerBlock, lane, lo, hi);
+        flow_accumulate<T, WIDE>(A, Vc, flagc, nzc, e0, e1, warp, kWarpsPerBlock, lane, lo, hi);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             uint4 r;
@@ -682,16 +700,19 @@ k_pull_flow(const FlowArgs A)
         const bool to_out = j >= A.ncl;
         uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                : Vc + (size_t)j * A.Rc;
+        int nonzero = 0;
         for (uint32_t r = threadIdx.x; r < (uint32_t)(T * kRowsPerT); r += kSolveThreads) {
             uint64_t s = Vc[(size_t)j * A.Rc + r];
 #pragma unroll
             for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w][r];
-            dst[r] = mod_u64(s, A.p, A.pinv);
+            const uint32_t v = mod_u64(s, A.p, A.pinv);
+            dst[r] = v;
+            nonzero |= v != 0;
         }
         if (!to_out) {
             __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release(&flagc[j], A.epoch);
+            nonzero = __syncthreads_or(nonzero);
+            if (threadIdx.x == 0) { nzc[j] = nonzero ? 1 : 0; st_release(&flagc[j], A.epoch); }
         }
     }
 }
@@ -826,6 +847,164 @@ __global__ void k_ge_eliminate(uint32_t *__restrict__ D, uint64_t ld, uint32_t n
     }
     any = __syncthreads_or(any);
     if (threadIdx.x == 0) colflag[cc] = (uint8_t)(any != 0);
+}
+
+/* ---- blocked right-looking Gauss-Jordan ---------------------------------- */
+/* The trailing block is swept in panels of up to 64 columns:
+ *   k_ge_panel_smem  : ONE cluster of 8 CTAs holds the panel in its shared
+ *                      memory (column ci lives in CTA ci % 8).  Columns are
+ *                      visited in order; the owner looks for a pivot, publishes
+ *                      {row, inverse} in a mailbox and the (final) pivot column
+ *                      in global memory, one cluster barrier later every CTA
+ *                      eliminates the pivot from the panel columns it owns.
+ *   k_ge_block_update: one CTA per column right of the panel replays the
+ *                      panel's pivots on its column, held in shared memory.
+ * Pivot columns are final once chosen (they carry the multipliers), pivot rows
+ * stay unnormalised (k_ge_extract applies the inverse), exactly as in the
+ * column-at-a-time kernels above, which remain the fallback for blocks whose
+ * columns do not fit shared memory. */
+constexpr int kPanelCluster = 8;
+constexpr int kPanelThreads = 512;
+constexpr int kPanelMaxCols = 64;
+constexpr int kUpdateThreads = 256;
+constexpr uint32_t kNoPivot = 0xffffffffu;
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+/* dynamic smem: [slots][nrows] columns | [nrows] pivot column | [nrows] used bytes */
+__global__ void __cluster_dims__(kPanelCluster, 1, 1) __launch_bounds__(kPanelThreads)
+k_ge_panel_smem(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t c0, uint32_t c1, uint32_t slots,
+                uint8_t *used, uint8_t *ispiv, GEState *st, uint32_t *pivcol, uint32_t *pivrow,
+                uint32_t *pivinv, uint32_t *mailbox, uint32_t p, uint64_t pinv)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t *s_cols = smem;
+    uint32_t *s_f = smem + (size_t)slots * nrows;
+    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_f + nrows);
+    __shared__ uint32_t s_min, s_inv;
+    const uint32_t q = cluster_ctarank();
+    const uint32_t tid = threadIdx.x;
+    const uint32_t B = c1 - c0;
+
+    for (uint32_t sl = 0; sl < slots; ++sl) {
+        const uint32_t ci = sl * kPanelCluster + q;
+        if (ci >= B) break;
+        const uint32_t *g = D + (size_t)(c0 + ci) * ld;
+        for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_cols[(size_t)sl * nrows + r] = g[r];
+    }
+    for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_used[r] = used[r];
+    uint32_t rank = st->rank;
+    if (q == 0 && tid == 0) st->cur_col = rank;          /* first pivot of this panel, for the block update */
+    __syncthreads();
+
+    for (uint32_t ci = 0; ci < B; ++ci) {
+        const uint32_t c = c0 + ci;
+        if (ci % kPanelCluster == q) {                   /* owner: look for a pivot */
+            uint32_t *col = s_cols + (size_t)(ci / kPanelCluster) * nrows;
+            if (tid == 0) s_min = kNoPivot;
+            __syncthreads();
+            for (uint32_t r = tid; r < nrows; r += kPanelThreads)
+                if (col[r] != 0 && !s_used[r]) { atomicMin(&s_min, r); break; }
+            __syncthreads();
+            const uint32_t piv = s_min;
+            if (piv != kNoPivot) {
+                uint32_t *g = D + (size_t)c * ld;
+                for (uint32_t r = tid; r < nrows; r += kPanelThreads) g[r] = col[r];
+                if (tid == 0) s_inv = modinv(col[piv], p);
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid == 0) { mailbox[2 * ci] = piv; mailbox[2 * ci + 1] = piv != kNoPivot ? s_inv : 0; }
+        }
+        cluster_barrier();
+        const uint32_t piv = __ldcg(&mailbox[2 * ci]);
+        if (piv == kNoPivot) continue;                   /* uniform over the cluster */
+        const uint32_t inv = __ldcg(&mailbox[2 * ci + 1]);
+        if (q == 0 && tid == 0) {
+            pivcol[rank] = c; pivrow[rank] = piv; pivinv[rank] = inv;
+            used[piv] = 1; ispiv[c] = 1;
+        }
+        rank++;
+        /* multipliers = the pivot column, now final in global memory */
+        const uint32_t *g = D + (size_t)c * ld;
+        for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_f[r] = __ldcg(&g[r]);
+        if (tid == 0) s_used[piv] = 1;
+        __syncthreads();
+        for (uint32_t sl = 0; sl < slots; ++sl) {
+            const uint32_t cj = sl * kPanelCluster + q;
+            if (cj >= B) break;
+            if (cj <= ci) continue;
+            uint32_t *col = s_cols + (size_t)sl * nrows;
+            const uint32_t sc = mulmod(col[piv], inv, p, pinv);
+            if (sc == 0) continue;                       /* uniform over the CTA */
+            for (uint32_t r = tid; r < nrows; r += kPanelThreads) {
+                const uint32_t f = s_f[r];
+                if (f && r != piv) {
+                    const uint32_t t = mulmod(f, sc, p, pinv);
+                    const uint32_t v = col[r];
+                    col[r] = v >= t ? v - t : v + p - t;
+                }
+            }
+        }
+        __syncthreads();                                 /* s_f is reused by the next pivot */
+    }
+    /* the panel is final: write it back (pivot columns were stored when chosen and
+     * have not changed since) */
+    for (uint32_t sl = 0; sl < slots; ++sl) {
+        const uint32_t ci = sl * kPanelCluster + q;
+        if (ci >= B) break;
+        uint32_t *g = D + (size_t)(c0 + ci) * ld;
+        for (uint32_t r = tid; r < nrows; r += kPanelThreads) g[r] = s_cols[(size_t)sl * nrows + r];
+    }
+    if (q == 0 && tid == 0) { st->rank = rank; st->next_col = c1; }
+}
+
+/* replay pivots [st->cur_col, st->rank) (those of the last panel) on every column >= c1 */
+__global__ void __launch_bounds__(kUpdateThreads)
+k_ge_block_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t c1, uint32_t ncr,
+                  const GEState *__restrict__ st, const uint32_t *__restrict__ pivcol,
+                  const uint32_t *__restrict__ pivrow, const uint32_t *__restrict__ pivinv,
+                  uint32_t p, uint64_t pinv)
+{
+    extern __shared__ uint32_t s_col[];
+    const uint32_t k0 = st->cur_col, k1 = st->rank;
+    if (k0 >= k1) return;
+    const uint32_t c = c1 + blockIdx.x;
+    if (c >= ncr) return;
+    uint32_t *g = D + (size_t)c * ld;
+    for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) s_col[r] = g[r];
+    __syncthreads();
+    bool touched = false;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t piv = pivrow[k];
+        const uint32_t sc = mulmod(s_col[piv], pivinv[k], p, pinv);
+        if (sc != 0) {                                   /* uniform over the CTA */
+            touched = true;
+            const uint32_t *fcol = D + (size_t)pivcol[k] * ld;
+            for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) {
+                const uint32_t f = __ldg(&fcol[r]);
+                if (f && r != piv) {
+                    const uint32_t t = mulmod(f, sc, p, pinv);
+                    const uint32_t v = s_col[r];
+                    s_col[r] = v >= t ? v - t : v + p - t;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (touched)
+        for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) g[r] = s_col[r];
 }
 
 /* Reduced echelon rows, dense: row t = pivot rank-1-t (decreasing lead). */

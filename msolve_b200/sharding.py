@@ -1,0 +1,58 @@
+"""Prime sharding of the QQ multi-modular loop across ranks (one rank per GPU).
+
+msolve runs the application phase of its tracer for a batch of independent
+primes in parallel (reference src/msolve/msolve.c:1815-1824, one prime per
+OpenMP thread) and only needs the per-prime results on the host for CRT lifting
+(msolve.c:2694-2740).  Across GPUs the same loop shards by prime: no exchange on
+the data path, one gather of the results at the end of a batch.  The functions
+here are backend agnostic (NCCL on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+
+def shard(items: Sequence[int], rank: int, world: int) -> List[int]:
+    """Round-robin shard: item k goes to rank k % world (msolve hands prime i to
+    thread i; with G GPUs prime i goes to GPU i % G)."""
+    return list(items[rank::world])
+
+
+def unshard(per_rank: Sequence[Sequence[int]]) -> List[int]:
+    """Inverse of :func:`shard`: interleave the per-rank lists back into batch order."""
+    world = len(per_rank)
+    n = sum(len(x) for x in per_rank)
+    out = [0] * n
+    for r, xs in enumerate(per_rank):
+        for k, v in enumerate(xs):
+            out[r + k * world] = v
+    return out
+
+
+def gather_uint64(local: Sequence[int], dist=None, device="cpu") -> List[List[int]]:
+    """All-gather one 64-bit value per local item (variable counts per rank).
+    Returns the per-rank lists on every rank.  ``dist`` is torch.distributed (or
+    None / uninitialised for a single process)."""
+    if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [list(int(x) for x in local)]
+    import torch
+    world = dist.get_world_size()
+    n = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    nmax = int(max(int(c.item()) for c in counts))
+    # uint64 -> two non-negative int64 halves (NCCL / gloo have no uint64)
+    arr = np.zeros((max(nmax, 1), 2), dtype=np.int64)
+    for k, v in enumerate(local):
+        arr[k, 0] = int(v) & 0xffffffff
+        arr[k, 1] = (int(v) >> 32) & 0xffffffff
+    t = torch.from_numpy(arr).to(device)
+    bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(bufs, t)
+    out = []
+    for r in range(world):
+        b = bufs[r].cpu().numpy()
+        out.append([int(b[k, 0]) | (int(b[k, 1]) << 32) for k in range(int(counts[r].item()))])
+    return out

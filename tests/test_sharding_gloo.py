@@ -1,0 +1,70 @@
+"""CPU tests of the multi-rank path (world_size 2, gloo): primes of the QQ
+multi-modular loop are sharded over the ranks, every rank replays the trace
+for its primes (here with the reference's CPU linear algebra, there is no GPU
+in this container), the per-prime results are gathered, and the gathered set
+equals the single-process run."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from msolve_b200 import sharding
+from oracle import refharness as rh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_roundtrip():
+    items = list(range(100, 117))
+    for world in (1, 2, 3, 8):
+        parts = [sharding.shard(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == items
+        assert sharding.unshard(parts) == items
+
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch.distributed as dist
+from msolve_b200 import sharding, systems
+from oracle import refharness as rh
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+primes = rh.primes_above(1 << 30, 7)
+rh.set_mode(rh.MODE_REFERENCE)
+rh.qq_setup(systems.by_name("katsura-6"), threads=1)
+assert rh.qq_learn(primes[0])["rc"] == 0
+mine = sharding.shard(primes[1:], rank, world)
+res, _ = rh.qq_apply(mine, threads=1)
+assert all(r["err"] == 0 for r in res)
+parts = sharding.gather_uint64([r["digest"] for r in res], dist)
+if rank == 0:
+    print("RESULT " + json.dumps(sharding.unshard(parts)))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not built")
+def test_qq_prime_sharding_world2_gloo(tmp_path):
+    from msolve_b200 import systems
+    primes = rh.primes_above(1 << 30, 7)
+    rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
+    rh.qq_setup(systems.by_name("katsura-6"), threads=1)
+    assert rh.qq_learn(primes[0])["rc"] == 0
+    single, _ = rh.qq_apply(primes[1:], threads=1)
+    want = [r["digest"] for r in single]
+
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+        capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    import json
+    got = json.loads(line[len("RESULT "):])
+    assert got == want
