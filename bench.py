@@ -151,7 +151,9 @@ def run_gpu(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     os.environ["F4LA_B200_DEVICE"] = str(local)
 
     host_threads = max(1, (os.cpu_count() or 8) // world)
@@ -332,32 +334,46 @@ def run_qq(args, rank, world, local, dist, torch):
     all_primes = rh.primes_above(1 << 30, 1 + per_rank * world)
     from msolve_b200 import sharding
     p0, mine = all_primes[0], sharding.shard(all_primes[1:], rank, world)[:per_rank]
+    # every rank always reaches the collectives below, whatever happens locally
+    local_err, res, learn, tot = None, [], {"seconds": 0.0, "nelts": 0}, {"ms_total": 0.0}
     L = gpu_helpers.install_backend()
     try:
         rh.qq_setup(system, threads=threads)
         learn = rh.qq_learn(p0)
         assert learn["rc"] == 0
-        gpu_helpers.neogb_totals(L)                       # reset
-        rh.qq_apply(mine[:threads], threads=threads, ngpus=1)    # warm-up
+        # ngpus=0: every host thread of this rank uses the rank's own GPU ($F4LA_B200_DEVICE)
+        rh.qq_apply(mine[:threads], threads=threads, ngpus=0)    # warm-up
         gpu_helpers.neogb_totals(L)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        res, wall = rh.qq_apply(mine, threads=threads, ngpus=1)
-        # NCCL all-gather of the per-prime results (msolve: residues for CRT on the host)
-        parts = sharding.gather_uint64([r["digest"] for r in res], dist if world > 1 else None, device="cuda")
-        torch.cuda.synchronize()
-        assert sum(len(x) for x in parts) == per_rank * world
-        el = time.perf_counter() - t0
+    except Exception as e:
+        local_err = repr(e)
+    torch.cuda.set_device(local)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    if local_err is None:
+        try:
+            res, wall = rh.qq_apply(mine, threads=threads, ngpus=0)
+            assert all(r["err"] == 0 and r["nelts"] == learn["nelts"] for r in res)
+        except Exception as e:
+            local_err, res = repr(e), []
+    torch.cuda.set_device(local)
+    # NCCL all-gather of the per-prime results (msolve: residues for CRT on the host)
+    parts = sharding.gather_uint64([r["digest"] for r in res], dist if world > 1 else None,
+                                  device=torch.device("cuda", local))
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    try:
         tot = gpu_helpers.neogb_totals(L)
     finally:
         gpu_helpers.uninstall_backend()
-    assert all(r["err"] == 0 and r["nelts"] == learn["nelts"] for r in res)
     if world > 1:
-        t = torch.tensor([el], device="cuda", dtype=torch.float64)
+        t = torch.tensor([el], device=torch.device("cuda", local), dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         el = float(t.item())
+    done = sum(len(x) for x in parts)
+    if local_err is not None or done != per_rank * world:
+        return {"error": local_err or f"only {done} of {per_rank * world} primes completed"}
     out = {"metric": "QQ primes/s (F4 tracer application phase)", "system": f"{args.qq_system} over QQ",
            "value": per_rank * world / el, "unit": "primes/s", "n_gpus": world, "primes": per_rank * world,
            "host_threads_per_gpu": threads, "seconds": el, "scaling": "weak",
