@@ -47,13 +47,12 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf sched, items, flowflags, nzflags, mailbox;
+    DevBuf sched, items, flowflags, mailbox;
     size_t        panel_smem_optin = 0;
     int           ge_panel = 0;         /* F4LA_B200_GE=panel: cluster/shared-memory panels (experimental, slower on low-rank blocks) */
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
-    int           use_levels = 0;       /* F4LA_B200_SCHED=levels: one launch per level (debug / A-B) */
     size_t        l2_budget = 0;
     HostBuf h_small, h_dense;
 };
@@ -128,27 +127,6 @@ inline unsigned blocks_for_warps(uint64_t nwarps, int threads = 256)
     if (b < 1) b = 1;
     if (b > 148 * 64) b = 148 * 64;
     return (unsigned)b;
-}
-
-template <int T>
-void launch_solve(f4la_ctx *ctx, const SolveArgs &a, unsigned nchunks, bool wide)
-{
-    const unsigned gx = a.n_long + (a.n_short + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (gx == 0 || nchunks == 0) return;
-    dim3 grid(gx, nchunks);
-    if (wide) k_pull_solve<T, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);
-    else      k_pull_solve<T, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a);
-    ctx->launches++;
-}
-
-void launch_solve_T(f4la_ctx *ctx, int T, const SolveArgs &a, unsigned nchunks, bool wide)
-{
-    switch (T) {
-        case 1: launch_solve<1>(ctx, a, nchunks, wide); break;
-        case 2: launch_solve<2>(ctx, a, nchunks, wide); break;
-        case 3: launch_solve<3>(ctx, a, nchunks, wide); break;
-        default: launch_solve<4>(ctx, a, nchunks, wide); break;
-    }
 }
 
 template <int T, bool WIDE>
@@ -310,10 +288,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             ctx->launches++;
         }
         /* class histogram: slot 2l = long columns of level l, 2l+1 = short ones */
-        OK(ensure(ctx, ctx->slots, ((size_t)2 * ncl + 4) * 4));
-        OK(ensure(ctx, ctx->slot_ptr, ((size_t)2 * ncl + 4) * 4));
+        OK(ensure(ctx, ctx->slots, ((size_t)kLenClasses * ncl + 8) * 4));
+        OK(ensure(ctx, ctx->slot_ptr, ((size_t)kLenClasses * ncl + 8) * 4));
         OK(ensure(ctx, ctx->order, (size_t)ncl * 4));
-        CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)2 * ncl + 4) * 4, s));
+        CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)kLenClasses * ncl + 8) * 4, s));
         k_level_count<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->level), as<uint32_t>(ctx->col_ptr), ncl,
                                                         as<uint32_t>(ctx->slots), d_err + 2);
         ctx->launches++;
@@ -321,7 +299,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
         nlev = h_small[0] + 1;
-        const uint32_t nslots = 2 * nlev;
+        const uint32_t nslots = kLenClasses * nlev;
         k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->slots), as<uint32_t>(ctx->slot_ptr), nslots);
         ctx->launches++;
         CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)nslots + 1) * 4, s));  /* reuse as cursor */
@@ -353,43 +331,35 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     OK(ensure(ctx, ctx->V, (size_t)G * nc * Rc * 4));
     OK(ensure(ctx, ctx->D, (size_t)ncr * ld * 4));
 
-    SolveArgs a;
-    memset(&a, 0, sizeof(a));
-    a.col_ptr = as<uint32_t>(ctx->col_ptr);
-    a.ent = as<uint2>(ctx->ent);
-    a.V = as<uint32_t>(ctx->V);
-    a.nc = nc; a.Rc = Rc; a.p = p; a.pinv = pinv;
-
-    /* dataflow schedule: items in level order, then the non-pivot columns */
+    /* dataflow schedule: items in (level, length class) order, then the non-pivot columns */
     uint32_t n_items = 0;
-    if (!ctx->use_levels) {
-        const uint32_t first = nlev ? slot_ptr_h[2] : ncl;      /* columns of level 0 have no sources */
+    {
+        const uint32_t first = nlev ? slot_ptr_h[kLenClasses] : ncl;      /* columns of level 0 have no sources */
         const uint32_t na = ncl - first;
         std::vector<uint32_t> items;
         items.reserve((size_t)na / 4 + ncr + 16);
         for (uint32_t l = 1; l < nlev; ++l) {
-            for (uint32_t q = slot_ptr_h[2 * l]; q < slot_ptr_h[2 * l + 1]; ++q)
+            const uint32_t *sp = &slot_ptr_h[(size_t)kLenClasses * l];
+            for (uint32_t q = sp[0]; q < sp[1]; ++q)                       /* long columns: one CTA each */
                 items.push_back(((q - first) << 5) | (1u << 1) | 1u);
-            for (uint32_t q = slot_ptr_h[2 * l + 1]; q < slot_ptr_h[2 * l + 2]; q += kWarpsPerBlock) {
-                const uint32_t cnt = slot_ptr_h[2 * l + 2] - q < (uint32_t)kWarpsPerBlock
-                                         ? slot_ptr_h[2 * l + 2] - q : (uint32_t)kWarpsPerBlock;
-                items.push_back(((q - first) << 5) | (cnt << 1));
-            }
+            for (int c = 1; c < kLenClasses; ++c)                          /* short ones: 8 of a class per CTA */
+                for (uint32_t q = sp[c]; q < sp[c + 1]; q += kWarpsPerBlock) {
+                    const uint32_t cnt = sp[c + 1] - q < (uint32_t)kWarpsPerBlock ? sp[c + 1] - q : (uint32_t)kWarpsPerBlock;
+                    items.push_back(((q - first) << 5) | (cnt << 1));
+                }
         }
         for (uint32_t k = 0; k < ncr; ++k) items.push_back(((na + k) << 5) | (1u << 1) | 1u);
         n_items = (uint32_t)items.size();
         OK(ensure(ctx, ctx->sched, ((size_t)na + ncr + 1) * 4));
         OK(ensure(ctx, ctx->items, ((size_t)n_items + 1) * 4));
         OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
-        OK(ensure(ctx, ctx->nzflags, (size_t)G * nc + 16));
         OK(ensure_host(ctx, ctx->h_dense, (size_t)n_items * 4 + 64));
         memcpy(ctx->h_dense.p, items.data(), (size_t)n_items * 4);
         CU(cudaMemcpyAsync(ctx->items.p, ctx->h_dense.p, (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
         k_flow_sched<<<(na + ncr + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->order), first, ncl, ncr,
                                                            as<uint32_t>(ctx->sched));
-        k_flow_init_flags<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), ncl, nc, G,
-                                                          as<uint32_t>(ctx->flowflags));
-        ctx->launches += 2;
+        ctx->launches++;
+        CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));
         /* the staging buffer is reused for the result later: the copy must be done first */
         CU(cudaStreamSynchronize(s));
     }
@@ -401,51 +371,35 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
-        if (!ctx->use_levels) CU(cudaMemsetAsync(ctx->nzflags.p, 0, (size_t)g * nc, s));
+        if (ncl) {
+            k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), ncl, nc, g,
+                                                               as<uint32_t>(ctx->flowflags));
+            ctx->launches++;
+        }
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
         k_scatter_lower<<<blocks_for_warps(rows_here), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
                                                                     d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
-                                                                    ctx->use_levels ? nullptr : as<uint8_t>(ctx->nzflags),
+                                                                    as<uint32_t>(ctx->flowflags),
                                                                     as<uint32_t>(ctx->V), d_err);
         ctx->launches++;
-        if (!ctx->use_levels) {
-            FlowArgs f;
-            memset(&f, 0, sizeof(f));
-            f.col_ptr = as<uint32_t>(ctx->col_ptr); f.ent = as<uint2>(ctx->ent);
-            f.V = as<uint32_t>(ctx->V); f.nc = nc; f.Rc = Rc;
-            f.sched = as<uint32_t>(ctx->sched); f.items = as<uint32_t>(ctx->items);
-            f.n_items = n_items; f.G = g;
-            f.flags = as<uint32_t>(ctx->flowflags); f.epoch = ++epoch;
-            f.nz = as<uint8_t>(ctx->nzflags);
-            f.counter = d_err + 4; f.err = d_err;
-            f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
-            f.p = p; f.pinv = pinv;
-            CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
-            launch_flow(ctx, T, f, wide);
-            if (want_rba && rba_words) {
-                dim3 grid(rba_words, g * (Rc / 128));
-                k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
-                                                as<uint32_t>(ctx->rba));
-                ctx->launches++;
-            }
-            continue;
+        FlowArgs f;
+        memset(&f, 0, sizeof(f));
+        f.col_ptr = as<uint32_t>(ctx->col_ptr); f.ent = as<uint2>(ctx->ent);
+        f.V = as<uint32_t>(ctx->V); f.nc = nc; f.Rc = Rc;
+        f.sched = as<uint32_t>(ctx->sched); f.items = as<uint32_t>(ctx->items);
+        f.n_items = n_items; f.G = g;
+        f.flags = as<uint32_t>(ctx->flowflags); f.epoch = ++epoch;
+        f.counter = d_err + 4; f.err = d_err;
+        f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
+        f.p = p; f.pinv = pinv;
+        CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
+        launch_flow(ctx, T, f, wide);
+        if (want_rba && rba_words) {
+            dim3 grid(rba_words, g * (Rc / 128));
+            k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
+                                            as<uint32_t>(ctx->rba));
+            ctx->launches++;
         }
-        /* level 0 columns have no sources: V[j] already final */
-        for (uint32_t l = 1; l < nlev; ++l) {
-            SolveArgs b = a;
-            b.long_cols = as<uint32_t>(ctx->order) + slot_ptr_h[2 * l];
-            b.n_long = slot_ptr_h[2 * l + 1] - slot_ptr_h[2 * l];
-            b.short_cols = as<uint32_t>(ctx->order) + slot_ptr_h[2 * l + 1];
-            b.n_short = slot_ptr_h[2 * l + 2] - slot_ptr_h[2 * l + 1];
-            b.out = nullptr;
-            launch_solve_T(ctx, T, b, g, wide);
-        }
-        /* the non-pivot columns: D' = D - M B, written to the trailing block */
-        SolveArgs b = a;
-        b.long_cols = nullptr; b.short_cols = nullptr; b.col_base = ncl;
-        b.n_long = ncr; b.n_short = 0;
-        b.out = as<uint32_t>(ctx->D); b.out_ld = ld; b.out_col0 = ncl; b.chunk0 = c0;
-        launch_solve_T(ctx, T, b, g, wide);
     }
     CU(cudaEventRecord(ctx->ev[2], s));
 
@@ -625,7 +579,6 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         }
     }
     if (want_rba && rba_words) {
-        if (ctx->use_levels) return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_WANT_RBA is not available with F4LA_B200_SCHED=levels");
         out->rba_words = rba_words;
         out->rba = (uint32_t *)malloc((size_t)nrl * rba_words * 4);
         CU(cudaMemcpyAsync(out->rba, ctx->rba.p, (size_t)nrl * rba_words * 4, cudaMemcpyDeviceToHost, s));
@@ -736,8 +689,6 @@ f4la_ctx *f4la_b200_create(int device)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
-    const char *sched = getenv("F4LA_B200_SCHED");
-    ctx->use_levels = sched && !strcmp(sched, "levels");
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_panel = ge && !strcmp(ge, "panel");
     const char *bud = getenv("F4LA_B200_L2_MB");
@@ -753,7 +704,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->nzflags, &ctx->mailbox, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->mailbox, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba};
     for (auto b : bufs) free_dev(*b);

@@ -41,7 +41,19 @@ constexpr int kWarpsPerBlock  = kSolveThreads / 32;
 constexpr int kRowsPerT       = 128;   /* rows covered by one uint4 per lane */
 constexpr int kMaxT           = 4;     /* chunk = 128*T rows, T in 1..4      */
 constexpr uint32_t kFoldEvery = 1u << 15; /* entries between overflow folds  */
-constexpr uint32_t kLongColumn = 48;   /* >= this many entries: one CTA/col  */
+constexpr uint32_t kLongColumn = 128;  /* >= this many entries: one CTA/col  */
+constexpr int kLenClasses     = 7;     /* class 0 = long, 1..6 = short columns by decreasing length */
+
+__host__ __device__ __forceinline__ uint32_t len_class(uint32_t len)
+{
+    if (len >= kLongColumn) return 0;
+    if (len >= 64) return 1;
+    if (len >= 32) return 2;
+    if (len >= 16) return 3;
+    if (len >= 8) return 4;
+    if (len >= 4) return 5;
+    return 6;
+}
 
 /* x mod p for any 64-bit x, pinv = floor((2^64-1)/p).  The quotient estimate
  * is short by at most 2, the loop repairs it. */
@@ -261,14 +273,15 @@ __global__ void k_level_flow(const uint32_t *__restrict__ col_ptr, const uint2 *
     }
 }
 
-/* Histogram of (level, long/short) classes: slot = 2*level + (short ? 1 : 0). */
+/* Histogram of (level, length class): slot = kLenClasses * level + len_class(len).
+ * Short columns of similar length share an item, so the 8 warps of a CTA finish together. */
 __global__ void k_level_count(const uint32_t *__restrict__ level, const uint32_t *__restrict__ col_ptr,
                               uint32_t ncl, uint32_t *__restrict__ slot_cnt, uint32_t *__restrict__ max_level)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncl) return;
     const uint32_t len = col_ptr[j + 1] - col_ptr[j];
-    atomicAdd(&slot_cnt[2 * level[j] + (len >= kLongColumn ? 0 : 1)], 1u);
+    atomicAdd(&slot_cnt[kLenClasses * level[j] + len_class(len)], 1u);
     atomicMax(max_level, level[j]);
 }
 
@@ -279,7 +292,7 @@ __global__ void k_level_fill(const uint32_t *__restrict__ level, const uint32_t 
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncl) return;
     const uint32_t len = col_ptr[j + 1] - col_ptr[j];
-    const uint32_t s = 2 * level[j] + (len >= kLongColumn ? 0 : 1);
+    const uint32_t s = kLenClasses * level[j] + len_class(len);
     order[slot_ptr[s] + atomicAdd(&cursor[s], 1u)] = j;
 }
 
@@ -292,7 +305,7 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
                                 const void *__restrict__ cf, uint32_t cf_bytes,
                                 uint32_t nru, uint32_t nrl, uint32_t nc, uint32_t p,
                                 uint32_t chunk0, uint32_t nchunks, uint32_t Rc,
-                                const uint32_t *__restrict__ colmap, uint8_t *__restrict__ nz,
+                                const uint32_t *__restrict__ colmap, uint32_t *__restrict__ flags,
                                 uint32_t *__restrict__ V, uint32_t *__restrict__ err)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -311,100 +324,15 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
             if (colmap) j = colmap[j];
             const uint32_t v = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
             Vc[(size_t)j * Rc + lr] = v;
-            if (nz && v) nz[(size_t)lc * nc + j] = 1;     /* columns without sources keep this flag */
+            if (flags && v && flags[(size_t)lc * nc + j] == 0xfffffffeu)      /* kFlagAlwaysZ -> kFlagAlwaysNZ */
+                flags[(size_t)lc * nc + j] = 0xffffffffu;
         }
     }
 }
 
 /* ------------------------------------------------------------------ */
-/* the hot kernel: pull-solve of a set of columns                      */
+/* arithmetic helpers of the hot kernel                                 */
 /* ------------------------------------------------------------------ */
-
-struct SolveArgs {
-    const uint32_t *col_ptr;   /* pull lists                                  */
-    const uint2    *ent;
-    uint32_t       *V;         /* [nchunks][nc][Rc] of the chunk group        */
-    uint32_t        nc;
-    uint32_t        Rc;        /* 128*T                                       */
-    const uint32_t *long_cols; /* columns solved by a whole CTA               */
-    uint32_t        n_long;
-    const uint32_t *short_cols;/* columns solved by one warp each             */
-    uint32_t        n_short;
-    uint32_t        col_base;  /* when the lists are NULL: columns col_base+k */
-    uint32_t       *out;       /* != NULL: results go to out instead of V     */
-    uint64_t        out_ld;    /* out[(j-out_col0)*out_ld + chunk*Rc + row]   */
-    uint32_t        out_col0;
-    uint32_t        chunk0;    /* first chunk of the group (for out)          */
-    uint32_t        p;
-    uint64_t        pinv;
-};
-
-/* Accumulate entries [e0,e1) with stride `step` of column j into acc.
- * Lane owns rows 4*lane + 128*t + {0,1,2,3}. */
-template <int T, bool WIDE>
-__device__ __forceinline__ void pull_accumulate(const SolveArgs &A, const uint32_t *__restrict__ Vc,
-                                                uint32_t e0, uint32_t e1, uint32_t step, uint32_t lane,
-                                                uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
-{
-    constexpr int U = (T <= 2) ? 4 : 2;       /* entries in flight per warp */
-    const uint2 *__restrict__ ent = A.ent;
-    const uint32_t Rc = A.Rc;
-    uint32_t since_fold = 0;
-    uint32_t e = e0;
-    for (; e + (U - 1) * step < e1; e += U * step) {
-        uint2 en[U];
-        uint4 v[U][T];
-#pragma unroll
-        for (int u = 0; u < U; ++u) en[u] = __ldg(&ent[e + u * step]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(Vc + (size_t)en[u].x * Rc) + lane;
-#pragma unroll
-            for (int t = 0; t < T; ++t) v[u][t] = src[t * 32];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t cl = WIDE ? (en[u].y & 0xffffu) : en[u].y;
-            const uint32_t ch = en[u].y >> 16;
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                lo[t][0] += (uint64_t)v[u][t].x * cl; lo[t][1] += (uint64_t)v[u][t].y * cl;
-                lo[t][2] += (uint64_t)v[u][t].z * cl; lo[t][3] += (uint64_t)v[u][t].w * cl;
-                if (WIDE) {
-                    hi[t][0] += (uint64_t)v[u][t].x * ch; hi[t][1] += (uint64_t)v[u][t].y * ch;
-                    hi[t][2] += (uint64_t)v[u][t].z * ch; hi[t][3] += (uint64_t)v[u][t].w * ch;
-                }
-            }
-        }
-        since_fold += U;
-        if (since_fold >= kFoldEvery) {
-            since_fold = 0;
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
-                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
-                }
-        }
-    }
-    for (; e < e1; e += step) {               /* tail, < U entries */
-        const uint2 en = __ldg(&ent[e]);
-        const uint4 *src = reinterpret_cast<const uint4 *>(Vc + (size_t)en.x * Rc) + lane;
-        const uint32_t cl = WIDE ? (en.y & 0xffffu) : en.y;
-        const uint32_t ch = en.y >> 16;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const uint4 v = src[t * 32];
-            lo[t][0] += (uint64_t)v.x * cl; lo[t][1] += (uint64_t)v.y * cl;
-            lo[t][2] += (uint64_t)v.z * cl; lo[t][3] += (uint64_t)v.w * cl;
-            if (WIDE) {
-                hi[t][0] += (uint64_t)v.x * ch; hi[t][1] += (uint64_t)v.y * ch;
-                hi[t][2] += (uint64_t)v.z * ch; hi[t][3] += (uint64_t)v.w * ch;
-            }
-        }
-    }
-}
 
 /* canonical residue of lo + 2^16 * hi */
 template <bool WIDE>
@@ -413,71 +341,6 @@ __device__ __forceinline__ uint32_t fold_lohi(uint64_t lo, uint64_t hi, uint32_t
     uint64_t x = mod_u64(lo, p, pinv);
     if (WIDE) x += (uint64_t)mod_u64(hi, p, pinv) << 16;
     return mod_u64(x, p, pinv);
-}
-
-template <int T, bool WIDE>
-__global__ void __launch_bounds__(kSolveThreads)
-k_pull_solve(const SolveArgs A)
-{
-    __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];   /* long columns only */
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.y;
-    uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
-    const bool is_long = blockIdx.x < A.n_long;
-
-    uint32_t j;
-    if (is_long) {
-        j = A.long_cols ? A.long_cols[blockIdx.x] : A.col_base + blockIdx.x;
-    } else {
-        const uint32_t k = (blockIdx.x - A.n_long) * kWarpsPerBlock + warp;
-        if (k >= A.n_short) return;
-        j = A.short_cols ? A.short_cols[k] : A.col_base + A.n_long + k;
-    }
-    const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-
-    uint64_t lo[T][4], hi[T][4];
-#pragma unroll
-    for (int t = 0; t < T; ++t)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { lo[t][k] = 0; hi[t][k] = 0; }
-
-    uint32_t *dst = A.out ? A.out + (size_t)(j - A.out_col0) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
-                          : Vc + (size_t)j * A.Rc;
-    const uint4 *init = reinterpret_cast<const uint4 *>(Vc + (size_t)j * A.Rc) + lane;
-
-    if (!is_long) {
-        pull_accumulate<T, WIDE>(A, Vc, e0, e1, 1, lane, lo, hi);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const uint4 x = init[t * 32];
-            uint4 r;
-            r.x = fold_lohi<WIDE>(lo[t][0] + x.x, hi[t][0], A.p, A.pinv);
-            r.y = fold_lohi<WIDE>(lo[t][1] + x.y, hi[t][1], A.p, A.pinv);
-            r.z = fold_lohi<WIDE>(lo[t][2] + x.z, hi[t][2], A.p, A.pinv);
-            r.w = fold_lohi<WIDE>(lo[t][3] + x.w, hi[t][3], A.p, A.pinv);
-            reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
-        }
-        return;
-    }
-
-    /* long column: the 8 warps take interleaved entries, then reduce */
-    pull_accumulate<T, WIDE>(A, Vc, e0 + warp, e1, kWarpsPerBlock, lane, lo, hi);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        uint4 r;
-        r.x = fold_lohi<WIDE>(lo[t][0], hi[t][0], A.p, A.pinv);
-        r.y = fold_lohi<WIDE>(lo[t][1], hi[t][1], A.p, A.pinv);
-        r.z = fold_lohi<WIDE>(lo[t][2], hi[t][2], A.p, A.pinv);
-        r.w = fold_lohi<WIDE>(lo[t][3], hi[t][3], A.p, A.pinv);
-        reinterpret_cast<uint4 *>(&part[warp][t * kRowsPerT])[lane] = r;
-    }
-    __syncthreads();
-    for (uint32_t r = threadIdx.x; r < (uint32_t)(T * kRowsPerT); r += kSolveThreads) {
-        uint64_t s = Vc[(size_t)j * A.Rc + r];
-#pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w][r];
-        dst[r] = mod_u64(s, A.p, A.pinv);
-    }
 }
 
 /* ------------------------------------------------------------------ */
@@ -492,7 +355,10 @@ k_pull_solve(const SolveArgs A)
  * depends on columns of earlier items, hence the oldest unfinished item never
  * waits: no deadlock whatever the number of resident CTAs. */
 
-constexpr uint32_t kFlagAlways = 0xffffffffu;   /* column without sources: V[j] = X[j] */
+/* ready word of a column: (epoch << 1) | nonzero; columns without sources (V[j] = X[j])
+ * are always ready: kFlagAlwaysZ when no lower row of the chunk touches them, else kFlagAlwaysNZ */
+constexpr uint32_t kFlagAlwaysZ  = 0xfffffffeu;
+constexpr uint32_t kFlagAlwaysNZ = 0xffffffffu;
 constexpr uint32_t kSpinLimit  = 1u << 24;      /* polls before the watchdog gives up (seconds) */
 constexpr uint32_t kErrWatchdog = 16u;
 
@@ -504,8 +370,7 @@ struct FlowArgs {
     const uint32_t *sched;      /* column ids in schedule order                   */
     const uint32_t *items;      /* (pos << 5) | (count << 1) | is_long            */
     uint32_t        n_items, G;
-    uint32_t       *flags;      /* [G][nc] ready epoch of each column             */
-    uint8_t        *nz;         /* [G][nc] 1 iff the column's vector is non-zero   */
+    uint32_t       *flags;      /* [G][nc] ready word of each column              */
     uint32_t        epoch;
     uint32_t       *counter;    /* work counter, zeroed before the launch         */
     uint32_t       *err;        /* error bits (kErrWatchdog)                      */
@@ -537,33 +402,31 @@ __device__ __forceinline__ uint4 ld_cg_u4(const uint4 *ptr)
     return v;
 }
 
-/* Entries [e0,e1) of one column, taken in batches of 32 with stride
- * `nslots` batches starting at batch `slot`; waits for every source. */
+/* Entries [b0,b1) of one column in batches of 32; waits for every source. */
 template <int T, bool WIDE>
 __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_t *__restrict__ Vc,
                                                 const uint32_t *__restrict__ flagc,
-                                                const uint8_t *__restrict__ nzc,
-                                                uint32_t e0, uint32_t e1, uint32_t slot, uint32_t nslots,
+                                                uint32_t b0, uint32_t b1,
                                                 uint32_t lane, uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
 {
     constexpr int U = (T <= 2) ? 4 : 2;
     const uint32_t Rc = A.Rc;
     uint32_t since_fold = 0;
-    for (uint32_t b = e0 + 32 * slot; b < e1; b += 32 * nslots) {
-        const uint32_t n = min(32u, e1 - b);
+    for (uint32_t b = b0; b < b1; b += 32) {
+        const uint32_t n = min(32u, b1 - b);
         uint2 en = make_uint2(0, 0);
-        bool ready = true;
+        uint32_t f = kFlagAlwaysZ;
         if (lane < n) {
             en = __ldg(&A.ent[b + lane]);
-            const uint32_t f = ld_acquire(&flagc[en.x]);
-            ready = (f == A.epoch) || (f == kFlagAlways);
+            f = ld_acquire(&flagc[en.x]);
         }
+        bool ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
         uint32_t spins = 0;
         while (!__all_sync(0xffffffffu, ready)) {
             if (!ready) {
                 __nanosleep(64);
-                const uint32_t f = ld_acquire(&flagc[en.x]);
-                ready = (f == A.epoch) || (f == kFlagAlways);
+                f = ld_acquire(&flagc[en.x]);
+                ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
                 if (++spins > kSpinLimit) {          /* watchdog: never hang the GPU */
                     atomicOr(A.err, kErrWatchdog);
                     ready = true;
@@ -574,7 +437,7 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
         /* Sources whose vector is entirely zero in this chunk contribute nothing:
          * the lower rows come clustered, 15-60 % of the (pivot, chunk) vectors are
          * zero, so their loads and multiplies are skipped altogether. */
-        uint32_t live = __ballot_sync(0xffffffffu, lane < n && __ldcg(&nzc[en.x]) != 0);
+        uint32_t live = __ballot_sync(0xffffffffu, lane < n && (f & 1u));
         since_fold += __popc(live);
         while (live) {
             uint32_t src[U], cf[U];
@@ -645,7 +508,6 @@ k_pull_flow(const FlowArgs A)
         const bool is_long = it & 1u;
         uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
         uint32_t *flagc = A.flags + (size_t)chunk * A.nc;
-        uint8_t *nzc = A.nz + (size_t)chunk * A.nc;
 
         uint64_t lo[T][4], hi[T][4];
 #pragma unroll
@@ -657,7 +519,7 @@ k_pull_flow(const FlowArgs A)
             if (warp < cnt) {
                 const uint32_t j = A.sched[pos + warp];
                 const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-                flow_accumulate<T, WIDE>(A, Vc, flagc, nzc, e0, e1, 0, 1, lane, lo, hi);
+                flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi);
                 const bool to_out = j >= A.ncl;
                 uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                        : Vc + (size_t)j * A.Rc;
@@ -678,7 +540,7 @@ k_pull_flow(const FlowArgs A)
                     const bool any = __any_sync(0xffffffffu, nonzero != 0);
                     __threadfence();
                     __syncwarp();
-                    if (lane == 0) { nzc[j] = any ? 1 : 0; st_release(&flagc[j], A.epoch); }
+                    if (lane == 0) st_release(&flagc[j], (A.epoch << 1) | (any ? 1u : 0u));
                 }
             }
             continue;       /* the two barriers at the loop head keep the CTA together */
@@ -686,7 +548,12 @@ k_pull_flow(const FlowArgs A)
 
         const uint32_t j = A.sched[pos];
         const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-        flow_accumulate<T, WIDE>(A, Vc, flagc, nzc, e0, e1, warp, kWarpsPerBlock, lane, lo, hi);
+        {
+            /* equal contiguous shares of the entries for the 8 warps */
+            const uint32_t seg = (e1 - e0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
+            const uint32_t b0 = min(e1, e0 + warp * seg), b1 = min(e1, b0 + seg);
+            flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi);
+        }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             uint4 r;
@@ -712,19 +579,20 @@ k_pull_flow(const FlowArgs A)
         if (!to_out) {
             __threadfence();
             nonzero = __syncthreads_or(nonzero);
-            if (threadIdx.x == 0) { nzc[j] = nonzero ? 1 : 0; st_release(&flagc[j], A.epoch); }
+            if (threadIdx.x == 0) st_release(&flagc[j], (A.epoch << 1) | (nonzero ? 1u : 0u));
         }
     }
 }
 
-/* flags of the columns without sources, for all G chunk slots */
-__global__ void k_flow_init_flags(const uint32_t *__restrict__ col_ptr, uint32_t ncl, uint32_t nc, uint32_t G,
-                                  uint32_t *__restrict__ flags)
+/* ready words of the columns without sources, for the g chunk slots of a group: "always
+ * ready, zero"; k_scatter_lower upgrades the touched ones to "non-zero".  The words of the
+ * other columns are left alone (their epoch is stale until the column is solved). */
+__global__ void k_flow_reset_flags(const uint32_t *__restrict__ col_ptr, uint32_t ncl, uint32_t nc, uint32_t g,
+                                   uint32_t *__restrict__ flags)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nc) return;
-    const uint32_t f = (j < ncl && col_ptr[j + 1] == col_ptr[j]) ? kFlagAlways : 0u;
-    for (uint32_t g = 0; g < G; ++g) flags[(size_t)g * nc + j] = f;
+    if (j >= ncl || col_ptr[j + 1] != col_ptr[j]) return;
+    for (uint32_t k = 0; k < g; ++k) flags[(size_t)k * nc + j] = kFlagAlwaysZ;
 }
 
 /* schedule = pivot columns with sources in level order, then the non-pivot columns */
