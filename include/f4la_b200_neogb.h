@@ -62,6 +62,21 @@ void f4la_b200_linear_algebra(void *mat, const void *tbr, const void *bs, void *
 /* Replaces `exact_linear_algebra` (data.h:531-536; io.c:962). */
 void f4la_b200_exact_linear_algebra(void *mat, const void *tbr, const void *bs, void *st);
 
+/* Replaces `application_linear_algebra` (data.h:559-563; io.c dispatch_application_linear_algebra
+ * -> exact_application_sparse_linear_algebra_ff_*, la_ff_32.c:4041/3135): same echelon form,
+ * returns 1 when a row reduced to zero (unlucky prime), else 0. */
+int f4la_b200_application_linear_algebra(void *mat, const void *bs, void *st);
+
+/* Replaces `trace_linear_algebra` (data.h:571-576; exact_trace_sparse_linear_algebra_ff_*,
+ * la_ff_32.c:4075/3004): echelon form + reducer bit arrays + construct_trace(trace, mat). */
+void f4la_b200_trace_linear_algebra(void *trace, void *mat, const void *bs, void *st);
+
+/* Replaces `interreduce_matrix_rows` (data.h:584-589; interreduce_matrix_rows_ff_*,
+ * la_ff_32.c:4254-4326).  free_basis != 0 needs the reference's (static) free_basis_elements,
+ * handed over with f4la_b200_neogb_set_free_basis_elements(). */
+void f4la_b200_interreduce_matrix_rows(void *mat, void *bs, void *st, int free_basis);
+void f4la_b200_neogb_set_free_basis_elements(void (*fn)(void *bs));
+
 /* Accumulated device statistics of the calling thread since the last reset. */
 typedef struct f4la_neogb_totals {
     uint64_t calls;

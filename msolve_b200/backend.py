@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "f4la_b200_free_result",
     # include/f4la_b200_neogb.h
     "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",
-    "f4la_b200_exact_linear_algebra", "f4la_b200_neogb_get_totals",
+    "f4la_b200_exact_linear_algebra", "f4la_b200_application_linear_algebra", "f4la_b200_trace_linear_algebra",
+    "f4la_b200_interreduce_matrix_rows", "f4la_b200_neogb_set_free_basis_elements", "f4la_b200_neogb_get_totals",
 ]
 
 

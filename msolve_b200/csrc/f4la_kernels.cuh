@@ -382,10 +382,15 @@ struct FlowArgs {
     uint64_t        pinv;
 };
 
+/* Ready words are polled with a relaxed, L1-bypassing load.  An acquire load would
+ * invalidate the whole L1 on every poll (CCTL.IVALL, 5 % of the stall samples in ncu) although
+ * nothing read through L1 can be stale: the vectors V[src] are fetched with ld.cg straight from
+ * L2, the point of coherence, and only after the branch that consumed the ready word, while the
+ * producer makes its stores visible (fence) before the release store of that word. */
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *ptr)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
     return v;
 }
 
@@ -488,7 +493,7 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
 }
 
 template <int T, bool WIDE>
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, (T <= 2) ? 4 : 2)
 k_pull_flow(const FlowArgs A)
 {
     __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];

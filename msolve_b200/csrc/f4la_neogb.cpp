@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "f4la_b200.h"
@@ -28,6 +29,9 @@ namespace {
 f4la_neogb_layout L;
 bool g_configured = false;
 void (*g_construct_trace)(void *, void *) = nullptr;
+void (*g_free_basis_elements)(void *) = nullptr;
+
+enum class Entry { Normal, Application, Trace };
 
 struct ThreadState {
     f4la_ctx *ctx = nullptr;
@@ -87,8 +91,9 @@ f4la_ctx *ctx()
     return T.ctx;
 }
 
-/* Echelon form of mat->tr modulo mat->rr; the body shared by both pointers. */
-void echelon(void *mat, const void *tbr, const void *bs, void *st)
+/* Echelon form of mat->tr modulo mat->rr; the body shared by the four matrix-level pointers.
+ * Returns 1 for an unlucky prime in Entry::Application (la_ff_32.c:3215-3217), else 0. */
+int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = Entry::Normal, void *trace = nullptr)
 {
     if (!g_configured) die("f4la_b200_neogb_configure() was not called");
     const double ct0 = cpu_s(), rt0 = wall_s();
@@ -102,7 +107,11 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     const bool nf_mode = fld<int32_t>(st, L.md_nf) > 0;
     const bool final_step = fld<int32_t>(st, L.md_in_final_reduction_step) != 0;
     /* the reference records no trace in the final reduction step (la_ff_32.c:2713) */
-    const bool learn = trace_level == 1 /* LEARN_TRACER */ && !final_step && !nf_mode;
+    /* trace_linear_algebra always learns into the trace it is given (la_ff_32.c:3004-3133);
+     * linear_algebra learns when the F4 driver runs in LEARN_TRACER mode (la_ff_32.c:2669, 2713) */
+    const bool learn = entry == Entry::Trace || (trace_level == 1 /* LEARN_TRACER */ && !final_step && !nf_mode);
+    if (entry != Entry::Normal && (nf_mode || final_step))
+        die("application / trace linear algebra in nf or final-reduction mode is not defined by the reference");
     if (learn && !g_construct_trace)
         die("LEARN_TRACER needs f4la_b200_neogb_set_construct_trace() (see INTEGRATION.md)");
 
@@ -200,7 +209,7 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
             if (rba && rba[i] && res.rba) memcpy(rba[i], res.rba + (size_t)i * words, (size_t)words * 4);
             if (!kept[i]) { free(tr[i]); tr[i] = nullptr; }
         }
-        g_construct_trace(fld<void *>(st, L.md_tr), mat);
+        g_construct_trace(entry == Entry::Trace ? trace : fld<void *>(st, L.md_tr), mat);
     }
 
     /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
@@ -210,6 +219,7 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
 
     uint32_t np = res.nrows;
+    int bad_prime = 0;
     if (nf_mode || final_step) {
         /* rows are returned in place, one per input row, NULL when it vanished;
          * np = nrl (la_ff_32.c:2672-2684, 2764-2766) */
@@ -236,10 +246,11 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
         fld<uint32_t>(mat, L.mat_np) = np;
         fld<uint32_t>(mat, L.mat_nr) = np;
         fld<uint32_t>(mat, L.mat_sz) = np;
-    } else if (trace_level == 2 /* APPLY_TRACER */ && np != nrl) {
+    } else if ((trace_level == 2 /* APPLY_TRACER */ || entry == Entry::Application) && np != nrl) {
         /* a row reduced to zero while applying the tracer: bad prime
          * (la_ff_32.c:2679-2683, 2700-2709) */
         np = 0;
+        bad_prime = 1;
         if (fld<int32_t>(st, L.md_info_level) > 0)
             fprintf(stderr, "Zero reduction while applying tracer, bad prime.\n");
         fld<uint32_t>(mat, L.mat_np) = 0;
@@ -292,6 +303,89 @@ void echelon(void *mat, const void *tbr, const void *bs, void *st)
     t.ms_echelon += stats.ms_echelon; t.ms_d2h += stats.ms_d2h;
     t.units += stats.units; t.bytes_h2d += stats.bytes_h2d; t.bytes_d2h += stats.bytes_d2h;
     t.kernel_launches += stats.kernel_launches;
+    return entry == Entry::Application ? bad_prime : 0;
+}
+
+/* interreduce_matrix_rows_ff_* (la_ff_32.c:4254-4326): every row of mat->rr is a pivot
+ * with its own lead column; the rows are reduced by each other (unique result: the reduced
+ * row echelon form of their span), returned in mat->tr by INCREASING lead column with
+ * COEFFS = lead column (mat->cf_* has one slot per column), mat->np = mat->nr. */
+void interreduce(void *mat, void *bs, void *st, int free_basis)
+{
+    if (!g_configured) die("f4la_b200_neogb_configure() was not called");
+    const int32_t ff_bits = fld<int32_t>(st, L.md_ff_bits);
+    const uint32_t w = ff_bits == 8 ? 1 : ff_bits == 16 ? 2 : 4;
+    if (ff_bits != 8 && ff_bits != 16 && ff_bits != 32) die("unsupported field (ff_bits must be 8, 16 or 32)");
+    const uint32_t nrows = fld<uint32_t>(mat, L.mat_nr), ncols = fld<uint32_t>(mat, L.mat_nc);
+    uint32_t **rr = fld<uint32_t **>(mat, L.mat_rr);
+    const uint32_t cf_off = w == 1 ? L.mat_cf_8 : w == 2 ? L.mat_cf_16 : L.mat_cf_32;
+    const uint32_t bcf_off = w == 1 ? L.bs_cf_8 : w == 2 ? L.bs_cf_16 : L.bs_cf_32;
+    if (fld<int32_t>(st, L.md_info_level) > 1) fprintf(stderr, "                          ");
+
+    uint32_t **&tr = fld<uint32_t **>(mat, L.mat_tr);
+    tr = (uint32_t **)realloc(tr, (size_t)(ncols ? ncols : 1) * sizeof(uint32_t *));
+    void **&mcf = fld<void **>(mat, cf_off);
+    mcf = (void **)realloc(mcf, (size_t)(ncols ? ncols : 1) * sizeof(void *));
+    memset(mcf, 0, (size_t)ncols * sizeof(void *));
+
+    /* flatten: no known pivots, the rows themselves are the lower rows, keyed by lead */
+    std::vector<uint64_t> row_ptr(nrows + 1), cf_ptr(nrows + 1);
+    uint64_t nnz = 0;
+    for (uint32_t r = 0; r < nrows; ++r) { row_ptr[r] = nnz; cf_ptr[r] = nnz; nnz += rr[r][L.row_length]; }
+    row_ptr[nrows] = nnz; cf_ptr[nrows] = nnz;
+    uint32_t *cols = (uint32_t *)stage(1, (nnz + 1) * 4);
+    unsigned char *pool = (unsigned char *)stage(4, (nnz + 1) * w);
+    std::vector<uint32_t> row_cf(nrows);
+    void *const *bs_cf = fld<void *const *>(bs, bcf_off);
+    for (uint32_t r = 0; r < nrows; ++r) {
+        const uint32_t len = rr[r][L.row_length];
+        memcpy(cols + row_ptr[r], rr[r] + L.row_offset, (size_t)len * 4);
+        memcpy(pool + row_ptr[r] * w, bs_cf[rr[r][L.row_coeffs]], (size_t)len * w);   /* not shared here, as :4279 notes */
+        row_cf[r] = r;
+    }
+    f4la_flat_matrix fm;
+    memset(&fm, 0, sizeof(fm));
+    fm.fc = fld<uint32_t>(st, L.md_fc); fm.cf_bytes = w; fm.nru = 0; fm.nrl = nrows; fm.ncl = 0; fm.ncr = ncols;
+    fm.ncf = nrows; fm.flags = F4LA_FLAG_PIVOT_BY_LEAD;
+    fm.row_ptr = row_ptr.data(); fm.cols = cols; fm.row_cf = row_cf.data(); fm.cf_ptr = cf_ptr.data(); fm.cf = pool;
+    f4la_flat_result res;
+    f4la_stats stats;
+    if (f4la_b200_reduce(ctx(), &fm, &res, &stats) != F4LA_OK) die(f4la_b200_last_error(ctx()));
+
+    /* position of every row in the output = rank of its lead column */
+    std::vector<uint32_t> order(nrows);
+    for (uint32_t r = 0; r < nrows; ++r) order[r] = r;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return rr[a][L.row_offset] < rr[b][L.row_offset]; });
+    for (uint32_t k = 0; k < nrows; ++k) {
+        const uint32_t r = order[k];
+        const uint64_t a = res.row_ptr[r];
+        const uint32_t len = (uint32_t)(res.row_ptr[r + 1] - a);
+        const uint32_t lead = rr[r][L.row_offset];
+        uint32_t *row = (uint32_t *)malloc(((size_t)len + L.row_offset) * sizeof(uint32_t));
+        void *cf = malloc((size_t)(len ? len : 1) * w);
+        memcpy(row + L.row_offset, res.cols + a, (size_t)len * 4);
+        memcpy(cf, (unsigned char *)res.cf + a * w, (size_t)len * w);
+        row[L.row_deg] = 0;
+        row[L.row_bindex] = rr[r][L.row_bindex];
+        row[L.row_mult] = rr[r][L.row_mult];
+        row[L.row_coeffs] = lead;
+        row[L.row_preloop] = len % L.unroll;
+        row[L.row_length] = len;
+        mcf[lead] = cf;
+        tr[k] = row;
+    }
+    f4la_b200_free_result(&res);
+    for (uint32_t r = 0; r < nrows; ++r) free(rr[r]);
+    if (free_basis != 0) {
+        if (!g_free_basis_elements) die("interreduce_matrix_rows(free_basis != 0) needs f4la_b200_neogb_set_free_basis_elements()");
+        g_free_basis_elements(bs);
+    }
+    free(rr);
+    fld<uint32_t **>(mat, L.mat_rr) = nullptr;
+    fld<uint32_t>(mat, L.mat_np) = nrows;
+    T.tot.calls++;
+    T.tot.kernel_launches += stats.kernel_launches;
+    T.tot.ms_total += stats.ms_total;
 }
 
 } // namespace
@@ -326,6 +420,23 @@ void f4la_b200_exact_linear_algebra(void *mat, const void *tbr, const void *bs, 
 {
     echelon(mat, tbr, bs, st);
 }
+
+int f4la_b200_application_linear_algebra(void *mat, const void *bs, void *st)
+{
+    return echelon(mat, bs, bs, st, Entry::Application);
+}
+
+void f4la_b200_trace_linear_algebra(void *trace, void *mat, const void *bs, void *st)
+{
+    echelon(mat, bs, bs, st, Entry::Trace, trace);
+}
+
+void f4la_b200_interreduce_matrix_rows(void *mat, void *bs, void *st, int free_basis)
+{
+    interreduce(mat, bs, st, free_basis);
+}
+
+void f4la_b200_neogb_set_free_basis_elements(void (*fn)(void *bs)) { g_free_basis_elements = fn; }
 
 void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset)
 {

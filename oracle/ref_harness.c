@@ -454,6 +454,82 @@ int refh_reference_la(const f4la_flat_matrix *in, int32_t laopt, int32_t threads
     return 0;
 }
 
+/* Generic driver for the matrix-level entry points on a flat matrix.
+ *   which 0: fn(mat, tbr, bs, st)            linear_algebra / exact_linear_algebra signature
+ *   which 1: int fn(mat, bs, st)             application_linear_algebra signature
+ *   which 2: fn(mat, bs, st, free_basis=0)   interreduce_matrix_rows signature; the LOWER rows of
+ *                                            the flat matrix are handed over as mat->rr
+ * fn == NULL runs the reference's own dispatcher.  *ret receives the int result (which 1). */
+int refh_call_entry(const f4la_flat_matrix *in, int32_t which, void *fn, int32_t threads,
+                    f4la_flat_result *out, int32_t *ret, uint32_t *out_coeffs_index)
+{
+    const uint32_t n = in->nru + in->nrl;
+    const size_t w = in->cf_bytes;
+    const int ff_bits = w == 1 ? 8 : w == 2 ? 16 : 32;
+    mat_t *mat = calloc(1, sizeof(mat_t));
+    bs_t  *bs  = calloc(1, sizeof(bs_t));
+    md_t  *st  = calloc(1, sizeof(md_t));
+    st->fc = in->fc; st->gfc = in->fc; st->nthrds = threads; st->laopt = 2;
+    st->ff_bits = ff_bits; st->trace_level = NO_TRACER; st->info_level = 0;
+    st->nf = (in->flags & F4LA_FLAG_NORMALFORM) ? 1 : 0;
+    st->in_final_reduction_step = (in->flags & F4LA_FLAG_PIVOT_BY_LEAD) ? 1 : 0;
+    bs->ld = bs->sz = in->ncf;
+    void **cfarr = calloc(in->ncf ? in->ncf : 1, sizeof(void *));
+    for (uint32_t c = 0; c < in->ncf; ++c) cfarr[c] = (unsigned char *)in->cf + in->cf_ptr[c] * w;
+    bs->cf_8 = (cf8_t **)cfarr; bs->cf_16 = (cf16_t **)cfarr; bs->cf_32 = (cf32_t **)cfarr;
+    mat->ncl = in->ncl; mat->ncr = in->ncr; mat->nc = in->ncl + in->ncr;
+    hm_t **rows = malloc((n ? n : 1) * sizeof(hm_t *));
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint64_t len = in->row_ptr[r + 1] - in->row_ptr[r];
+        hm_t *row = malloc((len + OFFSET) * sizeof(hm_t));
+        row[DEG] = 0; row[BINDEX] = r; row[MULT] = 7 * r + 1; row[COEFFS] = in->row_cf[r];
+        row[PRELOOP] = (hm_t)(len % UNROLL); row[LENGTH] = (hm_t)len;
+        memcpy(row + OFFSET, in->cols + in->row_ptr[r], len * sizeof(hm_t));
+        rows[r] = row;
+    }
+    if (which == 2) {
+        if (in->nru) { free(rows); return -1; }
+        mat->rr = rows; mat->tr = NULL; mat->nr = mat->nru = in->nrl; mat->nrl = 0; mat->sz = in->nrl;
+        if (fn) ((ir_fn_t)fn)(mat, bs, st, 0); else dispatch_interreduce_matrix_rows(mat, bs, st, 0);
+    } else {
+        mat->nru = in->nru; mat->nrl = in->nrl; mat->nr = mat->sz = n;
+        mat->rr = malloc((in->nru ? in->nru : 1) * sizeof(hm_t *));
+        mat->tr = malloc((in->nrl ? in->nrl : 1) * sizeof(hm_t *));
+        memcpy(mat->rr, rows, in->nru * sizeof(hm_t *));
+        memcpy(mat->tr, rows + in->nru, in->nrl * sizeof(hm_t *));
+        free(rows);
+        if (which == 1) {
+            typedef int (*app_fn_t)(mat_t *, const bs_t *const, md_t *);
+            const int r = fn ? ((app_fn_t)fn)(mat, bs, st) : 0;
+            if (!fn) dispatch_linear_algebra(mat, bs, bs, st);      /* the reference's own app variant is stale */
+            if (ret) *ret = fn ? r : (mat->np != in->nrl);
+        } else {
+            if (fn) ((la_fn_t)fn)(mat, bs, bs, st);
+            else if (in->flags & (F4LA_FLAG_NORMALFORM | F4LA_FLAG_PIVOT_BY_LEAD)) dispatch_exact_linear_algebra(mat, bs, bs, st);
+            else dispatch_linear_algebra(mat, bs, bs, st);
+        }
+    }
+    uint32_t *bi, *mu;
+    flatten_output(out, &bi, &mu, mat, st);
+    out->src_row = bi;
+    if (out_coeffs_index)
+        for (len_t i = 0; i < mat->np; ++i) out_coeffs_index[i] = mat->tr[i] ? mat->tr[i][COEFFS] : 0xffffffffu;
+    /* MULT was set to 7*BINDEX+1: a backend must carry both over together (the reference's own
+     * 8/16-bit reducers leave them unset, la_ff_16.c:407-409, so it is not checked itself) */
+    int bad = 0;
+    if (fn) for (len_t i = 0; i < mat->np; ++i) if (mat->tr[i] && mu[i] != 7 * bi[i] + 1) bad = 1;
+    free(mu);
+    for (len_t i = 0; i < mat->np; ++i) {
+        if (!mat->tr || !mat->tr[i]) continue;
+        hm_t ci = mat->tr[i][COEFFS];
+        if (ff_bits == 8) free(mat->cf_8[ci]); else if (ff_bits == 16) free(mat->cf_16[ci]); else free(mat->cf_32[ci]);
+        free(mat->tr[i]);
+    }
+    free(mat->rr); free(mat->tr); free(mat->cf_8); free(mat->cf_16); free(mat->cf_32);
+    free(mat); free(cfarr); free(bs); free(st);
+    return bad ? -2 : 0;
+}
+
 void refh_free_result(f4la_flat_result *r)
 {
     free(r->row_ptr); free(r->cols); free(r->cf); free(r->src_row);

@@ -242,6 +242,26 @@ def primes_above(start: int, n: int):
     return out
 
 
+def call_entry(m: FlatMatrix, which: int, fn=None, threads: int = 1):
+    """Drive a matrix-level entry point (reference dispatcher when fn is None, else the
+    given function address) on a flat matrix.  -> (FlatResult, int return value, COEFFS indices)"""
+    L = lib()
+    L.refh_call_entry.restype = C.c_int
+    L.refh_call_entry.argtypes = [C.POINTER(CFlatMatrix), C.c_int32, C.c_void_p, C.c_int32,
+                                  C.POINTER(CFlatResult), C.POINTER(C.c_int32), C.c_void_p]
+    cm = m.c_struct()
+    res = CFlatResult()
+    ret = C.c_int32(0)
+    cidx = np.zeros(m.nru + m.nrl + m.ncl + m.ncr + 1, dtype=np.uint32)
+    addr = None if fn is None else (fn if isinstance(fn, int) else C.cast(fn, C.c_void_p).value)
+    rc = L.refh_call_entry(C.byref(cm), which, addr, threads, C.byref(res), C.byref(ret), cidx.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"refh_call_entry failed: {rc} (-2: BINDEX/MULT not carried over together)")
+    out = FlatResult.from_c(res)
+    L.refh_free_result(C.byref(res))
+    return out, int(ret.value), cidx[:out.nrows].copy()
+
+
 def struct_layout() -> List[int]:
     buf = (C.c_uint64 * 128)()
     n = lib().refh_struct_layout(buf, 128)

@@ -217,3 +217,40 @@ def test_gpu_rba_bits_match_multipliers(backend):
         if n >= 6:
             break
     assert n > 2
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+def test_gpu_interreduce_and_application_entry_points():
+    """The remaining matrix-level pointers of data.h:529-595 driven on mat_t/bs_t/md_t built by
+    the harness: interreduce_matrix_rows (la_ff_32.c:4254) against the reference's dispatcher,
+    application_linear_algebra (return code + rows) against the reference's exact LA."""
+    import ctypes as C
+    import gpu_helpers
+    L = gpu_helpers.install_backend()
+    ir = C.cast(L.f4la_b200_interreduce_matrix_rows, C.c_void_p).value
+    app = C.cast(L.f4la_b200_application_linear_algebra, C.c_void_p).value
+    n_ir = n_app = n_bad = 0
+    try:
+        for path in golden_io.fixture_files():
+            for m, ref, meta in golden_io.load_cases(path):
+                if meta["kind"] == 1:
+                    # all rows of the final reduction step have distinct lead columns
+                    m2 = FlatMatrix(m.fc, 0, m.nru + m.nrl, 0, m.ncl + m.ncr, m.row_ptr, m.cols, m.row_cf,
+                                    m.cf_ptr, m.cf, flags=0)
+                    want, _, want_idx = rh.call_entry(m2, 2, None)
+                    got, _, got_idx = rh.call_entry(m2, 2, ir)
+                    assert got.same_rows(want) and np.array_equal(got_idx, want_idx)
+                    n_ir += 1
+                elif m.nru > 0:
+                    want, want_ret, _ = rh.call_entry(m, 1, None)
+                    got, got_ret, _ = rh.call_entry(m, 1, app)
+                    assert got_ret == want_ret
+                    if got_ret == 0:
+                        assert got.same_rows(want) and got.same_rows(ref)
+                    else:
+                        assert got.nrows == 0
+                        n_bad += 1
+                    n_app += 1
+    finally:
+        gpu_helpers.uninstall_backend()
+    assert n_ir >= 5 and n_app >= 20 and n_bad >= 1
