@@ -49,6 +49,8 @@ struct f4la_ctx {
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
     DevBuf sched, items, flowflags, mailbox;
     size_t        panel_smem_optin = 0;
+    int           ge_columnwise = 0;    /* F4LA_B200_GE=columnwise: one find + one elimination pass per pivot (fallback, A-B) */
+    size_t        batch_smem_optin = 0;
     int           ge_panel = 0;         /* F4LA_B200_GE=panel: cluster/shared-memory panels (experimental, slower on low-rank blocks) */
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
@@ -451,6 +453,37 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(s));
+        } else if ((size_t)nrl * 5 + 64 <= smem_cap && !ctx->ge_columnwise) {
+            /* batched: discover up to kGeBatch pivots on one SM, then one update pass over the block */
+            const size_t disc_smem = (size_t)nrl * 5 + 64, upd_smem = (size_t)nrl * 4;
+            if (disc_smem > ctx->batch_smem_optin) {
+                CU(cudaFuncSetAttribute(k_ge_discover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                CU(cudaFuncSetAttribute(k_ge_batch_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                ctx->batch_smem_optin = smem_cap;
+            }
+            k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+            ctx->launches++;
+            for (uint32_t batches = 0;;) {
+                const int group = 4;
+                for (int k = 0; k < group; ++k) {
+                    k_ge_discover<<<1, kDiscoverThreads, disc_smem, s>>>(
+                        Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
+                        as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                        as<uint32_t>(ctx->pivinv), p, pinv);
+                    k_ge_batch_update<<<ncr, kUpdateThreads, upd_smem, s>>>(
+                        Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
+                        as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                        as<uint32_t>(ctx->pivinv), p, pinv);
+                    ctx->launches += 2;
+                }
+                batches += group;
+                CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+                CU(cudaGetLastError());
+                CU(cudaStreamSynchronize(s));
+                if (h_state->done) break;
+                if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
+                    return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+            }
         } else {
         k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
         ctx->launches++;
@@ -691,6 +724,7 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_panel = ge && !strcmp(ge, "panel");
+    ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
     const char *bud = getenv("F4LA_B200_L2_MB");
     ctx->l2_budget = bud && atoi(bud) > 0 ? (size_t)atoi(bud) << 20 : kL2BudgetDefault;
     return ctx;

@@ -70,6 +70,21 @@ __device__ __forceinline__ uint32_t mulmod(uint32_t a, uint32_t b, uint32_t p, u
     return mod_u64((uint64_t)a * b, p, pinv);
 }
 
+/* Shoup multiplication by a fixed scalar sc < p < 2^31: w = floor(sc * 2^32 / p) once, then
+ * f * sc mod p costs one mul.hi, two mul.lo and a conditional subtraction (the estimate of the
+ * quotient is short by at most one, so the remainder lies in [0, 2p) and fits 32 bits). */
+__device__ __forceinline__ uint32_t shoup_pre(uint32_t sc, uint32_t p)
+{
+    return (uint32_t)(((uint64_t)sc << 32) / p);
+}
+
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t f, uint32_t sc, uint32_t w, uint32_t p)
+{
+    const uint32_t q = __umulhi(f, w);
+    const uint32_t r = f * sc - q * p;
+    return r >= p ? r - p : r;
+}
+
 /* Modular inverse by extended Euclid (same recurrence as the reference's
  * mod_p_inverse_32, tools.h:95-122). */
 __device__ __forceinline__ uint32_t modinv(uint32_t val, uint32_t p)
@@ -878,6 +893,155 @@ k_ge_block_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_
     }
     if (touched)
         for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) g[r] = s_col[r];
+}
+
+/* ---- batched Gauss-Jordan: discover up to kGeBatch pivots, then one update pass ---- */
+/* k_ge_discover (one CTA) walks the flagged columns left to right; a visited column is loaded
+ * into shared memory, brought up to date with the pivots found EARLIER IN THIS BATCH (the
+ * pivots of previous batches were applied by k_ge_batch_update), and searched for a pivot.
+ * A pivot column is written back (it is final and carries the multipliers of its pivot);
+ * a column without pivot is discarded, the update pass recomputes it.
+ * k_ge_batch_update (one CTA per column) then applies the batch to every non-pivot column
+ * right of the batch's first pivot and refreshes the column flags.  Compared with one
+ * find + one full elimination pass per pivot this divides the number of passes over the
+ * block by the batch size. */
+constexpr uint32_t kGeBatch = 16;
+constexpr int kDiscoverThreads = 1024;
+
+/* dynamic smem: [nrows] column | [nrows] used bytes */
+__global__ void __launch_bounds__(kDiscoverThreads)
+k_ge_discover(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t ncr, const uint8_t *colflag, uint8_t *used,
+              uint8_t *ispiv, GEState *st, uint32_t *pivcol, uint32_t *pivrow, uint32_t *pivinv,
+              uint32_t p, uint64_t pinv)
+{
+    extern __shared__ uint32_t s_col[];
+    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_col + nrows);
+    __shared__ uint32_t s_min, s_inv;
+    const uint32_t tid = threadIdx.x;
+    if (st->done) {                        /* nothing left: make the following update pass a no-op */
+        if (tid == 0) st->cur_col = st->rank;
+        return;
+    }
+    const uint32_t k0 = st->rank;
+    uint32_t c = st->next_col;
+    for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_used[r] = used[r];
+    __syncthreads();
+    uint32_t np = 0, misses = 0;
+    bool exhausted = false;
+    /* the flags are as of the last update pass: a flagged column may turn out empty once the
+     * pivots of this batch are applied.  Two such misses in a row end the batch, the update
+     * pass then refreshes every flag (this is what ends the elimination when the rank is
+     * exhausted: no column stays flagged). */
+    while (np < kGeBatch && misses < 2) {
+        /* next flagged column */
+        if (tid == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t base = c; base < ncr; base += kDiscoverThreads) {
+            const uint32_t k = base + tid;
+            if (k < ncr && colflag[k]) atomicMin(&s_min, k);
+            __syncthreads();
+            if (s_min != 0xffffffffu) break;           /* uniform: read after the barrier */
+            __syncthreads();
+        }
+        __syncthreads();
+        c = s_min;
+        __syncthreads();
+        if (c == 0xffffffffu) { exhausted = true; break; }
+        uint32_t *g = D + (size_t)c * ld;
+        for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_col[r] = g[r];
+        __syncthreads();
+        for (uint32_t k = k0; k < k0 + np; ++k) {       /* pivots of this batch, all left of c */
+            const uint32_t piv = pivrow[k];
+            const uint32_t sc = mulmod(s_col[piv], pivinv[k], p, pinv);
+            __syncthreads();                            /* everybody has read s_col[piv] */
+            if (sc != 0) {
+                const uint32_t *fcol = D + (size_t)pivcol[k] * ld;
+                const uint32_t w = shoup_pre(sc, p);
+                for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
+                    const uint32_t f = __ldcg(&fcol[r]);
+                    if (f && r != piv) {
+                        const uint32_t t = shoup_mul(f, sc, w, p);
+                        const uint32_t v = s_col[r];
+                        s_col[r] = v >= t ? v - t : v + p - t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t r = tid; r < nrows; r += kDiscoverThreads)
+            if (s_col[r] != 0 && !s_used[r]) { atomicMin(&s_min, r); break; }
+        __syncthreads();
+        const uint32_t piv = s_min;
+        if (piv != 0xffffffffu) {
+            for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) g[r] = s_col[r];
+            if (tid == 0) {
+                const uint32_t inv = modinv(s_col[piv], p);
+                pivcol[k0 + np] = c; pivrow[k0 + np] = piv; pivinv[k0 + np] = inv;
+                used[piv] = 1; s_used[piv] = 1; ispiv[c] = 1;
+            }
+            __threadfence();
+            np++;
+            misses = 0;
+        } else {
+            misses++;
+        }
+        __syncthreads();
+        c = c + 1;
+    }
+    if (tid == 0) {
+        st->cur_col = k0;                 /* batch = pivots [cur_col, rank) */
+        st->rank = k0 + np;
+        st->next_col = exhausted ? ncr : c;
+        if (exhausted) st->done = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kUpdateThreads)
+k_ge_batch_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t ncr,
+                  uint8_t *__restrict__ colflag, const uint8_t *__restrict__ used,
+                  const uint8_t *__restrict__ ispiv, const GEState *__restrict__ st,
+                  const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,
+                  const uint32_t *__restrict__ pivinv, uint32_t p, uint64_t pinv)
+{
+    extern __shared__ uint32_t s_col[];
+    const uint32_t k0 = st->cur_col, k1 = st->rank;
+    if (k0 >= k1) return;
+    const uint32_t c = blockIdx.x;
+    if (c >= ncr || ispiv[c] || c <= pivcol[k0]) return;
+    uint32_t *g = D + (size_t)c * ld;
+    for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) s_col[r] = g[r];
+    __syncthreads();
+    bool touched = false;
+    for (uint32_t k = k0; k < k1; ++k) {
+        if (pivcol[k] >= c) break;                       /* pivot columns ascend within a batch */
+        const uint32_t piv = pivrow[k];
+        const uint32_t sc = mulmod(s_col[piv], pivinv[k], p, pinv);
+        __syncthreads();
+        if (sc != 0) {                                   /* uniform over the CTA */
+            touched = true;
+            const uint32_t *fcol = D + (size_t)pivcol[k] * ld;
+            const uint32_t w = shoup_pre(sc, p);
+            for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) {
+                const uint32_t f = __ldg(&fcol[r]);
+                if (f && r != piv) {
+                    const uint32_t t = shoup_mul(f, sc, w, p);
+                    const uint32_t v = s_col[r];
+                    s_col[r] = v >= t ? v - t : v + p - t;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    int any = 0;
+    for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) {
+        const uint32_t v = s_col[r];
+        if (touched) g[r] = v;
+        any |= (v != 0) && !used[r];
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) colflag[c] = (uint8_t)(any != 0);
 }
 
 /* Reduced echelon rows, dense: row t = pivot rank-1-t (decreasing lead). */
