@@ -112,6 +112,10 @@ typedef struct f4la_stats {
     uint64_t bytes_d2h;
     uint32_t kernel_launches; /* kernels launched by this library in the call */
     uint32_t rank;            /* number of new pivots                         */
+    double   ms_hot_kernel;   /* sum over the launches of k_pull_flow (CUDA
+                                 events around each launch)                   */
+    uint32_t hot_kernel_launches;
+    uint32_t reserved;
 } f4la_stats;
 
 typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */

@@ -37,10 +37,13 @@ double now_ms()
 
 } // namespace
 
+constexpr int kMaxFlowEvents = 512;
+
 struct f4la_ctx {
     int           device = 0;
     cudaStream_t  stream = nullptr;
     cudaEvent_t   ev[8] = {};
+    cudaEvent_t   flow_ev[kMaxFlowEvents] = {};   /* around every launch of the hot kernel */
     int           sm_count = 0;
     char          err[512] = {0};
     uint32_t      launches = 0;
@@ -370,6 +373,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     if (want_rba && rba_words) OK(ensure(ctx, ctx->rba, (size_t)nrl * rba_words * 4 + 16));
 
     uint32_t epoch = 0;
+    int n_flow_ev = 0;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
@@ -379,7 +383,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             ctx->launches++;
         }
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
-        k_scatter_lower<<<blocks_for_warps(rows_here), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
+        k_scatter_lower<<<blocks_for_warps((uint64_t)rows_here * kScatterSplit), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
                                                                     d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
                                                                     as<uint32_t>(ctx->flowflags),
                                                                     as<uint32_t>(ctx->V), d_err);
@@ -395,7 +399,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
         f.p = p; f.pinv = pinv;
         CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
+        if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
+        if (st && n_flow_ev + 2 <= kMaxFlowEvents) { CU(cudaEventRecord(ctx->flow_ev[n_flow_ev + 1], s)); n_flow_ev += 2; }
         if (want_rba && rba_words) {
             dim3 grid(rba_words, g * (Rc / 128));
             k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
@@ -585,20 +591,28 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->nrows = nout; out->cf_bytes = d.cf_bytes;
         out->row_ptr = (uint64_t *)malloc(((size_t)nout + 1) * sizeof(uint64_t));
         out->src_row = (uint32_t *)malloc((size_t)nout * sizeof(uint32_t));
+        std::vector<uint64_t> rnz(nout, 0);
+#pragma omp parallel for schedule(static) if (nout > 16)
+        for (uint32_t t = 0; t < nout; ++t) {
+            if (pick[t] < 0) continue;
+            const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
+            uint64_t n = 0;
+            for (uint32_t c = 0; c < ncr; ++c) n += row[c] != 0;
+            rnz[t] = n;
+        }
         uint64_t nnz = 0;
         for (uint32_t t = 0; t < nout; ++t) {
             out->row_ptr[t] = nnz;
             out->src_row[t] = (nf_mode || by_lead) ? t : h_pivrow[rank - 1 - t];
-            if (pick[t] < 0) continue;
-            const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
-            for (uint32_t c = 0; c < ncr; ++c) nnz += row[c] != 0;
+            nnz += rnz[t];
         }
         out->row_ptr[nout] = nnz;
         out->cols = (uint32_t *)malloc((nnz ? nnz : 1) * sizeof(uint32_t));
         out->cf = malloc((nnz ? nnz : 1) * (size_t)d.cf_bytes);
-        uint64_t k = 0;
+#pragma omp parallel for schedule(static) if (nout > 16)
         for (uint32_t t = 0; t < nout; ++t) {
             if (pick[t] < 0) continue;
+            uint64_t k = out->row_ptr[t];
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
             for (uint32_t c = 0; c < ncr; ++c) {
                 const uint32_t v = row[c];
@@ -627,6 +641,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_reduce = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st->ms_echelon = ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_d2h = ms;
+        for (int k = 0; k < n_flow_ev; k += 2) {
+            cudaEventElapsedTime(&ms, ctx->flow_ev[k], ctx->flow_ev[k + 1]);
+            st->ms_hot_kernel += ms;
+        }
+        st->hot_kernel_launches = (uint32_t)(n_flow_ev / 2);
         st->units = (uint64_t)nnz_pull * nrl;
         st->pivot_applications = (uint64_t)nnz_pull;
         st->bytes_d2h = d2h_bytes;
@@ -722,6 +741,7 @@ f4la_ctx *f4la_b200_create(int device)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_panel = ge && !strcmp(ge, "panel");
     ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
@@ -745,6 +765,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
     for (auto &e : ctx->ev) cudaEventDestroy(e);
+    for (auto &e : ctx->flow_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -41,6 +41,7 @@ constexpr int kWarpsPerBlock  = kSolveThreads / 32;
 constexpr int kRowsPerT       = 128;   /* rows covered by one uint4 per lane */
 constexpr int kMaxT           = 4;     /* chunk = 128*T rows, T in 1..4      */
 constexpr uint32_t kFoldEvery = 1u << 15; /* entries between overflow folds  */
+constexpr uint32_t kScatterSplit = 8;  /* warps per lower row in k_scatter_lower */
 constexpr uint32_t kLongColumn = 128;  /* >= this many entries: one CTA/col  */
 constexpr int kLenClasses     = 7;     /* class 0 = long, 1..6 = short columns by decreasing length */
 
@@ -328,12 +329,15 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t r0 = chunk0 * Rc;
     const uint32_t r1 = min(nrl, (chunk0 + nchunks) * Rc);
-    for (uint32_t r = r0 + warp; r < r1; r += nwarps) {
+    /* kScatterSplit warps share a row: a chunk has only a few hundred rows */
+    const uint32_t nwork = (r1 - r0) * kScatterSplit;
+    for (uint32_t wk = warp; wk < nwork; wk += nwarps) {
+        const uint32_t r = r0 + wk / kScatterSplit, part = wk % kScatterSplit;
         const uint64_t a = row_ptr[nru + r], b = row_ptr[nru + r + 1];
         const uint64_t c0 = cf_ptr[row_cf[nru + r]];
         const uint32_t lc = (r - r0) / Rc, lr = (r - r0) % Rc;
         uint32_t *Vc = V + (size_t)lc * nc * Rc;
-        for (uint64_t k = a + lane; k < b; k += 32) {
+        for (uint64_t k = a + part * 32 + lane; k < b; k += 32 * kScatterSplit) {
             uint32_t j = cols[k];
             if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
             if (colmap) j = colmap[j];
