@@ -254,3 +254,42 @@ def test_gpu_interreduce_and_application_entry_points():
     finally:
         gpu_helpers.uninstall_backend()
     assert n_ir >= 5 and n_app >= 20 and n_bad >= 1
+
+
+def test_gpu_very_long_column_folds_accumulators(backend):
+    """A non-pivot column fed by 40 000 pivot rows: more than 2^15 products go into one
+    64-bit accumulator pair, which exercises the overflow fold of the hot kernel."""
+    p = 2147483629                       # largest 31-bit prime: worst case for the accumulators
+    rng = np.random.default_rng(5)
+    nru, nrl, ncr = 40000, 70, 3
+    rows, cfs = [], []
+    for i in range(nru):
+        rows.append(np.array([i, nru + (i % 2)]))               # lead + one entry in column nru or nru+1
+        cfs.append(np.array([1, p - 1 - (i % 7)]))
+    for r in range(nrl):
+        c = np.sort(rng.choice(nru + ncr, size=2000, replace=False))
+        rows.append(c)
+        cfs.append(rng.integers(p - 1000, p, size=len(c)))      # large residues
+    row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in rows])])
+    m = FlatMatrix(p, nru, nrl, nru, ncr, row_ptr, np.concatenate(rows), np.arange(nru + nrl), row_ptr.copy(),
+                   np.concatenate(cfs).astype(np.uint32))
+    out, st = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref) and out.nrows == 3
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+@pytest.mark.parametrize("name", ["katsura-11", "eco-12", "randquad-10"])
+def test_gpu_backend_inside_reference_f4_large(name):
+    """Larger members of the BASELINE families (config 2 and 4 shapes): all five LA pointers on
+    the GPU, reduced Groebner basis bit-exact against the reference's (tests/golden/gb_digests.json)."""
+    import gpu_helpers
+    p = P31
+    L = gpu_helpers.install_backend()
+    try:
+        gb = rh.run_f4(systems.by_name(name, p), p, threads=8, laopt=2)
+    finally:
+        gpu_helpers.uninstall_backend()
+    want = golden_io.gb_digests()[f"{name}@{p}"]
+    assert (len(gb.lens), int(gb.lens.sum())) == (want["nelts"], want["nterms"])
+    assert gb.digest() == want["digest"]
