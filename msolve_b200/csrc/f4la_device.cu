@@ -50,11 +50,9 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf sched, items, flowflags, mailbox;
-    size_t        panel_smem_optin = 0;
+    DevBuf sched, items, flowflags;
     int           ge_columnwise = 0;    /* F4LA_B200_GE=columnwise: one find + one elimination pass per pivot (fallback, A-B) */
     size_t        batch_smem_optin = 0;
-    int           ge_panel = 0;         /* F4LA_B200_GE=panel: cluster/shared-memory panels (experimental, slower on low-rank blocks) */
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
@@ -427,39 +425,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
         CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
         GEState *h_state = (GEState *)ctx->h_small.p;
-        /* blocked path when a panel of at least 8 columns fits the cluster's shared memory */
         const size_t smem_cap = (size_t)216 * 1024;
-        const size_t fixed = (size_t)nrl * 4 + nrl + 64;
-        uint32_t slots = fixed < smem_cap ? (uint32_t)((smem_cap - fixed) / ((size_t)nrl * 4)) : 0;
-        if (slots > (uint32_t)(kPanelMaxCols / kPanelCluster)) slots = kPanelMaxCols / kPanelCluster;
-        if (slots >= 1 && ctx->ge_panel) {
-            const uint32_t B = slots * kPanelCluster;
-            const size_t panel_smem = (size_t)slots * nrl * 4 + fixed;
-            const size_t upd_smem = (size_t)nrl * 4;
-            if (panel_smem > ctx->panel_smem_optin) {
-                CU(cudaFuncSetAttribute(k_ge_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                CU(cudaFuncSetAttribute(k_ge_block_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                ctx->panel_smem_optin = smem_cap;
-            }
-            OK(ensure(ctx, ctx->mailbox, 2 * kPanelMaxCols * 4));
-            for (uint32_t c0 = 0; c0 < ncr; c0 += B) {
-                const uint32_t c1 = c0 + B < ncr ? c0 + B : ncr;
-                k_ge_panel_smem<<<kPanelCluster, kPanelThreads, panel_smem, s>>>(
-                    Dm, ld, nrl, c0, c1, slots, as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
-                    as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
-                    as<uint32_t>(ctx->pivinv), as<uint32_t>(ctx->mailbox), p, pinv);
-                ctx->launches++;
-                if (c1 < ncr) {
-                    k_ge_block_update<<<ncr - c1, kUpdateThreads, upd_smem, s>>>(
-                        Dm, ld, nrl, c1, ncr, as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
-                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
-                    ctx->launches++;
-                }
-            }
-            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
-            CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(s));
-        } else if ((size_t)nrl * 5 + 64 <= smem_cap && !ctx->ge_columnwise) {
+        if ((size_t)nrl * 5 + 64 <= smem_cap && !ctx->ge_columnwise) {
             /* batched: discover up to kGeBatch pivots on one SM, then one update pass over the block */
             const size_t disc_smem = (size_t)nrl * 5 + 64, upd_smem = (size_t)nrl * 4;
             if (disc_smem > ctx->batch_smem_optin) {
@@ -743,7 +710,6 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
-    ctx->ge_panel = ge && !strcmp(ge, "panel");
     ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
     const char *bud = getenv("F4LA_B200_L2_MB");
     ctx->l2_budget = bud && atoi(bud) > 0 ? (size_t)atoi(bud) << 20 : kL2BudgetDefault;
@@ -758,7 +724,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->mailbox, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba};
     for (auto b : bufs) free_dev(*b);

@@ -741,163 +741,7 @@ __global__ void k_ge_eliminate(uint32_t *__restrict__ D, uint64_t ld, uint32_t n
     if (threadIdx.x == 0) colflag[cc] = (uint8_t)(any != 0);
 }
 
-/* ---- blocked right-looking Gauss-Jordan ---------------------------------- */
-/* The trailing block is swept in panels of up to 64 columns:
- *   k_ge_panel_smem  : ONE cluster of 8 CTAs holds the panel in its shared
- *                      memory (column ci lives in CTA ci % 8).  Columns are
- *                      visited in order; the owner looks for a pivot, publishes
- *                      {row, inverse} in a mailbox and the (final) pivot column
- *                      in global memory, one cluster barrier later every CTA
- *                      eliminates the pivot from the panel columns it owns.
- *   k_ge_block_update: one CTA per column right of the panel replays the
- *                      panel's pivots on its column, held in shared memory.
- * Pivot columns are final once chosen (they carry the multipliers), pivot rows
- * stay unnormalised (k_ge_extract applies the inverse), exactly as in the
- * column-at-a-time kernels above, which remain the fallback for blocks whose
- * columns do not fit shared memory. */
-constexpr int kPanelCluster = 8;
-constexpr int kPanelThreads = 512;
-constexpr int kPanelMaxCols = 64;
 constexpr int kUpdateThreads = 256;
-constexpr uint32_t kNoPivot = 0xffffffffu;
-
-__device__ __forceinline__ void cluster_barrier()
-{
-    __threadfence();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-/* dynamic smem: [slots][nrows] columns | [nrows] pivot column | [nrows] used bytes */
-__global__ void __cluster_dims__(kPanelCluster, 1, 1) __launch_bounds__(kPanelThreads)
-k_ge_panel_smem(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t c0, uint32_t c1, uint32_t slots,
-                uint8_t *used, uint8_t *ispiv, GEState *st, uint32_t *pivcol, uint32_t *pivrow,
-                uint32_t *pivinv, uint32_t *mailbox, uint32_t p, uint64_t pinv)
-{
-    extern __shared__ uint32_t smem[];
-    uint32_t *s_cols = smem;
-    uint32_t *s_f = smem + (size_t)slots * nrows;
-    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_f + nrows);
-    __shared__ uint32_t s_min, s_inv;
-    const uint32_t q = cluster_ctarank();
-    const uint32_t tid = threadIdx.x;
-    const uint32_t B = c1 - c0;
-
-    for (uint32_t sl = 0; sl < slots; ++sl) {
-        const uint32_t ci = sl * kPanelCluster + q;
-        if (ci >= B) break;
-        const uint32_t *g = D + (size_t)(c0 + ci) * ld;
-        for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_cols[(size_t)sl * nrows + r] = g[r];
-    }
-    for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_used[r] = used[r];
-    uint32_t rank = st->rank;
-    if (q == 0 && tid == 0) st->cur_col = rank;          /* first pivot of this panel, for the block update */
-    __syncthreads();
-
-    for (uint32_t ci = 0; ci < B; ++ci) {
-        const uint32_t c = c0 + ci;
-        if (ci % kPanelCluster == q) {                   /* owner: look for a pivot */
-            uint32_t *col = s_cols + (size_t)(ci / kPanelCluster) * nrows;
-            if (tid == 0) s_min = kNoPivot;
-            __syncthreads();
-            for (uint32_t r = tid; r < nrows; r += kPanelThreads)
-                if (col[r] != 0 && !s_used[r]) { atomicMin(&s_min, r); break; }
-            __syncthreads();
-            const uint32_t piv = s_min;
-            if (piv != kNoPivot) {
-                uint32_t *g = D + (size_t)c * ld;
-                for (uint32_t r = tid; r < nrows; r += kPanelThreads) g[r] = col[r];
-                if (tid == 0) s_inv = modinv(col[piv], p);
-                __threadfence();
-            }
-            __syncthreads();
-            if (tid == 0) { mailbox[2 * ci] = piv; mailbox[2 * ci + 1] = piv != kNoPivot ? s_inv : 0; }
-        }
-        cluster_barrier();
-        const uint32_t piv = __ldcg(&mailbox[2 * ci]);
-        if (piv == kNoPivot) continue;                   /* uniform over the cluster */
-        const uint32_t inv = __ldcg(&mailbox[2 * ci + 1]);
-        if (q == 0 && tid == 0) {
-            pivcol[rank] = c; pivrow[rank] = piv; pivinv[rank] = inv;
-            used[piv] = 1; ispiv[c] = 1;
-        }
-        rank++;
-        /* multipliers = the pivot column, now final in global memory */
-        const uint32_t *g = D + (size_t)c * ld;
-        for (uint32_t r = tid; r < nrows; r += kPanelThreads) s_f[r] = __ldcg(&g[r]);
-        if (tid == 0) s_used[piv] = 1;
-        __syncthreads();
-        for (uint32_t sl = 0; sl < slots; ++sl) {
-            const uint32_t cj = sl * kPanelCluster + q;
-            if (cj >= B) break;
-            if (cj <= ci) continue;
-            uint32_t *col = s_cols + (size_t)sl * nrows;
-            const uint32_t sc = mulmod(col[piv], inv, p, pinv);
-            if (sc == 0) continue;                       /* uniform over the CTA */
-            for (uint32_t r = tid; r < nrows; r += kPanelThreads) {
-                const uint32_t f = s_f[r];
-                if (f && r != piv) {
-                    const uint32_t t = mulmod(f, sc, p, pinv);
-                    const uint32_t v = col[r];
-                    col[r] = v >= t ? v - t : v + p - t;
-                }
-            }
-        }
-        __syncthreads();                                 /* s_f is reused by the next pivot */
-    }
-    /* the panel is final: write it back (pivot columns were stored when chosen and
-     * have not changed since) */
-    for (uint32_t sl = 0; sl < slots; ++sl) {
-        const uint32_t ci = sl * kPanelCluster + q;
-        if (ci >= B) break;
-        uint32_t *g = D + (size_t)(c0 + ci) * ld;
-        for (uint32_t r = tid; r < nrows; r += kPanelThreads) g[r] = s_cols[(size_t)sl * nrows + r];
-    }
-    if (q == 0 && tid == 0) { st->rank = rank; st->next_col = c1; }
-}
-
-/* replay pivots [st->cur_col, st->rank) (those of the last panel) on every column >= c1 */
-__global__ void __launch_bounds__(kUpdateThreads)
-k_ge_block_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t c1, uint32_t ncr,
-                  const GEState *__restrict__ st, const uint32_t *__restrict__ pivcol,
-                  const uint32_t *__restrict__ pivrow, const uint32_t *__restrict__ pivinv,
-                  uint32_t p, uint64_t pinv)
-{
-    extern __shared__ uint32_t s_col[];
-    const uint32_t k0 = st->cur_col, k1 = st->rank;
-    if (k0 >= k1) return;
-    const uint32_t c = c1 + blockIdx.x;
-    if (c >= ncr) return;
-    uint32_t *g = D + (size_t)c * ld;
-    for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) s_col[r] = g[r];
-    __syncthreads();
-    bool touched = false;
-    for (uint32_t k = k0; k < k1; ++k) {
-        const uint32_t piv = pivrow[k];
-        const uint32_t sc = mulmod(s_col[piv], pivinv[k], p, pinv);
-        if (sc != 0) {                                   /* uniform over the CTA */
-            touched = true;
-            const uint32_t *fcol = D + (size_t)pivcol[k] * ld;
-            for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) {
-                const uint32_t f = __ldg(&fcol[r]);
-                if (f && r != piv) {
-                    const uint32_t t = mulmod(f, sc, p, pinv);
-                    const uint32_t v = s_col[r];
-                    s_col[r] = v >= t ? v - t : v + p - t;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (touched)
-        for (uint32_t r = threadIdx.x; r < nrows; r += kUpdateThreads) g[r] = s_col[r];
-}
 
 /* ---- batched Gauss-Jordan: discover up to kGeBatch pivots, then one update pass ---- */
 /* k_ge_discover (one CTA) walks the flagged columns left to right; a visited column is loaded
