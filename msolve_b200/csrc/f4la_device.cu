@@ -27,7 +27,10 @@ struct HostBuf {            /* pinned */
     size_t cap = 0;
 };
 
-constexpr size_t kL2BudgetDefault = (size_t)88 << 20;   /* bytes of V kept in flight */
+/* bytes of V (vectors of the chunks in flight).  Measured on K12: keeping V inside the 126 MB L2
+ * (88 MB) is SLOWER than letting all chunks run in one launch (1.3 GB of V, most hot vectors
+ * still hit L2): the kernel is latency bound and wants the parallelism. */
+constexpr size_t kL2BudgetDefault = (size_t)1024 << 20;
 
 double now_ms()
 {
@@ -57,6 +60,7 @@ struct f4la_ctx {
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
+    int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense;
 };
 
@@ -322,7 +326,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
 
     /* ---- 3. chunking of the lower rows ---- */
     int T = (int)((nrl + kRowsPerT - 1) / kRowsPerT);
-    if (T > kMaxT) T = kMaxT;
+    if (T > ctx->tmax) T = ctx->tmax;
     const size_t kL2Budget = ctx->l2_budget;
     while (T > 1 && (size_t)nc * kRowsPerT * T * 4 > kL2Budget) --T;
     const uint32_t Rc = kRowsPerT * T;
@@ -711,6 +715,8 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
+    const char *tm = getenv("F4LA_B200_TMAX");
+    if (tm && atoi(tm) >= 1 && atoi(tm) <= kMaxT) ctx->tmax = atoi(tm);
     const char *bud = getenv("F4LA_B200_L2_MB");
     ctx->l2_budget = bud && atoi(bud) > 0 ? (size_t)atoi(bud) << 20 : kL2BudgetDefault;
     return ctx;
