@@ -753,7 +753,7 @@ constexpr int kUpdateThreads = 256;
  * right of the batch's first pivot and refreshes the column flags.  Compared with one
  * find + one full elimination pass per pivot this divides the number of passes over the
  * block by the batch size. */
-constexpr uint32_t kGeBatch = 16;
+constexpr uint32_t kGeBatch = 8;
 constexpr int kDiscoverThreads = 1024;
 
 /* dynamic smem: [nrows] column | [nrows] used bytes */
