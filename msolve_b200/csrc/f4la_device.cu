@@ -60,6 +60,7 @@ struct f4la_ctx {
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
+    int           bulk = 0;             /* F4LA_B200_BULK=1: bulk-copy (TMA engine) staging of the source vectors */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense;
 };
@@ -136,24 +137,36 @@ inline unsigned blocks_for_warps(uint64_t nwarps, int threads = 256)
     return (unsigned)b;
 }
 
-template <int T, bool WIDE>
-int flow_occupancy()
+template <int T, bool WIDE, bool BULK>
+int flow_occupancy(size_t smem)
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pull_flow<T, WIDE>, kSolveThreads, 0) != cudaSuccess) n = 2;
+    if (BULK && smem > 48 * 1024)
+        cudaFuncSetAttribute(k_pull_flow<T, WIDE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pull_flow<T, WIDE, BULK>, kSolveThreads, smem) != cudaSuccess) n = 2;
     return n < 1 ? 1 : n;
+}
+
+size_t flow_smem(int T, bool bulk)
+{
+    return bulk ? (size_t)kWarpsPerBlock * kBulkStages * ((size_t)T * kRowsPerT * 4 + 8) : 0;
 }
 
 int flow_blocks(f4la_ctx *ctx, int T, bool wide)
 {
     int &c = ctx->flow_blocks_per_sm[wide ? 1 : 0][T];
     if (c == 0) {
+        const bool b = ctx->bulk != 0;
+        const size_t sm = flow_smem(T, b);
+#define OCC(TT) (b ? (wide ? flow_occupancy<TT, true, true>(sm) : flow_occupancy<TT, false, true>(sm))          \
+                   : (wide ? flow_occupancy<TT, true, false>(sm) : flow_occupancy<TT, false, false>(sm)))
         switch (T) {
-            case 1: c = wide ? flow_occupancy<1, true>() : flow_occupancy<1, false>(); break;
-            case 2: c = wide ? flow_occupancy<2, true>() : flow_occupancy<2, false>(); break;
-            case 3: c = wide ? flow_occupancy<3, true>() : flow_occupancy<3, false>(); break;
-            default: c = wide ? flow_occupancy<4, true>() : flow_occupancy<4, false>(); break;
+            case 1: c = OCC(1); break;
+            case 2: c = OCC(2); break;
+            case 3: c = OCC(3); break;
+            default: c = OCC(4); break;
         }
+#undef OCC
     }
     return c;
 }
@@ -165,9 +178,13 @@ void launch_flow(f4la_ctx *ctx, int T, const FlowArgs &a, bool wide)
     uint64_t g = (uint64_t)ctx->sm_count * flow_blocks(ctx, T, wide);
     if (g > total) g = total;
     const unsigned grid = (unsigned)g;
-#define FLOW(TT)                                                                                   \
-    if (wide) k_pull_flow<TT, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);                    \
-    else      k_pull_flow<TT, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a)
+    const bool b = ctx->bulk != 0;
+    const size_t sm = flow_smem(T, b);
+#define FLOW(TT)                                                                                          \
+    if (b) { if (wide) k_pull_flow<TT, true, true><<<grid, kSolveThreads, sm, ctx->stream>>>(a);           \
+             else      k_pull_flow<TT, false, true><<<grid, kSolveThreads, sm, ctx->stream>>>(a); }        \
+    else   { if (wide) k_pull_flow<TT, true, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a);           \
+             else      k_pull_flow<TT, false, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a); }
     switch (T) {
         case 1: FLOW(1); break;
         case 2: FLOW(2); break;
@@ -715,6 +732,8 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
+    const char *bk = getenv("F4LA_B200_BULK");
+    ctx->bulk = bk && atoi(bk) != 0;
     const char *tm = getenv("F4LA_B200_TMAX");
     if (tm && atoi(tm) >= 1 && atoi(tm) <= kMaxT) ctx->tmax = atoi(tm);
     const char *bud = getenv("F4LA_B200_L2_MB");

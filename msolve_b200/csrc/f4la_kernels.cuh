@@ -511,14 +511,164 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
     }
 }
 
+/* ---- bulk-copy (TMA engine) variant of the inner loop ------------------------------------ */
+/* The register file bounds the bytes a warp can keep in flight with LDG (4 registers per lane
+ * and 16-byte load).  Here the source vectors (one contiguous 128*T*4-byte line each) are
+ * fetched by the bulk-copy engine straight into a per-warp ring in shared memory
+ * (cp.async.bulk.shared.global, completion on an mbarrier per stage), lanes read them back
+ * with conflict-free LDS.128.  kBulkStages copies are in flight per warp. */
+constexpr int kBulkStages = 8;
+
+struct BulkPipe {
+    uint32_t stage_base;   /* shared address of this warp's ring                  */
+    uint32_t bar_base;     /* shared address of this warp's kBulkStages mbarriers */
+    uint32_t issued;
+    uint32_t consumed;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void bulk_issue(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int T, bool WIDE>
-__global__ void __launch_bounds__(kSolveThreads, (T <= 2) ? 4 : 2)
+__device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const uint32_t *__restrict__ Vc,
+                                                     const uint32_t *__restrict__ flagc,
+                                                     uint32_t b0, uint32_t b1, uint32_t lane,
+                                                     uint64_t (&lo)[T][4], uint64_t (&hi)[T][4], BulkPipe &pp)
+{
+    constexpr uint32_t kBytes = T * kRowsPerT * 4;
+    const uint32_t Rc = A.Rc;
+    uint32_t since_fold = 0;
+    for (uint32_t b = b0; b < b1; b += 32) {
+        const uint32_t n = min(32u, b1 - b);
+        uint2 en = make_uint2(0, 0);
+        uint32_t f = kFlagAlwaysZ;
+        if (lane < n) {
+            en = __ldg(&A.ent[b + lane]);
+            f = ld_acquire(&flagc[en.x]);
+        }
+        bool ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
+        uint32_t spins = 0;
+        while (!__all_sync(0xffffffffu, ready)) {
+            if (!ready) {
+                __nanosleep(64);
+                f = ld_acquire(&flagc[en.x]);
+                ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
+                if (++spins > kSpinLimit) { atomicOr(A.err, kErrWatchdog); ready = true; }
+            }
+        }
+        __syncwarp();
+        /* the vectors were written through the generic proxy (by other SMs), the bulk engine reads
+         * through the async proxy */
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t live = __ballot_sync(0xffffffffu, lane < n && (f & 1u));
+        const uint32_t nl = __popc(live);
+        since_fold += nl;
+        /* compact: lane k holds the k-th live entry */
+        const uint32_t from = __fns(live, 0, lane + 1) & 31u;
+        const uint32_t csrc = __shfl_sync(0xffffffffu, en.x, from);
+        const uint32_t ccf  = __shfl_sync(0xffffffffu, en.y, from);
+
+        const uint32_t npro = min((uint32_t)kBulkStages, nl);
+        for (uint32_t k = 0; k < npro; ++k) {
+            const uint32_t s = __shfl_sync(0xffffffffu, csrc, k);
+            if (lane == 0) {
+                const uint32_t st = pp.issued % kBulkStages;
+                bulk_issue(pp.stage_base + st * kBytes, Vc + (size_t)s * Rc, kBytes, pp.bar_base + st * 8);
+            }
+            pp.issued++;
+        }
+        for (uint32_t k = 0; k < nl; ++k) {
+            const uint32_t st = pp.consumed % kBulkStages;
+            const uint32_t parity = (pp.consumed / kBulkStages) & 1u;
+            uint32_t tries = 0;
+            while (!mbar_try_wait(pp.bar_base + st * 8, parity)) {
+                if (++tries > kSpinLimit) { atomicOr(A.err, kErrWatchdog); break; }
+            }
+            uint4 v[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) v[t] = lds_u4(pp.stage_base + st * kBytes + t * 512 + lane * 16);
+            const uint32_t cf = __shfl_sync(0xffffffffu, ccf, k);
+            const uint32_t cl = WIDE ? (cf & 0xffffu) : cf;
+            const uint32_t ch = cf >> 16;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                lo[t][0] += (uint64_t)v[t].x * cl; lo[t][1] += (uint64_t)v[t].y * cl;
+                lo[t][2] += (uint64_t)v[t].z * cl; lo[t][3] += (uint64_t)v[t].w * cl;
+                if (WIDE) {
+                    hi[t][0] += (uint64_t)v[t].x * ch; hi[t][1] += (uint64_t)v[t].y * ch;
+                    hi[t][2] += (uint64_t)v[t].z * ch; hi[t][3] += (uint64_t)v[t].w * ch;
+                }
+            }
+            pp.consumed++;
+            __syncwarp();                 /* every lane has read the stage before it is refilled */
+            if (k + kBulkStages < nl) {
+                const uint32_t s = __shfl_sync(0xffffffffu, csrc, k + kBulkStages);
+                if (lane == 0) {
+                    const uint32_t st2 = pp.issued % kBulkStages;
+                    bulk_issue(pp.stage_base + st2 * kBytes, Vc + (size_t)s * Rc, kBytes, pp.bar_base + st2 * 8);
+                }
+                pp.issued++;
+            }
+        }
+        if (since_fold >= kFoldEvery) {
+            since_fold = 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
+                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
+                }
+        }
+    }
+}
+
+template <int T, bool WIDE, bool BULK>
+__global__ void __launch_bounds__(kSolveThreads, BULK ? 2 : ((T <= 2) ? 4 : 2))
 k_pull_flow(const FlowArgs A)
 {
     __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];
     __shared__ uint32_t s_id;
+    extern __shared__ __align__(128) uint8_t dyn_smem[];      /* BULK: rings + mbarriers */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t total = A.n_items * A.G;
+
+    BulkPipe pp = {0, 0, 0, 0};
+    if (BULK) {
+        constexpr uint32_t kBytes = T * kRowsPerT * 4;
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(dyn_smem);
+        pp.stage_base = base + warp * kBulkStages * kBytes;
+        pp.bar_base = base + kWarpsPerBlock * kBulkStages * kBytes + warp * kBulkStages * 8;
+        if (lane == 0) {
+            for (int st = 0; st < kBulkStages; ++st) mbar_init(pp.bar_base + st * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     for (;;) {
         if (threadIdx.x == 0) s_id = atomicAdd(A.counter, 1u);
@@ -543,7 +693,8 @@ k_pull_flow(const FlowArgs A)
             if (warp < cnt) {
                 const uint32_t j = A.sched[pos + warp];
                 const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-                flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi);
+                if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi, pp);
+                else flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi);
                 const bool to_out = j >= A.ncl;
                 uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                        : Vc + (size_t)j * A.Rc;
@@ -576,7 +727,8 @@ k_pull_flow(const FlowArgs A)
             /* equal contiguous shares of the entries for the 8 warps */
             const uint32_t seg = (e1 - e0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
             const uint32_t b0 = min(e1, e0 + warp * seg), b1 = min(e1, b0 + seg);
-            flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi);
+            if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi, pp);
+            else flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi);
         }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
