@@ -311,3 +311,110 @@ def test_gpu_columnwise_elimination_fallback(monkeypatch):
         assert n > 20
     finally:
         be.close()
+
+
+def test_gpu_more_edge_cases(backend):
+    """p = 2, empty lower rows, duplicate lower rows, a lower-row count beyond the shared-memory
+    limit of the batched elimination (column-at-a-time fallback), resident-matrix API."""
+    rng = np.random.default_rng(99)
+    # p = 2 and p = 3
+    for p in (2, 3):
+        m = random_matrix(rng, p, 120, 75, 31, 0.2, np.uint8)
+        out, _ = backend.reduce(m)
+        ref, _, _ = oracle.reduce(m)
+        assert out.same_rows(ref), p
+    # empty and duplicate lower rows
+    p = P16
+    rows = [np.array([0, 3, 5]), np.array([1, 4]), np.array([2, 3, 4, 5])]       # pivots 0..2, cols 3..5 free
+    cfs = [np.array([1, 7, 9]), np.array([1, 11]), np.array([1, 2, 3, 4])]
+    lower = [np.array([], dtype=int), np.array([0, 1, 5]), np.array([0, 1, 5]), np.array([4]), np.array([], dtype=int)]
+    lcf = [np.array([], dtype=int), np.array([5, 6, 7]), np.array([5, 6, 7]), np.array([9]), np.array([], dtype=int)]
+    allrows, allcf = rows + lower, cfs + lcf
+    row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in allrows])])
+    m = FlatMatrix(p, 3, 5, 3, 3, row_ptr, np.concatenate(allrows), np.arange(8), row_ptr.copy(),
+                   np.concatenate(allcf).astype(np.uint16))
+    out, _ = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref) and out.nrows == 2
+    # 60 000 lower rows: columns do not fit 216 KB of shared memory -> per-pivot fallback
+    p = P31
+    nrl, ncr = 60000, 6
+    lower = [np.sort(rng.choice(ncr, size=rng.integers(1, 4), replace=False)) for _ in range(nrl)]
+    lcf = [rng.integers(1, p, size=len(c)) for c in lower]
+    row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in lower])])
+    m = FlatMatrix(p, 0, nrl, 0, ncr, row_ptr, np.concatenate(lower), np.arange(nrl), row_ptr.copy(),
+                   np.concatenate(lcf).astype(np.uint32))
+    out, _ = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref) and out.nrows == ncr
+    # resident API gives the same rows as the host-buffer API
+    m = random_matrix(rng, P31, 300, 200, 64, 0.05, np.uint32)
+    a, _ = backend.reduce(m)
+    rm = backend.upload(m)
+    b, st = backend.reduce_resident(rm)
+    rm.release()
+    assert a.same_rows(b) and st["hot_kernel_launches"] >= 1 and st["ms_hot_kernel"] > 0
+
+
+def test_gpu_two_host_threads_two_contexts():
+    """The backend is re-entrant per context (the QQ loop runs one F4 instance per host thread,
+    msolve.c:1815-1824): two threads, each with its own context, reduce different matrices."""
+    import threading
+    from msolve_b200.backend import Backend
+    rng = np.random.default_rng(3)
+    mats = [random_matrix(rng, P31, 400, 260, 90, 0.04, np.uint32) for _ in range(6)]
+    refs = [oracle.reduce(m)[0] for m in mats]
+    errors = []
+
+    def work(k):
+        try:
+            be = Backend(0)
+            for rep in range(3):
+                for i in range(k, len(mats), 2):
+                    out, _ = be.reduce(mats[i])
+                    if not out.same_rows(refs[i]):
+                        errors.append((k, i))
+            be.close()
+        except Exception as e:      # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+def test_gpu_pivot_by_lead_random_independent_rows(backend):
+    """F4LA_FLAG_PIVOT_BY_LEAD on matrices that are not from an F4 run: echelonised random rows with
+    distinct leads (made by the oracle in echelon mode) are scrambled by adding multiples of later
+    rows' tails; the final-step contract returns the reduced form of every row in place."""
+    from msolve_b200.flat import FLAG_PIVOT_BY_LEAD
+    rng = np.random.default_rng(17)
+    for p, dt in ((P31, np.uint32), (P8, np.uint8)):
+        src = random_matrix(rng, p, 0, 60, 90, 0.3, dt)
+        ech, _, _ = oracle.reduce(src)                    # reduced rows, distinct leads, decreasing
+        k = ech.nrows
+        assert k > 20
+        # rows with distinct leads that are NOT inter-reduced: row i += c * row j (lead_j > lead_i)
+        dense = np.zeros((k, 90), dtype=np.int64)
+        for i in range(k):
+            a, b = int(ech.row_ptr[i]), int(ech.row_ptr[i + 1])
+            dense[i, ech.cols[a:b]] = ech.cf[a:b]
+        for i in range(k):                                 # row 0 has the largest lead
+            for j in range(i):
+                dense[i] = (dense[i] + int(rng.integers(1, p)) * dense[j]) % p
+        # half of the rows become "known pivots keyed by lead", half stay lower rows
+        order = rng.permutation(k)
+        piv, low = sorted(order[: k // 2]), sorted(order[k // 2:])
+        rows = [np.nonzero(dense[i])[0] for i in piv] + [np.nonzero(dense[i])[0] for i in low]
+        cfs = [dense[i][np.nonzero(dense[i])[0]] for i in piv] + [dense[i][np.nonzero(dense[i])[0]] for i in low]
+        row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in rows])])
+        m = FlatMatrix(p, len(piv), len(low), 0, 90, row_ptr, np.concatenate(rows), np.arange(k), row_ptr.copy(),
+                       np.concatenate(cfs).astype(dt), flags=FLAG_PIVOT_BY_LEAD)
+        # pivot rows must be monic with the lead first: they are (echelon rows are normalised, adding
+        # multiples of rows with LARGER leads does not touch the lead)
+        out, _ = backend.reduce(m)
+        ref, _, _ = oracle.reduce(m)
+        again, _, _, _ = rh.reference_la(m, laopt=2, threads=1)
+        assert out.nrows == len(low) and out.same_rows(ref) and out.same_rows(again)
