@@ -253,6 +253,27 @@ def run_gpu(args, rank, world):
     el_v, aggs_v, clocks = timed(pass_resident, "device-resident")
     el_e, aggs_e, _ = timed(lambda: pass_host()[0], "host buffers (e2e)")
 
+    # the reference's -l 44 semantics on the same matrices: random row combinations (F4LA_FLAG_PROBABILISTIC)
+    prob = None
+    if not args.no_prob:
+        from msolve_b200.flat import FLAG_PROBABILISTIC
+        for rm in resident:
+            rm.release()
+        resident = []
+        for m in mats:
+            m.flags = FLAG_PROBABILISTIC
+            resident.append(be.upload(m))
+        for rm, r in zip(resident, recs):
+            out, _ = be.reduce_resident(rm)
+            assert out.same_rows(r.result), "probabilistic mode changed the reduced rows"
+        el_p, aggs_p, _ = timed(pass_resident, "device-resident, probabilistic (-l 44 semantics)")
+        prob = {"what": "same matrices with F4LA_FLAG_PROBABILISTIC (random combinations of the lower rows, the "
+                        "reference's -l 42/43/44 semantics); reduced rows verified identical to the exact ones",
+                "la_seconds": el_p / args.steps, "value": 2.0 * units * world / (el_p / args.steps) / 1e9, "unit": "Gop/s",
+                "phases_ms": {k: sum(a[k] for a in aggs_p) / args.steps for k in ("ms_prep", "ms_reduce", "ms_echelon", "ms_d2h")}}
+        for m in mats:
+            m.flags = 0
+
     # the matrices are not needed any more
     for rm in resident:
         rm.release()
@@ -328,6 +349,7 @@ def run_gpu(args, rank, world):
                        "la_breakdown_ms": {k: tot["warm"][k] for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce",
                                                                        "ms_echelon", "ms_d2h", "ms_materialize")},
                        "host_threads": host_threads},
+        "probabilistic": prob,
         "qq": qq,
     }
     print(json.dumps(line), flush=True)
@@ -498,6 +520,7 @@ def main():
     ap.add_argument("--prime", type=int, default=P31)
     ap.add_argument("--per-matrix", action="store_true", help="log per-matrix phase times (stderr)")
     ap.add_argument("--no-qq", action="store_true", help="skip the QQ multi-modular block")
+    ap.add_argument("--no-prob", action="store_true", help="skip the probabilistic-mode block")
     ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
     ap.add_argument("--qq-system", default="katsura-10")
     ap.add_argument("--qq-primes-per-thread", type=int, default=4)

@@ -77,6 +77,11 @@ typedef struct f4la_flat_matrix {
  * applied to it (non-zero multipliers): the `rba` arrays the reference fills
  * while learning a trace (la_ff_32.c:1027-1036, data.h:209-213). */
 #define F4LA_FLAG_WANT_RBA    4u
+/* probabilistic echelon form (the reference's -l 42/43/44, la_ff_32.c:2305-2506): the lower
+ * rows are replaced by a few hundred random linear combinations when that is enough to span
+ * their space; same unique reduced rows with overwhelming probability (p > 2^15 only, else
+ * the exact path runs).  Ignored together with NORMALFORM / PIVOT_BY_LEAD / WANT_RBA. */
+#define F4LA_FLAG_PROBABILISTIC 8u
 
 /* Result: rows of the reduced row echelon form, as CSR over ALL columns
  * (column ids in 0..ncl+ncr-1, ascending inside a row).  In echelon mode the
@@ -129,6 +134,10 @@ int  f4la_b200_device_count(void);
 f4la_ctx *f4la_b200_create(int device);
 void f4la_b200_destroy(f4la_ctx *ctx);
 const char *f4la_b200_last_error(const f4la_ctx *ctx);
+
+/* Seed of the random combinations of F4LA_FLAG_PROBABILISTIC (default: a fixed constant, so a
+ * run is reproducible; the reference seeds rand() with --random-seed). */
+void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed);
 
 /* Page-locked host memory for the flat arrays handed to f4la_b200_reduce():
  * host->device copies from such buffers run at full PCIe rate and

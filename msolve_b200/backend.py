@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libf4la_b200.so")
 EXPORTED_SYMBOLS = [
     # include/f4la_b200.h
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
-    "f4la_b200_last_error", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
+    "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
     "f4la_b200_reduce", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
     "f4la_b200_free_result",
     # include/f4la_b200_neogb.h
@@ -69,6 +69,7 @@ def load_library() -> C.CDLL:
     L.f4la_b200_destroy.argtypes = [C.c_void_p]
     L.f4la_b200_last_error.restype = C.c_char_p
     L.f4la_b200_last_error.argtypes = [C.c_void_p]
+    L.f4la_b200_set_seed.argtypes = [C.c_void_p, C.c_uint64]
     L.f4la_b200_pinned_alloc.restype = C.c_void_p
     L.f4la_b200_pinned_alloc.argtypes = [C.c_size_t]
     L.f4la_b200_pinned_free.argtypes = [C.c_void_p]
@@ -110,6 +111,9 @@ class Backend:
         if not self.ctx:
             raise F4LAError(f"f4la_b200_create({device}) failed: no usable sm_100 GPU (no CPU fallback)")
         self.device = device
+
+    def set_seed(self, seed: int) -> None:
+        self.lib.f4la_b200_set_seed(self.ctx, seed)
 
     def close(self) -> None:
         if self.ctx:

@@ -60,6 +60,7 @@ struct f4la_ctx {
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
+    uint64_t      seed = 0x9e3779b97f4a7c15ull;   /* random combinations of the probabilistic mode */
     int           bulk = 0;             /* F4LA_B200_BULK=1: bulk-copy (TMA engine) staging of the source vectors */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense;
@@ -209,7 +210,9 @@ void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
 int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f4la_stats *st)
 {
     const f4la_flat_matrix &d = m->dims;
-    const uint32_t nru = d.nru, nrl = d.nrl, p = d.fc;
+    const uint32_t nru = d.nru, nrl_in = d.nrl, p = d.fc;
+    uint32_t nrl = nrl_in;          /* rows the solve / elimination work on: the lower rows, or in
+                                       probabilistic mode the random combinations standing in for them */
     const uint32_t nc = d.ncl + d.ncr;
     const bool by_lead = (d.flags & F4LA_FLAG_PIVOT_BY_LEAD) != 0;
     const bool nf_mode = (d.flags & F4LA_FLAG_NORMALFORM) != 0;
@@ -225,7 +228,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     const bool want_rba = (d.flags & F4LA_FLAG_WANT_RBA) != 0;
     if (want_rba && by_lead)
         return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_WANT_RBA needs pivots keyed by row index");
-    if (d.flags & ~(F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_NORMALFORM | F4LA_FLAG_WANT_RBA))
+    if (d.flags & ~(F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_NORMALFORM | F4LA_FLAG_WANT_RBA | F4LA_FLAG_PROBABILISTIC))
         return fail(ctx, F4LA_ERR_ARG, "unknown flags 0x%x", d.flags);
     if (by_lead && nf_mode)
         return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD and F4LA_FLAG_NORMALFORM cannot be combined");
@@ -341,23 +344,45 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     }
     CU(cudaEventRecord(ctx->ev[1], s));
 
+    /* Probabilistic mode (the reference's -l 42/43/44, la_ff_32.c:2305-2506): the nrl lower rows
+     * are replaced by k << nrl random linear combinations of them; when the echelon form of the
+     * combinations has a rank well below k they span the same space (w.h.p., p > 2^15) and the
+     * reduced rows are the same unique ones.  Every lower row enters kProbWeight combinations (one
+     * per family, so no row can be missed); k starts at 512 and is quadrupled while the rank comes
+     * within kProbSlack of it; k >= nrl/2 switches to the exact path. */
+    constexpr uint32_t kProbWeight = 8, kProbSlack = 48;
+    const bool prob = (d.flags & F4LA_FLAG_PROBABILISTIC) && !by_lead && !nf_mode && !want_rba && p > 32768u;
+    uint32_t nvr = nrl_in;
+    if (prob && nrl_in >= 3 * 512) nvr = 512;
+    uint32_t rank = 0, Rc = 0, nchunks = 0, G = 0, n_items = 0, maxrank = 0;
+    uint64_t ld = 0;
+    int T = 1, n_flow_ev = 0;
+    bool items_built = false;
+    uint32_t *Dm = nullptr;
+    const uint32_t rba_words = (nru + 31) / 32;
+
+    for (;;) {
+    nrl = nvr;
+    const bool combos = nvr < nrl_in;
     /* ---- 3. chunking of the lower rows ---- */
-    int T = (int)((nrl + kRowsPerT - 1) / kRowsPerT);
+    T = (int)((nrl + kRowsPerT - 1) / kRowsPerT);
     if (T > ctx->tmax) T = ctx->tmax;
     const size_t kL2Budget = ctx->l2_budget;
     while (T > 1 && (size_t)nc * kRowsPerT * T * 4 > kL2Budget) --T;
-    const uint32_t Rc = kRowsPerT * T;
-    const uint32_t nchunks = (nrl + Rc - 1) / Rc;
-    uint32_t G = (uint32_t)(kL2Budget / ((size_t)nc * Rc * 4));
+    Rc = kRowsPerT * T;
+    nchunks = (nrl + Rc - 1) / Rc;
+    G = (uint32_t)(kL2Budget / ((size_t)nc * Rc * 4));
     if (G < 1) G = 1;
     if (G > nchunks) G = nchunks;
-    const uint64_t ld = (uint64_t)nchunks * Rc;
+    ld = (uint64_t)nchunks * Rc;
     OK(ensure(ctx, ctx->V, (size_t)G * nc * Rc * 4));
     OK(ensure(ctx, ctx->D, (size_t)ncr * ld * 4));
+    OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
+    CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));
 
     /* dataflow schedule: items in (level, length class) order, then the non-pivot columns */
-    uint32_t n_items = 0;
-    {
+    if (!items_built) {
+        items_built = true;
         const uint32_t first = nlev ? slot_ptr_h[kLenClasses] : ncl;      /* columns of level 0 have no sources */
         const uint32_t na = ncl - first;
         std::vector<uint32_t> items;
@@ -376,23 +401,19 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         n_items = (uint32_t)items.size();
         OK(ensure(ctx, ctx->sched, ((size_t)na + ncr + 1) * 4));
         OK(ensure(ctx, ctx->items, ((size_t)n_items + 1) * 4));
-        OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
         OK(ensure_host(ctx, ctx->h_dense, (size_t)n_items * 4 + 64));
         memcpy(ctx->h_dense.p, items.data(), (size_t)n_items * 4);
         CU(cudaMemcpyAsync(ctx->items.p, ctx->h_dense.p, (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
         k_flow_sched<<<(na + ncr + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->order), first, ncl, ncr,
                                                            as<uint32_t>(ctx->sched));
         ctx->launches++;
-        CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));
         /* the staging buffer is reused for the result later: the copy must be done first */
         CU(cudaStreamSynchronize(s));
     }
 
-    const uint32_t rba_words = (nru + 31) / 32;
     if (want_rba && rba_words) OK(ensure(ctx, ctx->rba, (size_t)nrl * rba_words * 4 + 16));
 
     uint32_t epoch = 0;
-    int n_flow_ev = 0;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
@@ -402,10 +423,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             ctx->launches++;
         }
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
-        k_scatter_lower<<<blocks_for_warps((uint64_t)rows_here * kScatterSplit), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
-                                                                    d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
-                                                                    as<uint32_t>(ctx->flowflags),
-                                                                    as<uint32_t>(ctx->V), d_err);
+        if (combos)
+            k_scatter_combos<<<blocks_for_warps((uint64_t)nrl_in * kProbWeight), 256, 0, s>>>(
+                m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes, nru, nrl_in, nc, p, pinv, c0, g, Rc,
+                nvr, kProbWeight, ctx->seed, as<uint32_t>(ctx->flowflags), as<uint32_t>(ctx->V), d_err);
+        else
+            k_scatter_lower<<<blocks_for_warps((uint64_t)rows_here * kScatterSplit), 256, 0, s>>>(
+                m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
+                as<uint32_t>(ctx->flowflags), as<uint32_t>(ctx->V), d_err);
         ctx->launches++;
         FlowArgs f;
         memset(&f, 0, sizeof(f));
@@ -431,9 +456,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     CU(cudaEventRecord(ctx->ev[2], s));
 
     /* ---- 4. Gauss-Jordan on the trailing block (not in normal-form mode) ---- */
-    const uint32_t maxrank = nrl < ncr ? nrl : ncr;
-    uint32_t *Dm = as<uint32_t>(ctx->D);
-    uint32_t rank = 0;
+    maxrank = nrl < ncr ? nrl : ncr;
+    Dm = as<uint32_t>(ctx->D);
+    rank = 0;
     if (!nf_mode) {
         OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
         OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
@@ -503,6 +528,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         }
         rank = h_state->rank;
     }
+    /* probabilistic mode: accept when the rank stays clear of the number of combinations */
+    if (!combos || rank + kProbSlack <= nvr) break;
+    nvr = (uint64_t)nvr * 4 >= nrl_in / 2 ? nrl_in : nvr * 4;
+    }   /* attempts */
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
         CU(cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
@@ -762,6 +791,8 @@ void f4la_b200_destroy(f4la_ctx *ctx)
 }
 
 const char *f4la_b200_last_error(const f4la_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed) { if (ctx) ctx->seed = seed ? seed : 0x9e3779b97f4a7c15ull; }
 
 void *f4la_b200_pinned_alloc(size_t bytes)
 {

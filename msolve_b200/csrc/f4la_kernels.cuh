@@ -349,6 +349,62 @@ __global__ void k_scatter_lower(const uint64_t *__restrict__ row_ptr,
     }
 }
 
+/* counter-based RNG (splitmix64 finaliser): coefficient / class of (seed, family, row) */
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+/* Probabilistic mode: V <- R * X for a sparse random R (nvr x nrl).  Lower row r enters one
+ * combination of each of the `weight` families (family f owns the combinations
+ * [f*kw, (f+1)*kw), kw = nvr / weight; the class inside the family and the non-zero
+ * coefficient come from the hash), so every row is represented `weight` times.  One warp per
+ * (row, family); several rows add into the same cell, hence the compare-and-swap modular add. */
+__global__ void k_scatter_combos(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
+                                 const uint32_t *__restrict__ row_cf, const uint64_t *__restrict__ cf_ptr,
+                                 const void *__restrict__ cf, uint32_t cf_bytes, uint32_t nru, uint32_t nrl,
+                                 uint32_t nc, uint32_t p, uint64_t pinv, uint32_t chunk0, uint32_t nchunks,
+                                 uint32_t Rc, uint32_t nvr, uint32_t weight, uint64_t seed,
+                                 uint32_t *__restrict__ flags, uint32_t *__restrict__ V, uint32_t *__restrict__ err)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t kw = nvr / weight;
+    const uint32_t v0 = chunk0 * Rc, v1 = min(nvr, (chunk0 + nchunks) * Rc);
+    for (uint32_t wk = warp; wk < nrl * weight; wk += nwarps) {
+        const uint32_t r = wk / weight, fam = wk % weight;
+        const uint64_t h = mix64(seed ^ ((uint64_t)fam << 40) ^ r);
+        const uint32_t vr = fam * kw + (uint32_t)(h % kw);                 /* the combination this row joins */
+        if (vr < v0 || vr >= v1) continue;
+        const uint32_t rho = 1u + (uint32_t)((h >> 20) % (p - 1));          /* non-zero multiplier */
+        const uint64_t a = row_ptr[nru + r], b = row_ptr[nru + r + 1];
+        const uint64_t c0 = cf_ptr[row_cf[nru + r]];
+        const uint32_t lc = (vr - v0) / Rc, lr = (vr - v0) % Rc;
+        uint32_t *Vc = V + (size_t)lc * nc * Rc;
+        for (uint64_t k = a + lane; k < b; k += 32) {
+            const uint32_t j = cols[k];
+            if (j >= nc) { atomicOr(err, kErrColumnRange); continue; }
+            const uint32_t x = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
+            const uint32_t t = mulmod(x, rho, p, pinv);
+            if (!t) continue;
+            uint32_t *cell = &Vc[(size_t)j * Rc + lr];
+            uint32_t old = *cell, assumed;
+            do {
+                assumed = old;
+                uint32_t nv = assumed + t;                 /* < 2^32: both < p < 2^31 */
+                if (nv >= p) nv -= p;
+                old = atomicCAS(cell, assumed, nv);
+            } while (old != assumed);
+            /* "non-zero" is only a hint that keeps the loads: a sum that cancels to zero is still correct */
+            if (flags[(size_t)lc * nc + j] == 0xfffffffeu) flags[(size_t)lc * nc + j] = 0xffffffffu;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* arithmetic helpers of the hot kernel                                 */
 /* ------------------------------------------------------------------ */

@@ -183,6 +183,12 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
     fm.flags = nf_mode ? F4LA_FLAG_NORMALFORM : final_step ? F4LA_FLAG_PIVOT_BY_LEAD : F4LA_FLAG_NONE;
     if (learn) fm.flags |= F4LA_FLAG_WANT_RBA;
+    /* -l 42 / 43 / 44: the reference's probabilistic variants (io.c:885-957); no tracer runs with
+     * them (f4.c:365), the device decides whether random combinations pay off */
+    const int32_t laopt = fld<int32_t>(st, L.md_laopt);
+    if ((laopt == 42 || laopt == 43 || laopt == 44) && entry == Entry::Normal && !learn && !nf_mode && !final_step &&
+        trace_level == 0)
+        fm.flags |= F4LA_FLAG_PROBABILISTIC;
     fm.row_ptr = row_ptr; fm.cols = cols; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = pool;
     const double t_flat = now_ms();
 

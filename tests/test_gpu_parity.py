@@ -418,3 +418,66 @@ def test_gpu_pivot_by_lead_random_independent_rows(backend):
         ref, _, _ = oracle.reduce(m)
         again, _, _, _ = rh.reference_la(m, laopt=2, threads=1)
         assert out.nrows == len(low) and out.same_rows(ref) and out.same_rows(again)
+
+
+def low_rank_matrix(rng, p, nru, nrl, ncr, rank, dt):
+    """[A B; C D] whose lower rows are random combinations of `rank` sparse base rows."""
+    base = random_matrix(rng, p, nru, rank, ncr, 0.05, dt)
+    nc = nru + ncr
+    dense = np.zeros((rank, nc), dtype=object)
+    for i in range(rank):
+        c, v = base.row(nru + i)
+        dense[i, c.astype(int)] = [int(x) for x in v]
+    rows, cfs = [], []
+    for i in range(nru):
+        c, v = base.row(i)
+        rows.append(c.astype(int)); cfs.append(v.astype(np.int64))
+    for r in range(nrl):
+        k = rng.choice(rank, size=3, replace=False)
+        row = np.zeros(nc, dtype=object)
+        for kk in k:
+            row = (row + int(rng.integers(1, p)) * dense[kk]) % p
+        nz = np.nonzero(row)[0]
+        rows.append(nz); cfs.append(np.array([int(row[j]) for j in nz], dtype=np.int64))
+    row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in rows])])
+    return FlatMatrix(p, nru, nrl, nru, ncr, row_ptr, np.concatenate(rows), np.arange(nru + nrl), row_ptr.copy(),
+                      np.concatenate(cfs).astype(dt))
+
+
+def test_gpu_probabilistic_mode_random_combinations(backend):
+    """F4LA_FLAG_PROBABILISTIC: 2 000 lower rows of rank <= 120 are replaced by 512 random
+    combinations (rank + slack < 512: accepted), 1 800 rows of rank 600 force the escalation to the
+    exact path; both give the oracle's rows, for several seeds."""
+    from msolve_b200.flat import FLAG_PROBABILISTIC
+    rng = np.random.default_rng(21)
+    for rank, nrl in ((120, 2000), (600, 1800)):
+        m = low_rank_matrix(rng, P31, 150, nrl, 700, rank, np.uint32)
+        ref, _, _ = oracle.reduce(m)
+        assert ref.nrows > rank // 2
+        m.flags = FLAG_PROBABILISTIC
+        for seed in (0, 1, 12345, 2 ** 63 + 7):
+            backend.set_seed(seed)
+            out, st = backend.reduce(m)
+            assert out.same_rows(ref), (rank, seed)
+    backend.set_seed(0)
+    # small prime: the flag is ignored (exact path), as the reference's CLI does below 2^15
+    m = low_rank_matrix(rng, P8, 60, 1700, 200, 40, np.uint8)
+    ref, _, _ = oracle.reduce(m)
+    m.flags = FLAG_PROBABILISTIC
+    out, _ = backend.reduce(m)
+    assert out.same_rows(ref)
+
+
+@pytest.mark.skipif(not rh.available(), reason="compiled reference not shipped")
+@pytest.mark.parametrize("name,laopt", [("katsura-11", 44), ("cyclic-8", 42), ("eco-12", 44), ("katsura-10", 43)])
+def test_gpu_backend_probabilistic_la_options(name, laopt):
+    """-l 42/43/44 through the drop-in: same reduced Groebner basis as the reference's exact run
+    (the property the reference's own diff tests assert for -l 44, test/diff/diff_source.sh)."""
+    import gpu_helpers
+    L = gpu_helpers.install_backend()
+    try:
+        gb = rh.run_f4(systems.by_name(name, P31), P31, threads=8, laopt=laopt)
+    finally:
+        gpu_helpers.uninstall_backend()
+    want = golden_io.gb_digests()[f"{name}@{P31}"]
+    assert gb.digest() == want["digest"]
