@@ -219,9 +219,9 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     }
 
     /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
-#pragma omp parallel for num_threads(nthr) schedule(static)
+    /* serial on purpose: the rows were all allocated by the F4 driver's main thread, freeing them
+     * from many threads only contends on that arena's lock (measured slower than one thread) */
     for (uint32_t i = 0; i < nrl; ++i) { free(tr[i]); tr[i] = nullptr; }
-#pragma omp parallel for num_threads(nthr) schedule(static)
     for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
 
     uint32_t np = res.nrows;
