@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "f4la_b200.h"
@@ -195,8 +196,27 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     /* ---- device ---- */
     f4la_flat_result res;
     f4la_stats stats;
-    const int rc = f4la_b200_reduce(ctx(), &fm, &res, &stats);
-    if (rc != F4LA_OK) die(f4la_b200_last_error(ctx()));
+    /* The LA consumes its inputs (la_ff_32.c:2666, 2718-2721).  Everything the device needs has
+     * been copied to the staging buffers, so a helper thread frees the ~10^4-10^5 input rows
+     * (tens of milliseconds of free()) while the GPU works.  Not while learning a trace:
+     * construct_trace() still reads the rows. */
+    f4la_ctx *cx = ctx();
+    std::thread reaper;
+    bool reaped = false;
+    if (!learn && (uint64_t)n > 2048) {
+        reaper = std::thread([=]() {
+            for (uint32_t i = 0; i < nrl; ++i) free(tr[i]);
+            for (uint32_t i = 0; i < nru; ++i) free(rr[i]);
+        });
+        reaped = true;
+    }
+    const int rc = f4la_b200_reduce(cx, &fm, &res, &stats);
+    if (reaped) {
+        reaper.join();
+        for (uint32_t i = 0; i < nrl; ++i) tr[i] = nullptr;
+        for (uint32_t i = 0; i < nru; ++i) rr[i] = nullptr;
+    }
+    if (rc != F4LA_OK) die(f4la_b200_last_error(cx));
     const double t_dev = now_ms();
 
     /* ---- learning: hand the reference's trace builder what it reads -------------
@@ -221,8 +241,10 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     /* ---- consume the inputs like the reference (la_ff_32.c:2666, 2718-2721) ---- */
     /* serial on purpose: the rows were all allocated by the F4 driver's main thread, freeing them
      * from many threads only contends on that arena's lock (measured slower than one thread) */
-    for (uint32_t i = 0; i < nrl; ++i) { free(tr[i]); tr[i] = nullptr; }
-    for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
+    if (!reaped) {
+        for (uint32_t i = 0; i < nrl; ++i) { free(tr[i]); tr[i] = nullptr; }
+        for (uint32_t i = 0; i < nru; ++i) { free(rr[i]); rr[i] = nullptr; }
+    }
 
     uint32_t np = res.nrows;
     int bad_prime = 0;
