@@ -218,7 +218,15 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     const bool nf_mode = (d.flags & F4LA_FLAG_NORMALFORM) != 0;
     /* effective split: with pivots keyed by lead column the columns are renumbered
      * (pivot columns first), so that ncl == nru holds for the rest of the pipeline */
-    const uint32_t ncl = by_lead ? nru : d.ncl;
+    /* Pivots keyed by lead column (final reduction step, interreduce_matrix_rows): the lower rows are
+     * pivots too (distinct leads, monic), so ALL rows form the unit upper triangular system
+     * [A B] and the wanted rows are rows of its reduced echelon form [I  A^-1 B].  Row i of A^-1 B
+     * is -D' of the unit vector e_lead(i) pushed through the same pull solve: no elimination, no
+     * pivot search (the former version ran a Gauss-Jordan with one pivot per basis element). */
+    const uint32_t npr = by_lead ? nru + nrl_in : nru;      /* rows that act as pivots */
+    const uint32_t ncl = by_lead ? npr : d.ncl;
+    if (ncl > nc)
+        return fail(ctx, F4LA_ERR_ARG, "more pivot rows (%u) than columns (%u)", ncl, nc);
     const uint32_t ncr = nc - ncl;
     const uint64_t pinv = ~0ULL / p;
     const bool wide = p >= 65536u;
@@ -234,12 +242,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD and F4LA_FLAG_NORMALFORM cannot be combined");
     if (!by_lead && nru != d.ncl)
         return fail(ctx, F4LA_ERR_ARG, "pivots keyed by row index need nru == ncl (got %u, %u)", nru, d.ncl);
-    if (nru > nc)
-        return fail(ctx, F4LA_ERR_ARG, "more pivot rows (%u) than columns (%u)", nru, nc);
     if (m->nnz >= 0xfffffff0ull)
         return fail(ctx, F4LA_ERR_ARG, "matrix too large: %llu non-zeros", (unsigned long long)m->nnz);
     if (nrl == 0 || (ncr == 0 && !by_lead && !nf_mode)) { empty_result(out, d.cf_bytes); return F4LA_OK; }
-    if (ncr == 0) {                       /* every lower row reduces to zero */
+    if (ncr == 0 && !by_lead) {           /* every lower row reduces to zero */
         empty_result(out, d.cf_bytes);
         free(out->row_ptr); free(out->src_row);
         out->nrows = nrl;
@@ -267,16 +273,16 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         OK(ensure(ctx, ctx->colmap, ((size_t)nc + 2) * 4));
         OK(ensure(ctx, ctx->invmap, ((size_t)nc + 2) * 4));
         CU(cudaMemsetAsync(ctx->is_piv.p, 0, ((size_t)nc + 2) * 4, s));
-        if (nru) k_mark_leads<<<(nru + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nc, as<uint32_t>(ctx->is_piv), d_err);
+        if (npr) k_mark_leads<<<(npr + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, npr, nc, as<uint32_t>(ctx->is_piv), d_err);
         k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc);
-        k_build_colmap<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc, nru,
+        k_build_colmap<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc, npr,
                                                        as<uint32_t>(ctx->colmap), as<uint32_t>(ctx->invmap));
         ctx->launches += 3;
         colmap = as<uint32_t>(ctx->colmap);
     }
-    if (nru) {
-        k_pull_count<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
-                                                           d.cf_bytes, nru, ncl, nc, colmap,
+    if (npr) {
+        k_pull_count<<<blocks_for_warps(npr), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
+                                                           d.cf_bytes, npr, ncl, nc, colmap,
                                                            as<uint32_t>(ctx->col_cnt), d_err);
         ctx->launches++;
     }
@@ -292,9 +298,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                     "triangular, 4 column out of range, 8 lead coefficient != 1, 32 duplicate pivot column)", h_small[1]);
     OK(ensure(ctx, ctx->ent, ((size_t)nnz_pull + 1) * sizeof(uint2)));
     CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));   /* reuse as cursor */
-    if (nru) {
-        k_pull_fill<<<blocks_for_warps(nru), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
-                                                          nru, nc, p, colmap, as<uint32_t>(ctx->col_ptr),
+    if (npr) {
+        k_pull_fill<<<blocks_for_warps(npr), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
+                                                          npr, nc, p, colmap, as<uint32_t>(ctx->col_ptr),
                                                           as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent));
         ctx->launches++;
     }
@@ -423,7 +429,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             ctx->launches++;
         }
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
-        if (combos)
+        if (by_lead)
+            k_scatter_units<<<(rows_here + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, nc, c0, g, Rc, colmap,
+                                                                    as<uint32_t>(ctx->flowflags), as<uint32_t>(ctx->V), d_err);
+        else if (combos)
             k_scatter_combos<<<blocks_for_warps((uint64_t)nrl_in * kProbWeight), 256, 0, s>>>(
                 m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes, nru, nrl_in, nc, p, pinv, c0, g, Rc,
                 nvr, kProbWeight, ctx->seed, as<uint32_t>(ctx->flowflags), as<uint32_t>(ctx->V), d_err);
@@ -459,7 +468,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     maxrank = nrl < ncr ? nrl : ncr;
     Dm = as<uint32_t>(ctx->D);
     rank = 0;
-    if (!nf_mode) {
+    if (!nf_mode && !by_lead) {
         OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
         OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
         OK(ensure(ctx, ctx->used, (size_t)ld + 16));
@@ -543,19 +552,20 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     CU(cudaEventRecord(ctx->ev[3], s));
 
     /* ---- 5. result rows back to the host ---- */
-    const uint32_t ndense = nf_mode ? nrl : rank;       /* dense rows produced on the device */
+    const uint32_t ndense = (nf_mode || by_lead) ? nrl : rank;       /* dense rows produced on the device */
     const uint32_t nout = (nf_mode || by_lead) ? nrl : rank;
     uint64_t d2h_bytes = 0;
     if (nout == 0) {
         empty_result(out, d.cf_bytes);
     } else {
         const size_t dense_bytes = (size_t)ndense * ncr * 4;
-        const size_t aux_words = 2 * (size_t)rank + (by_lead ? 2 * (size_t)nc + nrl : 0) + 16;
+        const size_t aux_words = 2 * (size_t)rank + (by_lead ? (size_t)nc + nrl : 0) + 16;
         OK(ensure(ctx, ctx->dense_out, dense_bytes + 16));
         OK(ensure_host(ctx, ctx->h_dense, dense_bytes + aux_words * 4));
-        if (nf_mode) {
+        if ((nf_mode || by_lead) && ncr) {
+            /* by_lead: the rows of A^-1 B are the NEGATED solve results */
             dim3 grid((ncr + 31) / 32, (nrl + 31) / 32), block(32, 8);
-            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, as<uint32_t>(ctx->dense_out));
+            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, by_lead ? p : 0u, as<uint32_t>(ctx->dense_out));
             ctx->launches++;
         } else if (rank) {
             dim3 grid((ncr + 255) / 256, rank);
@@ -567,7 +577,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
         uint32_t *h_pivrow = h_dense + (size_t)ndense * ncr;
         uint32_t *h_pivcol = h_pivrow + rank;
-        uint32_t *h_colmap = h_pivcol + rank, *h_invmap = h_colmap + (by_lead ? nc : 0);
+        uint32_t *h_invmap = h_pivcol + rank;
         uint32_t *h_leads = h_invmap + (by_lead ? nc : 0);
         if (dense_bytes) CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
         if (rank) {
@@ -578,7 +588,6 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             OK(ensure(ctx, ctx->leads, (size_t)nrl * 4 + 16));
             k_lower_leads<<<(nrl + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, as<uint32_t>(ctx->leads));
             ctx->launches++;
-            CU(cudaMemcpyAsync(h_colmap, ctx->colmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(h_invmap, ctx->invmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
         }
@@ -591,16 +600,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         if (nf_mode) {
             for (uint32_t i = 0; i < nrl; ++i) pick[i] = i;
         } else if (by_lead) {
-            std::vector<int32_t> row_of_col(ncr, -1);
-            for (uint32_t k = 0; k < rank; ++k) row_of_col[h_pivcol[k]] = (int32_t)(rank - 1 - k);
-            for (uint32_t i = 0; i < nrl; ++i) {
-                if (h_leads[i] >= nc) continue;                    /* empty input row */
-                const uint32_t nid = h_colmap[h_leads[i]];
-                if (nid >= ncl) pick[i] = row_of_col[nid - ncl];
-                if (pick[i] < 0)
-                    return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_PIVOT_BY_LEAD needs lower rows with distinct lead columns "
-                                "that are not pivot columns and that are linearly independent (row %u violates this)", i);
-            }
+            for (uint32_t i = 0; i < nrl; ++i)
+                if (h_leads[i] < nc) pick[i] = i;                  /* empty input rows stay empty */
         } else {
             for (uint32_t t = 0; t < rank; ++t) pick[t] = t;
         }
@@ -613,7 +614,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         for (uint32_t t = 0; t < nout; ++t) {
             if (pick[t] < 0) continue;
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
-            uint64_t n = 0;
+            uint64_t n = by_lead ? 1 : 0;                          /* by_lead: the lead term itself */
             for (uint32_t c = 0; c < ncr; ++c) n += row[c] != 0;
             rnz[t] = n;
         }
@@ -631,6 +632,13 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             if (pick[t] < 0) continue;
             uint64_t k = out->row_ptr[t];
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
+            if (by_lead) {
+                out->cols[k] = h_leads[t];
+                if (d.cf_bytes == 4) ((uint32_t *)out->cf)[k] = 1;
+                else if (d.cf_bytes == 2) ((uint16_t *)out->cf)[k] = 1;
+                else ((uint8_t *)out->cf)[k] = 1;
+                ++k;
+            }
             for (uint32_t c = 0; c < ncr; ++c) {
                 const uint32_t v = row[c];
                 if (!v) continue;

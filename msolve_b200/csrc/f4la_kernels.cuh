@@ -1139,6 +1139,27 @@ __global__ void k_rba_bits(const uint32_t *__restrict__ V, uint32_t nc, uint32_t
     rba[(size_t)row * words + w] = bits;
 }
 
+/* Pivot-by-lead mode: lower row i is represented by the unit vector of its (renumbered) lead
+ * column; the solve then yields row i of A^-1 (multipliers) and of -A^-1 B (trailing block). */
+__global__ void k_scatter_units(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
+                                uint32_t nru, uint32_t nrl, uint32_t nc, uint32_t chunk0, uint32_t nchunks, uint32_t Rc,
+                                const uint32_t *__restrict__ colmap, uint32_t *__restrict__ flags,
+                                uint32_t *__restrict__ V, uint32_t *__restrict__ err)
+{
+    const uint32_t r0 = chunk0 * Rc;
+    const uint32_t r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrl || r >= (chunk0 + nchunks) * Rc) return;
+    const uint64_t a = row_ptr[nru + r];
+    if (row_ptr[nru + r + 1] == a) return;                   /* empty row: stays zero */
+    const uint32_t lead = cols[a];
+    if (lead >= nc) { atomicOr(err, kErrColumnRange); return; }
+    const uint32_t j = colmap[lead];
+    const uint32_t lc = (r - r0) / Rc, lr = (r - r0) % Rc;
+    V[((size_t)lc * nc + j) * Rc + lr] = 1u;
+    if (flags[(size_t)lc * nc + j] == 0xfffffffeu)           /* kFlagAlwaysZ -> kFlagAlwaysNZ (sourceless column) */
+        flags[(size_t)lc * nc + j] = 0xffffffffu;
+}
+
 /* Lead (first stored) column of every lower row; 0xffffffff for an empty row. */
 __global__ void k_lower_leads(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ cols,
                               uint32_t nru, uint32_t nrl, uint32_t *__restrict__ leads)
@@ -1149,9 +1170,9 @@ __global__ void k_lower_leads(const uint64_t *__restrict__ row_ptr, const uint32
     leads[i] = row_ptr[nru + i + 1] > a ? cols[a] : 0xffffffffu;
 }
 
-/* Normal-form mode: row r of D' as is (no elimination). */
+/* Normal-form mode: row r of D' as is (no elimination); pivot-by-lead mode: negated (negate_mod = p). */
 __global__ void k_transpose_rows(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t nrows,
-                                 uint32_t *__restrict__ out)
+                                 uint32_t negate_mod, uint32_t *__restrict__ out)
 {
     __shared__ uint32_t tile[32][33];
     const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -1163,7 +1184,10 @@ __global__ void k_transpose_rows(const uint32_t *__restrict__ D, uint64_t ld, ui
     __syncthreads();
     for (uint32_t k = ty; k < 32; k += blockDim.y) {
         const uint32_t r = r0 + k, c = c0 + tx;
-        if (r < nrows && c < ncr) out[(size_t)r * ncr + c] = tile[tx][k];
+        if (r < nrows && c < ncr) {
+            const uint32_t v = tile[tx][k];
+            out[(size_t)r * ncr + c] = (negate_mod && v) ? negate_mod - v : v;
+        }
     }
 }
 
