@@ -451,6 +451,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.counter = d_err + 4; f.err = d_err;
         f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
         f.p = p; f.pinv = pinv;
+        f.two64 = (uint32_t)(((~0ull) % p + 1) % p);
         CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);

@@ -40,7 +40,6 @@ constexpr int kSolveThreads   = 256;   /* 8 warps */
 constexpr int kWarpsPerBlock  = kSolveThreads / 32;
 constexpr int kRowsPerT       = 128;   /* rows covered by one uint4 per lane */
 constexpr int kMaxT           = 4;     /* chunk = 128*T rows, T in 1..4      */
-constexpr uint32_t kFoldEvery = 1u << 15; /* entries between overflow folds  */
 constexpr uint32_t kScatterSplit = 8;  /* warps per lower row in k_scatter_lower */
 constexpr uint32_t kLongColumn = 128;  /* >= this many entries: one CTA/col  */
 constexpr int kLenClasses     = 7;     /* class 0 = long, 1..6 = short columns by decreasing length */
@@ -409,12 +408,33 @@ __global__ void k_scatter_combos(const uint64_t *__restrict__ row_ptr, const uin
 /* arithmetic helpers of the hot kernel                                 */
 /* ------------------------------------------------------------------ */
 
-/* canonical residue of lo + 2^16 * hi */
+/* Accumulator of one (row, column) dot product.
+ * WIDE (p >= 2^16): 96 bits.  A product v*c < 2^62 is added with ONE IMAD.WIDE.U32 (carry-out to a
+ * predicate) and one add-with-carry into the third word (IADD3.X, ALU pipe): the multiplier pipe
+ * issues IMAD.WIDE at 32 lanes/clk/SM, so the former scheme (coefficient split into 16-bit halves,
+ * two IMAD.WIDE into two u64 sums) topped out at 16 MAC/clk/SM; this one measures 28.8
+ * (tools/ubench/imad_wide.cu).  a2 counts carries: good for 2^32 products, more than a column
+ * can hold (nnz < 2^32), so no intermediate folds are needed.
+ * !WIDE (p < 2^16): products < 2^32, a plain 64-bit sum (one IMAD.WIDE) holds 2^32 of them. */
+struct Acc { uint32_t a0, a1, a2; };
+
 template <bool WIDE>
-__device__ __forceinline__ uint32_t fold_lohi(uint64_t lo, uint64_t hi, uint32_t p, uint64_t pinv)
+__device__ __forceinline__ void mac(Acc &a, uint32_t v, uint32_t c)
 {
-    uint64_t x = mod_u64(lo, p, pinv);
-    if (WIDE) x += (uint64_t)mod_u64(hi, p, pinv) << 16;
+    if (WIDE)
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+            : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2) : "r"(v), "r"(c));
+    else
+        asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+            : "+r"(a.a0), "+r"(a.a1) : "r"(v), "r"(c));
+}
+
+/* canonical residue of the accumulator plus extra (< 2^32); two64 = 2^64 mod p */
+template <bool WIDE>
+__device__ __forceinline__ uint32_t fold_acc(const Acc &a, uint32_t extra, uint32_t p, uint64_t pinv, uint32_t two64)
+{
+    uint64_t x = (uint64_t)mod_u64(((uint64_t)a.a1 << 32) | a.a0, p, pinv) + extra;
+    if (WIDE) x += mod_u64((uint64_t)a.a2 * two64, p, pinv);
     return mod_u64(x, p, pinv);
 }
 
@@ -454,6 +474,7 @@ struct FlowArgs {
     uint64_t        out_ld;
     uint32_t        chunk0;
     uint32_t        p;
+    uint32_t        two64;      /* 2^64 mod p                                     */
     uint64_t        pinv;
 };
 
@@ -487,11 +508,10 @@ template <int T, bool WIDE>
 __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_t *__restrict__ Vc,
                                                 const uint32_t *__restrict__ flagc,
                                                 uint32_t b0, uint32_t b1,
-                                                uint32_t lane, uint64_t (&lo)[T][4], uint64_t (&hi)[T][4])
+                                                uint32_t lane, Acc (&acc)[T][4])
 {
     constexpr int U = (T <= 2) ? 4 : 2;
     const uint32_t Rc = A.Rc;
-    uint32_t since_fold = 0;
     for (uint32_t b = b0; b < b1; b += 32) {
         const uint32_t n = min(32u, b1 - b);
         uint2 en = make_uint2(0, 0);
@@ -518,7 +538,6 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
          * the lower rows come clustered, 15-60 % of the (pivot, chunk) vectors are
          * zero, so their loads and multiplies are skipped altogether. */
         uint32_t live = __ballot_sync(0xffffffffu, lane < n && (f & 1u));
-        since_fold += __popc(live);
         while (live) {
             uint32_t src[U], cf[U];
             uint4 v[U][T];
@@ -541,28 +560,12 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint32_t cl = WIDE ? (cf[u] & 0xffffu) : cf[u];
-                const uint32_t ch = cf[u] >> 16;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    lo[t][0] += (uint64_t)v[u][t].x * cl; lo[t][1] += (uint64_t)v[u][t].y * cl;
-                    lo[t][2] += (uint64_t)v[u][t].z * cl; lo[t][3] += (uint64_t)v[u][t].w * cl;
-                    if (WIDE) {
-                        hi[t][0] += (uint64_t)v[u][t].x * ch; hi[t][1] += (uint64_t)v[u][t].y * ch;
-                        hi[t][2] += (uint64_t)v[u][t].z * ch; hi[t][3] += (uint64_t)v[u][t].w * ch;
-                    }
+                    mac<WIDE>(acc[t][0], v[u][t].x, cf[u]); mac<WIDE>(acc[t][1], v[u][t].y, cf[u]);
+                    mac<WIDE>(acc[t][2], v[u][t].z, cf[u]); mac<WIDE>(acc[t][3], v[u][t].w, cf[u]);
                 }
             }
-        }
-        if (since_fold >= kFoldEvery) {
-            since_fold = 0;
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
-                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
-                }
         }
     }
 }
@@ -613,11 +616,10 @@ template <int T, bool WIDE>
 __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const uint32_t *__restrict__ Vc,
                                                      const uint32_t *__restrict__ flagc,
                                                      uint32_t b0, uint32_t b1, uint32_t lane,
-                                                     uint64_t (&lo)[T][4], uint64_t (&hi)[T][4], BulkPipe &pp)
+                                                     Acc (&acc)[T][4], BulkPipe &pp)
 {
     constexpr uint32_t kBytes = T * kRowsPerT * 4;
     const uint32_t Rc = A.Rc;
-    uint32_t since_fold = 0;
     for (uint32_t b = b0; b < b1; b += 32) {
         const uint32_t n = min(32u, b1 - b);
         uint2 en = make_uint2(0, 0);
@@ -642,7 +644,6 @@ __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const ui
         asm volatile("fence.proxy.async;" ::: "memory");
         const uint32_t live = __ballot_sync(0xffffffffu, lane < n && (f & 1u));
         const uint32_t nl = __popc(live);
-        since_fold += nl;
         /* compact: lane k holds the k-th live entry */
         const uint32_t from = __fns(live, 0, lane + 1) & 31u;
         const uint32_t csrc = __shfl_sync(0xffffffffu, en.x, from);
@@ -668,16 +669,10 @@ __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const ui
 #pragma unroll
             for (int t = 0; t < T; ++t) v[t] = lds_u4(pp.stage_base + st * kBytes + t * 512 + lane * 16);
             const uint32_t cf = __shfl_sync(0xffffffffu, ccf, k);
-            const uint32_t cl = WIDE ? (cf & 0xffffu) : cf;
-            const uint32_t ch = cf >> 16;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                lo[t][0] += (uint64_t)v[t].x * cl; lo[t][1] += (uint64_t)v[t].y * cl;
-                lo[t][2] += (uint64_t)v[t].z * cl; lo[t][3] += (uint64_t)v[t].w * cl;
-                if (WIDE) {
-                    hi[t][0] += (uint64_t)v[t].x * ch; hi[t][1] += (uint64_t)v[t].y * ch;
-                    hi[t][2] += (uint64_t)v[t].z * ch; hi[t][3] += (uint64_t)v[t].w * ch;
-                }
+                mac<WIDE>(acc[t][0], v[t].x, cf); mac<WIDE>(acc[t][1], v[t].y, cf);
+                mac<WIDE>(acc[t][2], v[t].z, cf); mac<WIDE>(acc[t][3], v[t].w, cf);
             }
             pp.consumed++;
             __syncwarp();                 /* every lane has read the stage before it is refilled */
@@ -689,16 +684,6 @@ __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const ui
                 }
                 pp.issued++;
             }
-        }
-        if (since_fold >= kFoldEvery) {
-            since_fold = 0;
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    lo[t][k] = mod_u64(lo[t][k], A.p, A.pinv);
-                    if (WIDE) hi[t][k] = mod_u64(hi[t][k], A.p, A.pinv);
-                }
         }
     }
 }
@@ -739,18 +724,18 @@ k_pull_flow(const FlowArgs A)
         uint32_t *Vc = A.V + (size_t)chunk * A.nc * A.Rc;
         uint32_t *flagc = A.flags + (size_t)chunk * A.nc;
 
-        uint64_t lo[T][4], hi[T][4];
+        Acc acc[T][4];
 #pragma unroll
         for (int t = 0; t < T; ++t)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { lo[t][k] = 0; hi[t][k] = 0; }
+            for (int k = 0; k < 4; ++k) acc[t][k] = Acc{0u, 0u, 0u};
 
         if (!is_long) {
             if (warp < cnt) {
                 const uint32_t j = A.sched[pos + warp];
                 const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-                if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi, pp);
-                else flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, lo, hi);
+                if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, e0, e1, lane, acc, pp);
+                else flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, acc);
                 const bool to_out = j >= A.ncl;
                 uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                        : Vc + (size_t)j * A.Rc;
@@ -760,10 +745,10 @@ k_pull_flow(const FlowArgs A)
                 for (int t = 0; t < T; ++t) {
                     const uint4 x = init[t * 32];
                     uint4 r;
-                    r.x = fold_lohi<WIDE>(lo[t][0] + x.x, hi[t][0], A.p, A.pinv);
-                    r.y = fold_lohi<WIDE>(lo[t][1] + x.y, hi[t][1], A.p, A.pinv);
-                    r.z = fold_lohi<WIDE>(lo[t][2] + x.z, hi[t][2], A.p, A.pinv);
-                    r.w = fold_lohi<WIDE>(lo[t][3] + x.w, hi[t][3], A.p, A.pinv);
+                    r.x = fold_acc<WIDE>(acc[t][0], x.x, A.p, A.pinv, A.two64);
+                    r.y = fold_acc<WIDE>(acc[t][1], x.y, A.p, A.pinv, A.two64);
+                    r.z = fold_acc<WIDE>(acc[t][2], x.z, A.p, A.pinv, A.two64);
+                    r.w = fold_acc<WIDE>(acc[t][3], x.w, A.p, A.pinv, A.two64);
                     reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
                     nonzero |= r.x | r.y | r.z | r.w;
                 }
@@ -783,16 +768,16 @@ k_pull_flow(const FlowArgs A)
             /* equal contiguous shares of the entries for the 8 warps */
             const uint32_t seg = (e1 - e0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
             const uint32_t b0 = min(e1, e0 + warp * seg), b1 = min(e1, b0 + seg);
-            if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi, pp);
-            else flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, lo, hi);
+            if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, b0, b1, lane, acc, pp);
+            else flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, acc);
         }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             uint4 r;
-            r.x = fold_lohi<WIDE>(lo[t][0], hi[t][0], A.p, A.pinv);
-            r.y = fold_lohi<WIDE>(lo[t][1], hi[t][1], A.p, A.pinv);
-            r.z = fold_lohi<WIDE>(lo[t][2], hi[t][2], A.p, A.pinv);
-            r.w = fold_lohi<WIDE>(lo[t][3], hi[t][3], A.p, A.pinv);
+            r.x = fold_acc<WIDE>(acc[t][0], 0u, A.p, A.pinv, A.two64);
+            r.y = fold_acc<WIDE>(acc[t][1], 0u, A.p, A.pinv, A.two64);
+            r.z = fold_acc<WIDE>(acc[t][2], 0u, A.p, A.pinv, A.two64);
+            r.w = fold_acc<WIDE>(acc[t][3], 0u, A.p, A.pinv, A.two64);
             reinterpret_cast<uint4 *>(&part[warp][t * kRowsPerT])[lane] = r;
         }
         __syncthreads();
