@@ -57,11 +57,12 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("F4LA_B200_LIB", LIB_PATH)     # A/B builds of the same library (tools/)
+    if not os.path.exists(path):
         raise F4LAError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C msolve_b200/csrc). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
     L.f4la_b200_version.restype = C.c_char_p
     L.f4la_b200_device_count.restype = C.c_int
     L.f4la_b200_create.restype = C.c_void_p

@@ -54,7 +54,10 @@ struct f4la_ctx {
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
     DevBuf sched, items, flowflags;
-    int           ge_columnwise = 0;    /* F4LA_B200_GE=columnwise: one find + one elimination pass per pivot (fallback, A-B) */
+    int           ge_mode = 0;          /* F4LA_B200_GE: (default) batched with the batch's pivot columns in shared memory;
+                                           "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
+                                           elimination pass per pivot (the fallbacks for very tall blocks, kept selectable for A-B) */
+    size_t        cached_smem_optin = 0;
     size_t        batch_smem_optin = 0;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
@@ -482,7 +485,48 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
         GEState *h_state = (GEState *)ctx->h_small.p;
         const size_t smem_cap = (size_t)216 * 1024;
-        if ((size_t)nrl * 5 + 64 <= smem_cap && !ctx->ge_columnwise) {
+        /* pivots per batch such that the batch's pivot columns (+ one column, + the used bytes) fit in
+         * the shared memory of one SM */
+        const uint32_t nrows4 = (nrl + 3u) & ~3u;
+        uint32_t nb_fit = 0;
+        if ((size_t)nrows4 * 5 + 64 <= smem_cap)
+            nb_fit = (uint32_t)((smem_cap - 64 - nrows4) / ((size_t)nrows4 * 4)) - 1;
+        if (nb_fit > kGeBatch) nb_fit = kGeBatch;
+        if (nb_fit >= 2 && ctx->ge_mode == 0) {
+            /* batched, pivot columns of the batch cached in shared memory by both passes */
+            const size_t disc_smem = ((size_t)nb_fit + 1) * nrows4 * 4 + nrows4, upd_smem = (size_t)nb_fit * nrows4 * 4 + nrows4;
+            if (disc_smem > ctx->cached_smem_optin) {
+                CU(cudaFuncSetAttribute(k_ge_discover_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                CU(cudaFuncSetAttribute(k_ge_batch_update_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                ctx->cached_smem_optin = smem_cap;
+            }
+            const uint32_t two64 = (uint32_t)(((~0ull) % p + 1) % p);
+            uint32_t upd_grid = (ncr + 31) / 32;
+            if (upd_grid > (uint32_t)ctx->sm_count) upd_grid = (uint32_t)ctx->sm_count;
+            k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+            ctx->launches++;
+            for (uint32_t batches = 0;;) {
+                const int group = 4;
+                for (int k = 0; k < group; ++k) {
+                    k_ge_discover_cached<<<1, kDiscoverThreads, disc_smem, s>>>(
+                        Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                        as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
+                    k_ge_batch_update_cached<<<upd_grid, kUpdate2Threads, upd_smem, s>>>(
+                        Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                        as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
+                    ctx->launches += 2;
+                }
+                batches += group;
+                CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+                CU(cudaGetLastError());
+                CU(cudaStreamSynchronize(s));
+                if (h_state->done) break;
+                if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
+                    return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+            }
+        } else if ((size_t)nrl * 5 + 64 <= smem_cap && ctx->ge_mode != 2) {
             /* batched: discover up to kGeBatch pivots on one SM, then one update pass over the block */
             const size_t disc_smem = (size_t)nrl * 5 + 64, upd_smem = (size_t)nrl * 4;
             if (disc_smem > ctx->batch_smem_optin) {
@@ -769,7 +813,7 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
-    ctx->ge_columnwise = ge && !strcmp(ge, "columnwise");
+    ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : 0;
     const char *bk = getenv("F4LA_B200_BULK");
     ctx->bulk = bk && atoi(bk) != 0;
     const char *tm = getenv("F4LA_B200_TMAX");

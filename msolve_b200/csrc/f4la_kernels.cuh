@@ -1085,6 +1085,192 @@ k_ge_batch_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_
     if (threadIdx.x == 0) colflag[c] = (uint8_t)(any != 0);
 }
 
+/* ---- the same two passes with the batch's pivot columns held in shared memory ---- */
+/* The pivot columns of a batch are the only data both passes re-read: every visited column of
+ * the discovery and every column of the update pass needs all of them.  Here they live in
+ * shared memory (nb * nrows words, nb <= kGeBatch chosen by the host so that they fit):
+ *  - k_ge_discover_cached applies the batch's earlier pivots to a visited column from there;
+ *  - k_ge_batch_update_cached loads them once per CTA (one CTA per SM, 32 warps), then every warp
+ *    streams whole columns through registers: the nb multipliers of a column come from an
+ *    nb-step scalar recurrence on its pivot-row entries, after which each element is
+ *    v + sum_k (p - s_k) * piv_k[r] in one 96-bit accumulation and one reduction. */
+constexpr int kUpdate2Threads = 1024;
+
+/* dynamic smem: [nrows4] column | [nb][nrows4] pivot columns of the batch | [nrows4] used bytes */
+__global__ void __launch_bounds__(kDiscoverThreads)
+k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t ncr, uint32_t nb,
+                     const uint8_t *colflag, uint8_t *used, uint8_t *ispiv, GEState *st,
+                     uint32_t *pivcol, uint32_t *pivrow, uint32_t *pivinv, uint32_t p, uint64_t pinv)
+{
+    extern __shared__ __align__(16) uint32_t s_col[];
+    uint32_t *s_piv = s_col + nrows4;
+    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_piv + (size_t)nb * nrows4);
+    __shared__ uint32_t s_min, s_prow[kGeBatch], s_pinv[kGeBatch];
+    const uint32_t tid = threadIdx.x;
+    if (st->done) {
+        if (tid == 0) st->cur_col = st->rank;
+        return;
+    }
+    const uint32_t k0 = st->rank;
+    uint32_t c = st->next_col;
+    for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_used[r] = used[r];
+    __syncthreads();
+    uint32_t np = 0, misses = 0;
+    bool exhausted = false;
+    while (np < nb && misses < 2) {
+        if (tid == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t base = c; base < ncr; base += kDiscoverThreads) {
+            const uint32_t k = base + tid;
+            if (k < ncr && colflag[k]) atomicMin(&s_min, k);
+            __syncthreads();
+            if (s_min != 0xffffffffu) break;
+            __syncthreads();
+        }
+        __syncthreads();
+        c = s_min;
+        __syncthreads();
+        if (c == 0xffffffffu) { exhausted = true; break; }
+        uint32_t *g = D + (size_t)c * ld;
+        for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_col[r] = __ldcg(&g[r]);
+        __syncthreads();
+        for (uint32_t k = 0; k < np; ++k) {             /* pivots of this batch, all left of c */
+            const uint32_t piv = s_prow[k];
+            const uint32_t sc = mulmod(s_col[piv], s_pinv[k], p, pinv);
+            __syncthreads();
+            if (sc != 0) {
+                const uint32_t *fcol = s_piv + (size_t)k * nrows4;
+                const uint32_t w = shoup_pre(sc, p);
+                for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
+                    const uint32_t f = fcol[r];
+                    if (f && r != piv) {
+                        const uint32_t t = shoup_mul(f, sc, w, p);
+                        const uint32_t v = s_col[r];
+                        s_col[r] = v >= t ? v - t : v + p - t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t r = tid; r < nrows; r += kDiscoverThreads)
+            if (s_col[r] != 0 && !s_used[r]) { atomicMin(&s_min, r); break; }
+        __syncthreads();
+        const uint32_t piv = s_min;
+        if (piv != 0xffffffffu) {
+            uint32_t *keep = s_piv + (size_t)np * nrows4;
+            for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
+                const uint32_t v = s_col[r];
+                g[r] = v;
+                keep[r] = v;
+            }
+            if (tid == 0) {
+                const uint32_t inv = modinv(s_col[piv], p);
+                pivcol[k0 + np] = c; pivrow[k0 + np] = piv; pivinv[k0 + np] = inv;
+                s_prow[np] = piv; s_pinv[np] = inv;
+                used[piv] = 1; s_used[piv] = 1; ispiv[c] = 1;
+            }
+            __threadfence();
+            np++;
+            misses = 0;
+        } else {
+            misses++;
+        }
+        __syncthreads();
+        c = c + 1;
+    }
+    if (tid == 0) {
+        st->cur_col = k0;
+        st->rank = k0 + np;
+        st->next_col = exhausted ? ncr : c;
+        if (exhausted) st->done = 1;
+    }
+}
+
+/* dynamic smem: [nb][nrows4] pivot columns (own pivot-row entry zeroed) | [nrows4] used bytes */
+__global__ void __launch_bounds__(kUpdate2Threads, 1)
+k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t ncr,
+                         uint32_t nbmax, uint8_t *__restrict__ colflag, const uint8_t *__restrict__ used,
+                         const uint8_t *__restrict__ ispiv, const GEState *__restrict__ st,
+                         const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,
+                         const uint32_t *__restrict__ pivinv, uint32_t p, uint64_t pinv, uint32_t two64)
+{
+    extern __shared__ __align__(16) uint32_t s_piv[];
+    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_piv + (size_t)nbmax * nrows4);
+    __shared__ uint32_t s_pc[kGeBatch], s_pr[kGeBatch], s_pi[kGeBatch], s_x[kGeBatch][kGeBatch];
+    const uint32_t k0 = st->cur_col, k1 = st->rank;
+    if (k0 >= k1) return;
+    const uint32_t nb = k1 - k0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t first = pivcol[k0];
+    const uint32_t nwarps = gridDim.x * (kUpdate2Threads / 32);
+    const uint32_t gwarp = blockIdx.x * (kUpdate2Threads / 32) + (tid >> 5);
+    if (first + 1 + blockIdx.x * (kUpdate2Threads / 32) >= ncr) return;      /* no column for this CTA */
+    if (tid < nb) { s_pc[tid] = pivcol[k0 + tid]; s_pr[tid] = pivrow[k0 + tid]; s_pi[tid] = pivinv[k0 + tid]; }
+    __syncthreads();
+    for (uint32_t k = 0; k < nb; ++k) {
+        const uint32_t *src = D + (size_t)s_pc[k] * ld;
+        const uint32_t own = s_pr[k];
+        for (uint32_t r = tid; r < nrows4; r += kUpdate2Threads)
+            s_piv[(size_t)k * nrows4 + r] = (r < nrows && r != own) ? __ldcg(&src[r]) : 0u;
+    }
+    for (uint32_t r = tid; r < nrows4; r += kUpdate2Threads) s_used[r] = r < nrows ? used[r] : (uint8_t)1;
+    __syncthreads();
+    if (tid < kGeBatch * kGeBatch) {
+        const uint32_t k = tid / kGeBatch, j = tid % kGeBatch;
+        s_x[k][j] = (k < nb && j < nb) ? s_piv[(size_t)k * nrows4 + s_pr[j]] : 0u;
+    }
+    __syncthreads();
+
+    for (uint32_t c = first + 1 + gwarp; c < ncr; c += nwarps) {
+        if (ispiv[c]) continue;
+        uint32_t *g = D + (size_t)c * ld;
+        /* multipliers of the batch for this column (every lane computes the same values) */
+        uint32_t e[kGeBatch], neg[kGeBatch];
+        bool touched = false;
+#pragma unroll
+        for (int j = 0; j < (int)kGeBatch; ++j) e[j] = (uint32_t)j < nb ? g[s_pr[j]] : 0u;
+#pragma unroll
+        for (int k = 0; k < (int)kGeBatch; ++k) {
+            neg[k] = 0;
+            if ((uint32_t)k < nb && s_pc[k] < c) {           /* pivot columns ascend within a batch */
+                const uint32_t sc = mulmod(e[k], s_pi[k], p, pinv);
+                if (sc) {
+                    touched = true;
+                    neg[k] = p - sc;
+#pragma unroll
+                    for (int j = k + 1; j < (int)kGeBatch; ++j)
+                        if ((uint32_t)j < nb)
+                            e[j] = mod_u64((uint64_t)e[j] + (uint64_t)neg[k] * s_x[k][j], p, pinv);
+                }
+            }
+        }
+        int any = 0;
+        for (uint32_t r4 = lane * 4; r4 < nrows4; r4 += 128) {
+            uint4 v = *reinterpret_cast<const uint4 *>(g + r4);
+            if (touched) {
+                Acc a[4] = {{v.x, 0u, 0u}, {v.y, 0u, 0u}, {v.z, 0u, 0u}, {v.w, 0u, 0u}};
+#pragma unroll
+                for (int k = 0; k < (int)kGeBatch; ++k) {
+                    if (neg[k]) {                            /* uniform over the warp */
+                        const uint4 f = *reinterpret_cast<const uint4 *>(s_piv + (size_t)k * nrows4 + r4);
+                        mac<true>(a[0], f.x, neg[k]); mac<true>(a[1], f.y, neg[k]);
+                        mac<true>(a[2], f.z, neg[k]); mac<true>(a[3], f.w, neg[k]);
+                    }
+                }
+                v.x = fold_acc<true>(a[0], 0u, p, pinv, two64); v.y = fold_acc<true>(a[1], 0u, p, pinv, two64);
+                v.z = fold_acc<true>(a[2], 0u, p, pinv, two64); v.w = fold_acc<true>(a[3], 0u, p, pinv, two64);
+                *reinterpret_cast<uint4 *>(g + r4) = v;
+            }
+            const uchar4 u = *reinterpret_cast<const uchar4 *>(s_used + r4);
+            any |= (v.x && !u.x) | (v.y && !u.y) | (v.z && !u.z) | (v.w && !u.w);
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) colflag[c] = (uint8_t)(any != 0);
+    }
+}
+
 /* Reduced echelon rows, dense: row t = pivot rank-1-t (decreasing lead). */
 __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t rank,
                              const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,

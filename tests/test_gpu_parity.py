@@ -295,11 +295,13 @@ def test_gpu_backend_inside_reference_f4_large(name):
     assert gb.digest() == want["digest"]
 
 
-def test_gpu_columnwise_elimination_fallback(monkeypatch):
-    """Blocks whose columns do not fit shared memory fall back to one find + one elimination
-    pass per pivot; force that path and check it against the reference fixtures."""
+@pytest.mark.parametrize("mode", ["uncached", "columnwise"])
+def test_gpu_elimination_fallbacks(monkeypatch, mode):
+    """Tall trailing blocks fall back from the shared-memory-cached batches to batches that re-read
+    the pivot columns from L2 ("uncached"), and to one find + one elimination pass per pivot
+    ("columnwise"); force each path and check it against the reference fixtures."""
     from msolve_b200.backend import Backend
-    monkeypatch.setenv("F4LA_B200_GE", "columnwise")
+    monkeypatch.setenv("F4LA_B200_GE", mode)
     be = Backend(0)
     try:
         n = 0
