@@ -57,7 +57,11 @@ struct f4la_ctx {
     int           ge_mode = 0;          /* F4LA_B200_GE: (default) batched with the batch's pivot columns in shared memory;
                                            "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
                                            elimination pass per pivot (the fallbacks for very tall blocks, kept selectable for A-B) */
-    size_t        cached_smem_optin = 0;
+    size_t        cached_smem_optin = 0, compress_smem_optin = 0;
+    int           ge_compress = 1;      /* F4LA_B200_COMPRESS=0: never use compress-and-verify on tall trailing blocks */
+    DevBuf        D2, combo;            /* compressed block, combination member lists */
+    uint64_t      d2_ld = 0;
+    uint64_t      compress_attempts = 0, compress_rejected = 0;
     size_t        batch_smem_optin = 0;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
@@ -66,7 +70,7 @@ struct f4la_ctx {
     uint64_t      seed = 0x9e3779b97f4a7c15ull;   /* random combinations of the probabilistic mode */
     int           bulk = 0;             /* F4LA_B200_BULK=1: bulk-copy (TMA engine) staging of the source vectors */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
-    HostBuf h_small, h_dense;
+    HostBuf h_small, h_dense, h_combo;
 };
 
 struct f4la_resident {
@@ -207,6 +211,214 @@ void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
     out->cols = (uint32_t *)malloc(sizeof(uint32_t));
     out->cf = malloc(4);
     out->src_row = (uint32_t *)malloc(sizeof(uint32_t));
+}
+
+/* same finaliser as the device-side mix64 */
+uint64_t host_mix64(uint64_t x)
+{
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+/* Gauss-Jordan on a column-major block (ncr columns of ld words, nrl rows used): pivot columns, rows and
+ * inverses are left in ctx->pivcol / pivrow / pivinv, the block holds the reduced rows unnormalised
+ * (k_ge_extract scales them). */
+int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_t ncr, uint32_t p, uint64_t pinv,
+                 uint32_t *rank_out)
+{
+    cudaStream_t s = ctx->stream;
+    const uint32_t maxrank = nrl < ncr ? nrl : ncr;
+    OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
+    OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
+    OK(ensure(ctx, ctx->used, (size_t)ld + 16));
+    OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
+    OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
+    OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
+    OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
+    CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
+    CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
+    CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
+    GEState *h_state = (GEState *)ctx->h_small.p;
+    const size_t smem_cap = (size_t)216 * 1024;
+    /* pivots per batch such that the batch's pivot columns (+ one column, + the used bytes) fit in
+     * the shared memory of one SM */
+    const uint32_t nrows4 = (nrl + 3u) & ~3u;
+    uint32_t nb_fit = 0;
+    if ((size_t)nrows4 * 5 + 64 <= smem_cap)
+        nb_fit = (uint32_t)((smem_cap - 64 - nrows4) / ((size_t)nrows4 * 4)) - 1;
+    if (nb_fit > kGeBatch) nb_fit = kGeBatch;
+    if (nb_fit >= 2 && ctx->ge_mode == 0) {
+        /* batched, pivot columns of the batch cached in shared memory by both passes */
+        const size_t disc_smem = ((size_t)nb_fit + 1) * nrows4 * 4 + nrows4, upd_smem = (size_t)nb_fit * nrows4 * 4 + nrows4;
+        if (disc_smem > ctx->cached_smem_optin) {
+            CU(cudaFuncSetAttribute(k_ge_discover_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            CU(cudaFuncSetAttribute(k_ge_batch_update_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            ctx->cached_smem_optin = smem_cap;
+        }
+        const uint32_t two64 = (uint32_t)(((~0ull) % p + 1) % p);
+        uint32_t upd_grid = (ncr + 31) / 32;
+        if (upd_grid > (uint32_t)ctx->sm_count) upd_grid = (uint32_t)ctx->sm_count;
+        k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+        ctx->launches++;
+        for (uint32_t batches = 0;;) {
+            const int group = 4;
+            for (int k = 0; k < group; ++k) {
+                k_ge_discover_cached<<<1, kDiscoverThreads, disc_smem, s>>>(
+                    Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                    as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                    as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
+                k_ge_batch_update_cached<<<upd_grid, kUpdate2Threads, upd_smem, s>>>(
+                    Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                    as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
+                    as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
+                ctx->launches += 2;
+            }
+            batches += group;
+            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s));
+            if (h_state->done) break;
+            if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
+                return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+        }
+    } else if ((size_t)nrl * 5 + 64 <= smem_cap && ctx->ge_mode != 2) {
+        /* batched: discover up to kGeBatch pivots on one SM, then one update pass over the block */
+        const size_t disc_smem = (size_t)nrl * 5 + 64, upd_smem = (size_t)nrl * 4;
+        if (disc_smem > ctx->batch_smem_optin) {
+            CU(cudaFuncSetAttribute(k_ge_discover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            CU(cudaFuncSetAttribute(k_ge_batch_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            ctx->batch_smem_optin = smem_cap;
+        }
+        k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+        ctx->launches++;
+        for (uint32_t batches = 0;;) {
+            const int group = 4;
+            for (int k = 0; k < group; ++k) {
+                k_ge_discover<<<1, kDiscoverThreads, disc_smem, s>>>(
+                    Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
+                    as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                    as<uint32_t>(ctx->pivinv), p, pinv);
+                k_ge_batch_update<<<ncr, kUpdateThreads, upd_smem, s>>>(
+                    Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
+                    as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                    as<uint32_t>(ctx->pivinv), p, pinv);
+                ctx->launches += 2;
+            }
+            batches += group;
+            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s));
+            if (h_state->done) break;
+            if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
+                return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+        }
+    } else {
+    k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+    ctx->launches++;
+    for (uint32_t done_steps = 0;;) {
+        const int batch = 16;
+        for (int k = 0; k < batch; ++k) {
+            k_ge_find<<<1, 1024, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                         as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate),
+                                         as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                         as<uint32_t>(ctx->pivinv), p);
+            k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                                               as<GEState>(ctx->gestate), p, pinv);
+            ctx->launches += 2;
+        }
+        done_steps += batch;
+        CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        if (h_state->done) break;
+        if (done_steps > maxrank + 2 * batch)
+            return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+    }
+    }
+    *rank_out = h_state->rank;
+    return F4LA_OK;
+}
+
+/* Tall trailing block: eliminate on kc random combinations of its rows, then verify exactly that every
+ * row of the block lies in the span of the result (see k_ge_compress / k_ge_verify).  *ok = false
+ * means "not applicable or not confirmed": the caller eliminates on the block itself, which this
+ * function never modifies.  On success the reduced rows are in ctx->D2 (leading dimension ctx->d2_ld). */
+constexpr uint32_t kCompressRows = 768, kCompressWeight = 8, kCompressSlack = 48;
+
+int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_t ncr, uint32_t p,
+                        uint64_t pinv, uint32_t *rank_out, bool *ok)
+{
+    cudaStream_t s = ctx->stream;
+    *ok = false;
+    const uint32_t nrows4 = (nrl + 3u) & ~3u;
+    if ((size_t)nrows4 * 4 > (size_t)216 * 1024 || p < 3) return F4LA_OK;
+    const uint32_t two64 = (uint32_t)(((~0ull) % p + 1) % p);
+    for (uint32_t kc = kCompressRows; 2 * kc <= nrl; kc *= 4) {
+        /* members of every combination: row r joins one combination of each family (hash of seed, family, row) */
+        const uint32_t kw = kc / kCompressWeight;
+        const size_t nmem = (size_t)nrl * kCompressWeight;
+        OK(ensure_host(ctx, ctx->h_combo, ((size_t)kc + 1 + 2 * nmem) * 4 + 64));
+        uint32_t *h_ptr = (uint32_t *)ctx->h_combo.p, *h_row = h_ptr + kc + 1, *h_rho = h_row + nmem;
+        std::vector<uint32_t> slot(nmem), cnt(kc + 1, 0);
+        for (uint32_t r = 0; r < nrl; ++r)
+            for (uint32_t f = 0; f < kCompressWeight; ++f) {
+                const uint64_t h = host_mix64(ctx->seed ^ 0x5bd1e995u ^ ((uint64_t)f << 40) ^ ((uint64_t)kc << 48) ^ r);
+                const uint32_t q = f * kw + (uint32_t)(h % kw);
+                slot[(size_t)r * kCompressWeight + f] = q;
+                cnt[q + 1]++;
+            }
+        for (uint32_t q = 0; q < kc; ++q) cnt[q + 1] += cnt[q];
+        memcpy(h_ptr, cnt.data(), ((size_t)kc + 1) * 4);
+        for (uint32_t r = 0; r < nrl; ++r)
+            for (uint32_t f = 0; f < kCompressWeight; ++f) {
+                const uint64_t h = host_mix64(ctx->seed ^ 0x5bd1e995u ^ ((uint64_t)f << 40) ^ ((uint64_t)kc << 48) ^ r);
+                const uint32_t e = cnt[slot[(size_t)r * kCompressWeight + f]]++;
+                h_row[e] = r;
+                h_rho[e] = 1u + (uint32_t)((h >> 20) % (p - 1));
+            }
+        OK(ensure(ctx, ctx->combo, ((size_t)kc + 1 + 2 * nmem) * 4));
+        OK(ensure(ctx, ctx->D2, (size_t)ncr * kc * 4));
+        uint32_t *d_ptr = as<uint32_t>(ctx->combo), *d_row = d_ptr + kc + 1, *d_rho = d_row + nmem;
+        CU(cudaMemcpyAsync(d_ptr, h_ptr, ((size_t)kc + 1 + 2 * nmem) * 4, cudaMemcpyHostToDevice, s));
+        if ((size_t)nrows4 * 4 > ctx->compress_smem_optin) {
+            CU(cudaFuncSetAttribute(k_ge_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+            ctx->compress_smem_optin = (size_t)216 * 1024;
+        }
+        uint32_t *D2 = as<uint32_t>(ctx->D2);
+        k_ge_compress<<<ncr, 256, (size_t)nrows4 * 4, s>>>(Dm, ld, nrl, nrows4, kc, d_ptr, d_row, d_rho, D2, p, pinv, two64);
+        ctx->launches++;
+        uint32_t rank = 0;
+        OK(gauss_jordan(ctx, D2, kc, kc, ncr, p, pinv, &rank));
+        if (rank + kCompressSlack > kc) continue;            /* too close to the number of combinations */
+        OK(ensure(ctx, ctx->dense_out, (size_t)(rank ? rank : 1) * ncr * 4 + 16));
+        if (rank) {
+            dim3 grid((ncr + 255) / 256, rank);
+            k_ge_extract<<<grid, 256, 0, s>>>(D2, kc, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                              as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
+                                              as<uint32_t>(ctx->dense_out), p, pinv);
+            ctx->launches++;
+        }
+        uint32_t *d_bad = as<uint32_t>(ctx->flags32) + 8;
+        CU(cudaMemsetAsync(d_bad, 0, 4, s));
+        const uint32_t nrows_pad = (nrl + kVerTile - 1) / kVerTile * kVerTile;     /* <= ld, padding rows are zero */
+        dim3 vgrid(nrows_pad / kVerTile, (ncr + kVerTile - 1) / kVerTile);
+        k_ge_verify<<<vgrid, 256, 0, s>>>(Dm, ld, nrows_pad, ncr, rank, as<uint32_t>(ctx->pivcol),
+                                          as<uint32_t>(ctx->dense_out), p, pinv, two64, d_bad);
+        ctx->launches++;
+        uint32_t *h_bad = (uint32_t *)ctx->h_small.p + 128;
+        CU(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        ctx->compress_attempts++;
+        if (*h_bad) { ctx->compress_rejected++; return F4LA_OK; }      /* rank lost in the compression: eliminate directly */
+        ctx->d2_ld = kc;
+        *rank_out = rank;
+        *ok = true;
+        return F4LA_OK;
+    }
+    return F4LA_OK;
 }
 
 /* The whole pipeline on a device-resident matrix. */
@@ -368,6 +580,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     int T = 1, n_flow_ev = 0;
     bool items_built = false;
     uint32_t *Dm = nullptr;
+    uint64_t ge_ld = 0;               /* leading dimension of the block the reduced rows are read from */
     const uint32_t rba_words = (nru + 31) / 32;
 
     for (;;) {
@@ -473,114 +686,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     Dm = as<uint32_t>(ctx->D);
     rank = 0;
     if (!nf_mode && !by_lead) {
-        OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
-        OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
-        OK(ensure(ctx, ctx->used, (size_t)ld + 16));
-        OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
-        OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
-        OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
-        OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
-        CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
-        CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
-        CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
-        GEState *h_state = (GEState *)ctx->h_small.p;
-        const size_t smem_cap = (size_t)216 * 1024;
-        /* pivots per batch such that the batch's pivot columns (+ one column, + the used bytes) fit in
-         * the shared memory of one SM */
-        const uint32_t nrows4 = (nrl + 3u) & ~3u;
-        uint32_t nb_fit = 0;
-        if ((size_t)nrows4 * 5 + 64 <= smem_cap)
-            nb_fit = (uint32_t)((smem_cap - 64 - nrows4) / ((size_t)nrows4 * 4)) - 1;
-        if (nb_fit > kGeBatch) nb_fit = kGeBatch;
-        if (nb_fit >= 2 && ctx->ge_mode == 0) {
-            /* batched, pivot columns of the batch cached in shared memory by both passes */
-            const size_t disc_smem = ((size_t)nb_fit + 1) * nrows4 * 4 + nrows4, upd_smem = (size_t)nb_fit * nrows4 * 4 + nrows4;
-            if (disc_smem > ctx->cached_smem_optin) {
-                CU(cudaFuncSetAttribute(k_ge_discover_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                CU(cudaFuncSetAttribute(k_ge_batch_update_cached, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                ctx->cached_smem_optin = smem_cap;
-            }
-            const uint32_t two64 = (uint32_t)(((~0ull) % p + 1) % p);
-            uint32_t upd_grid = (ncr + 31) / 32;
-            if (upd_grid > (uint32_t)ctx->sm_count) upd_grid = (uint32_t)ctx->sm_count;
-            k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-            ctx->launches++;
-            for (uint32_t batches = 0;;) {
-                const int group = 4;
-                for (int k = 0; k < group; ++k) {
-                    k_ge_discover_cached<<<1, kDiscoverThreads, disc_smem, s>>>(
-                        Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                        as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
-                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
-                    k_ge_batch_update_cached<<<upd_grid, kUpdate2Threads, upd_smem, s>>>(
-                        Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                        as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
-                        as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
-                    ctx->launches += 2;
-                }
-                batches += group;
-                CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
-                CU(cudaGetLastError());
-                CU(cudaStreamSynchronize(s));
-                if (h_state->done) break;
-                if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
-                    return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
-            }
-        } else if ((size_t)nrl * 5 + 64 <= smem_cap && ctx->ge_mode != 2) {
-            /* batched: discover up to kGeBatch pivots on one SM, then one update pass over the block */
-            const size_t disc_smem = (size_t)nrl * 5 + 64, upd_smem = (size_t)nrl * 4;
-            if (disc_smem > ctx->batch_smem_optin) {
-                CU(cudaFuncSetAttribute(k_ge_discover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                CU(cudaFuncSetAttribute(k_ge_batch_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-                ctx->batch_smem_optin = smem_cap;
-            }
-            k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-            ctx->launches++;
-            for (uint32_t batches = 0;;) {
-                const int group = 4;
-                for (int k = 0; k < group; ++k) {
-                    k_ge_discover<<<1, kDiscoverThreads, disc_smem, s>>>(
-                        Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
-                        as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
-                        as<uint32_t>(ctx->pivinv), p, pinv);
-                    k_ge_batch_update<<<ncr, kUpdateThreads, upd_smem, s>>>(
-                        Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
-                        as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
-                        as<uint32_t>(ctx->pivinv), p, pinv);
-                    ctx->launches += 2;
-                }
-                batches += group;
-                CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
-                CU(cudaGetLastError());
-                CU(cudaStreamSynchronize(s));
-                if (h_state->done) break;
-                if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
-                    return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
-            }
-        } else {
-        k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-        ctx->launches++;
-        for (uint32_t done_steps = 0;;) {
-            const int batch = 16;
-            for (int k = 0; k < batch; ++k) {
-                k_ge_find<<<1, 1024, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                                             as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate),
-                                             as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
-                                             as<uint32_t>(ctx->pivinv), p);
-                k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
-                                                   as<GEState>(ctx->gestate), p, pinv);
-                ctx->launches += 2;
-            }
-            done_steps += batch;
-            CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
-            CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(s));
-            if (h_state->done) break;
-            if (done_steps > maxrank + 2 * batch)
-                return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
+        bool compressed = false;
+        if (!want_rba && !combos && ctx->ge_compress && nrl >= 2 * kCompressRows) {
+            int rc = compress_and_verify(ctx, Dm, ld, nrl, ncr, p, pinv, &rank, &compressed);
+            if (rc != F4LA_OK) return rc;
         }
-        }
-        rank = h_state->rank;
+        ge_ld = ld;
+        if (compressed) { Dm = as<uint32_t>(ctx->D2); ge_ld = ctx->d2_ld; }
+        else OK(gauss_jordan(ctx, Dm, ld, nrl, ncr, p, pinv, &rank));
     }
     /* probabilistic mode: accept when the rank stays clear of the number of combinations */
     if (!combos || rank + kProbSlack <= nvr) break;
@@ -614,7 +727,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             ctx->launches++;
         } else if (rank) {
             dim3 grid((ncr + 255) / 256, rank);
-            k_ge_extract<<<grid, 256, 0, s>>>(Dm, ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+            k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
                                               as<uint32_t>(ctx->dense_out), p, pinv);
             ctx->launches++;
@@ -814,6 +927,8 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : 0;
+    const char *cm = getenv("F4LA_B200_COMPRESS");
+    if (cm) ctx->ge_compress = atoi(cm) != 0;
     const char *bk = getenv("F4LA_B200_BULK");
     ctx->bulk = bk && atoi(bk) != 0;
     const char *tm = getenv("F4LA_B200_TMAX");
@@ -833,10 +948,11 @@ void f4la_b200_destroy(f4la_ctx *ctx)
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
                       &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
-                      &ctx->invmap, &ctx->leads, &ctx->rba};
+                      &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
     for (auto b : bufs) free_dev(*b);
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
+    if (ctx->h_combo.p) cudaFreeHost(ctx->h_combo.p);
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->flow_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);

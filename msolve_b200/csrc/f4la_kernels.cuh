@@ -1271,6 +1271,116 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
     }
 }
 
+/* ---- compress-and-verify for tall trailing blocks (exact, Las Vegas) ---------------------- */
+/* D' has nrl rows but a small rank r.  Instead of eliminating on all nrl rows:
+ *   1. D'' = R * D' for a sparse random R (kc x nrl, every row of D' enters `weight` combinations,
+ *      as in the probabilistic mode) -- kc rows only;
+ *   2. Gauss-Jordan on D'' gives pivot columns pc_k and reduced rows B (r x ncr);
+ *   3. VERIFY, exactly, that every row of D' lies in the row space of B: since B is reduced with
+ *      pivots at pc_k, row i can only be sum_k D'[i][pc_k] * B_k, so the test is the matrix identity
+ *      D' == D'[:, pc] * B.  rowspace(B) is inside rowspace(D') by construction, so a passed test
+ *      proves equality and B is THE reduced echelon form (unique) -- bit-identical output.  A failed
+ *      test (rank lost in the random compression, probability ~ 1/p per degree of slack) falls back
+ *      to the elimination on D' itself, which is untouched.
+ * The identity is a dense (nrl x r) x (r x ncr) product on the CUDA cores (96-bit accumulators):
+ * fully parallel, no pivot-by-pivot latency chain -- what bounds the direct elimination. */
+
+/* D''[c][q] = sum over the members e of combination q of rho[e] * D'[c][row[e]].  One CTA per column,
+ * the column staged in shared memory (nrows4 words). */
+__global__ void __launch_bounds__(256)
+k_ge_compress(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t kc,
+              const uint32_t *__restrict__ slot_ptr, const uint32_t *__restrict__ slot_row,
+              const uint32_t *__restrict__ slot_rho, uint32_t *__restrict__ out,
+              uint32_t p, uint64_t pinv, uint32_t two64)
+{
+    extern __shared__ __align__(16) uint32_t s_col[];
+    const uint32_t c = blockIdx.x;
+    const uint32_t *g = D + (size_t)c * ld;
+    int any = 0;
+    for (uint32_t r = threadIdx.x; r < nrows4; r += blockDim.x) {
+        const uint32_t v = r < nrows ? g[r] : 0u;
+        s_col[r] = v;
+        any |= v != 0;
+    }
+    any = __syncthreads_or(any);
+    uint32_t *o = out + (size_t)c * kc;
+    if (!any) {
+        for (uint32_t q = threadIdx.x; q < kc; q += blockDim.x) o[q] = 0;
+        return;
+    }
+    for (uint32_t q = threadIdx.x; q < kc; q += blockDim.x) {
+        Acc a = {0u, 0u, 0u};
+        const uint32_t e1 = slot_ptr[q + 1];
+        for (uint32_t e = slot_ptr[q]; e < e1; ++e) mac<true>(a, s_col[slot_row[e]], slot_rho[e]);
+        o[q] = fold_acc<true>(a, 0u, p, pinv, two64);
+    }
+}
+
+/* mismatch |= any(D'[i][c] != sum_t D'[i][pc(t)] * B[t][c]);  B row t belongs to pivot rank-1-t.
+ * 64 x 64 tile per CTA, 4 x 4 per thread, 16 pivots per shared-memory stage. */
+constexpr int kVerTile = 64, kVerK = 16;
+__global__ void __launch_bounds__(256)
+k_ge_verify(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows_pad, uint32_t ncr, uint32_t rank,
+            const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ B,
+            uint32_t p, uint64_t pinv, uint32_t two64, uint32_t *__restrict__ mismatch)
+{
+    __shared__ __align__(16) uint32_t sP[kVerK][kVerTile];
+    __shared__ __align__(16) uint32_t sB[kVerK][kVerTile];
+    const uint32_t i0 = blockIdx.x * kVerTile, c0 = blockIdx.y * kVerTile;
+    const uint32_t tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    Acc acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = Acc{0u, 0u, 0u};
+    for (uint32_t t0 = 0; t0 < rank; t0 += kVerK) {
+        /* stage: 16 x 64 of each operand, 4 words per thread */
+        {
+            const uint32_t kk = threadIdx.x >> 4, w = (threadIdx.x & 15) * 4;
+            const uint32_t t = t0 + kk;
+            uint4 pv = make_uint4(0, 0, 0, 0), bv = make_uint4(0, 0, 0, 0);
+            if (t < rank) {
+                const uint32_t pc = pivcol[rank - 1 - t];
+                pv = *reinterpret_cast<const uint4 *>(D + (size_t)pc * ld + i0 + w);
+                const uint32_t *brow = B + (size_t)t * ncr + c0 + w;
+                if (c0 + w + 3 < ncr && (((size_t)t * ncr + c0 + w) & 3) == 0) bv = *reinterpret_cast<const uint4 *>(brow);
+                else {
+                    if (c0 + w < ncr) bv.x = brow[0];
+                    if (c0 + w + 1 < ncr) bv.y = brow[1];
+                    if (c0 + w + 2 < ncr) bv.z = brow[2];
+                    if (c0 + w + 3 < ncr) bv.w = brow[3];
+                }
+            }
+            *reinterpret_cast<uint4 *>(&sP[kk][w]) = pv;
+            *reinterpret_cast<uint4 *>(&sB[kk][w]) = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kVerK; ++kk) {
+            const uint4 pv = *reinterpret_cast<const uint4 *>(&sP[kk][ty * 4]);
+            const uint4 bv = *reinterpret_cast<const uint4 *>(&sB[kk][tx * 4]);
+            const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ba[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) mac<true>(acc[a][b], pa[a], ba[b]);
+        }
+        __syncthreads();
+    }
+    uint32_t bad = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const uint32_t c = c0 + tx * 4 + b;
+        if (c >= ncr) continue;
+        const uint4 dv = *reinterpret_cast<const uint4 *>(D + (size_t)c * ld + i0 + ty * 4);
+        bad |= fold_acc<true>(acc[0][b], 0u, p, pinv, two64) != dv.x;
+        bad |= fold_acc<true>(acc[1][b], 0u, p, pinv, two64) != dv.y;
+        bad |= fold_acc<true>(acc[2][b], 0u, p, pinv, two64) != dv.z;
+        bad |= fold_acc<true>(acc[3][b], 0u, p, pinv, two64) != dv.w;
+    }
+    if (bad) atomicOr(mismatch, 1u);
+}
+
 /* Reduced echelon rows, dense: row t = pivot rank-1-t (decreasing lead). */
 __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t rank,
                              const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,
