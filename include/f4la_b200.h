@@ -71,7 +71,13 @@ typedef struct f4la_flat_matrix {
  * input lower row i; rows reducing to zero have length 0. */
 #define F4LA_FLAG_NORMALFORM  1u
 /* known pivots are keyed by their lead column instead of by row index
- * (in_final_reduction_step, la_ff_32.c:2618-2622) */
+ * (in_final_reduction_step, la_ff_32.c:2618-2622; interreduce_matrix_rows, :4254-4326).
+ * Contract: every row (upper and lower) is monic with its lead first, all leads are distinct,
+ * and the lower rows come in the reference's order (sort_matrix_rows_increasing, f4.c:603:
+ * a lower row only contains leads of lower rows that come BEFORE it).  The reference then
+ * reduces the lower rows one after the other by everything seen so far, which under that
+ * order is the full inter-reduction: result row i = reduced form of lower row i, in place.
+ * The device computes exactly that as one triangular solve of unit vectors (no elimination). */
 #define F4LA_FLAG_PIVOT_BY_LEAD 2u
 /* also return, for every lower row, the bit set of known pivots that were
  * applied to it (non-zero multipliers): the `rba` arrays the reference fills
@@ -120,7 +126,9 @@ typedef struct f4la_stats {
     double   ms_hot_kernel;   /* sum over the launches of k_pull_flow (CUDA
                                  events around each launch)                   */
     uint32_t hot_kernel_launches;
-    uint32_t reserved;
+    uint32_t echelon_path;    /* trailing block: bit 0 result from compress-and-verify, bit 1 a verification
+                                 failed (direct elimination used instead), bit 2 the number of combinations was
+                                 escalated at least once                                                   */
 } f4la_stats;
 
 typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */

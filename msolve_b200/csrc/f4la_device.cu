@@ -61,7 +61,9 @@ struct f4la_ctx {
     int           ge_compress = 1;      /* F4LA_B200_COMPRESS=0: never use compress-and-verify on tall trailing blocks */
     DevBuf        D2, combo;            /* compressed block, combination member lists */
     uint64_t      d2_ld = 0;
-    uint64_t      compress_attempts = 0, compress_rejected = 0;
+    uint64_t      compress_attempts = 0, compress_rejected = 0, compress_escalated = 0;
+    uint32_t      compress_rows = 768;  /* F4LA_B200_COMPRESS_ROWS: combinations of the first attempt (x4 per escalation) */
+    int           compress_fault = 0;   /* F4LA_B200_COMPRESS_FAULT=1 (tests): treat every verification as failed */
     size_t        batch_smem_optin = 0;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
@@ -345,7 +347,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
  * row of the block lies in the span of the result (see k_ge_compress / k_ge_verify).  *ok = false
  * means "not applicable or not confirmed": the caller eliminates on the block itself, which this
  * function never modifies.  On success the reduced rows are in ctx->D2 (leading dimension ctx->d2_ld). */
-constexpr uint32_t kCompressRows = 768, kCompressWeight = 8, kCompressSlack = 48;
+constexpr uint32_t kCompressRows = 768, kCompressWeight = 8, kCompressSlack = 48;   /* defaults; $F4LA_B200_COMPRESS_ROWS for tests */
 
 int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_t ncr, uint32_t p,
                         uint64_t pinv, uint32_t *rank_out, bool *ok)
@@ -355,7 +357,8 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
     const uint32_t nrows4 = (nrl + 3u) & ~3u;
     if ((size_t)nrows4 * 4 > (size_t)216 * 1024 || p < 3) return F4LA_OK;
     const uint32_t two64 = (uint32_t)(((~0ull) % p + 1) % p);
-    for (uint32_t kc = kCompressRows; 2 * kc <= nrl; kc *= 4) {
+    for (uint32_t kc = ctx->compress_rows; 2 * kc <= nrl; kc *= 4) {
+        const uint32_t slack = kc >= 8 * kCompressSlack ? kCompressSlack : kc / 8;
         /* members of every combination: row r joins one combination of each family (hash of seed, family, row) */
         const uint32_t kw = kc / kCompressWeight;
         const size_t nmem = (size_t)nrl * kCompressWeight;
@@ -391,7 +394,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         ctx->launches++;
         uint32_t rank = 0;
         OK(gauss_jordan(ctx, D2, kc, kc, ncr, p, pinv, &rank));
-        if (rank + kCompressSlack > kc) continue;            /* too close to the number of combinations */
+        if (rank + slack > kc) { ctx->compress_escalated++; continue; }   /* too close to the number of combinations */
         OK(ensure(ctx, ctx->dense_out, (size_t)(rank ? rank : 1) * ncr * 4 + 16));
         if (rank) {
             dim3 grid((ncr + 255) / 256, rank);
@@ -412,7 +415,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s));
         ctx->compress_attempts++;
-        if (*h_bad) { ctx->compress_rejected++; return F4LA_OK; }      /* rank lost in the compression: eliminate directly */
+        if (*h_bad || ctx->compress_fault) { ctx->compress_rejected++; return F4LA_OK; }      /* rank lost in the compression: eliminate directly */
         ctx->d2_ld = kc;
         *rank_out = rank;
         *ok = true;
@@ -581,6 +584,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     bool items_built = false;
     uint32_t *Dm = nullptr;
     uint64_t ge_ld = 0;               /* leading dimension of the block the reduced rows are read from */
+    uint32_t echelon_path = 0;
     const uint32_t rba_words = (nru + 31) / 32;
 
     for (;;) {
@@ -687,9 +691,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     rank = 0;
     if (!nf_mode && !by_lead) {
         bool compressed = false;
-        if (!want_rba && !combos && ctx->ge_compress && nrl >= 2 * kCompressRows) {
+        if (!want_rba && !combos && ctx->ge_compress && nrl >= 2 * ctx->compress_rows) {
+            const uint64_t rej0 = ctx->compress_rejected, esc0 = ctx->compress_escalated;
             int rc = compress_and_verify(ctx, Dm, ld, nrl, ncr, p, pinv, &rank, &compressed);
             if (rc != F4LA_OK) return rc;
+            echelon_path = (compressed ? 1u : 0u) | (ctx->compress_rejected != rej0 ? 2u : 0u) |
+                           (ctx->compress_escalated != esc0 ? 4u : 0u);
         }
         ge_ld = ld;
         if (compressed) { Dm = as<uint32_t>(ctx->D2); ge_ld = ctx->d2_ld; }
@@ -834,6 +841,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         st->bytes_d2h = d2h_bytes;
         st->kernel_launches = ctx->launches - launches0;
         st->rank = rank;
+        st->echelon_path = echelon_path;
     }
     return F4LA_OK;
 }
@@ -929,6 +937,10 @@ f4la_ctx *f4la_b200_create(int device)
     ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : 0;
     const char *cm = getenv("F4LA_B200_COMPRESS");
     if (cm) ctx->ge_compress = atoi(cm) != 0;
+    const char *cr = getenv("F4LA_B200_COMPRESS_ROWS");
+    if (cr && atoi(cr) >= 16) ctx->compress_rows = (uint32_t)atoi(cr) / 8 * 8;
+    const char *cf = getenv("F4LA_B200_COMPRESS_FAULT");
+    ctx->compress_fault = cf && atoi(cf) != 0;
     const char *bk = getenv("F4LA_B200_BULK");
     ctx->bulk = bk && atoi(bk) != 0;
     const char *tm = getenv("F4LA_B200_TMAX");

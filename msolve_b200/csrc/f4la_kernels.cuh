@@ -1095,6 +1095,8 @@ k_ge_batch_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_
  *    nb-step scalar recurrence on its pivot-row entries, after which each element is
  *    v + sum_k (p - s_k) * piv_k[r] in one 96-bit accumulation and one reduction. */
 constexpr int kUpdate2Threads = 1024;
+constexpr uint32_t kGeBatchCached = 32;      /* most pivots per batch (when nrows is small enough for shared memory) */
+constexpr uint32_t kGeMissLimit = 4;         /* consecutive empty visited columns that end a batch */
 
 /* dynamic smem: [nrows4] column | [nb][nrows4] pivot columns of the batch | [nrows4] used bytes */
 __global__ void __launch_bounds__(kDiscoverThreads)
@@ -1105,7 +1107,7 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
     extern __shared__ __align__(16) uint32_t s_col[];
     uint32_t *s_piv = s_col + nrows4;
     uint8_t *s_used = reinterpret_cast<uint8_t *>(s_piv + (size_t)nb * nrows4);
-    __shared__ uint32_t s_min, s_prow[kGeBatch], s_pinv[kGeBatch];
+    __shared__ uint32_t s_min, s_prow[kGeBatchCached], s_pinv[kGeBatchCached];
     const uint32_t tid = threadIdx.x;
     if (st->done) {
         if (tid == 0) st->cur_col = st->rank;
@@ -1117,7 +1119,7 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
     __syncthreads();
     uint32_t np = 0, misses = 0;
     bool exhausted = false;
-    while (np < nb && misses < 2) {
+    while (np < nb && misses < kGeMissLimit) {
         if (tid == 0) s_min = 0xffffffffu;
         __syncthreads();
         for (uint32_t base = c; base < ncr; base += kDiscoverThreads) {
@@ -1149,8 +1151,8 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
                         s_col[r] = v >= t ? v - t : v + p - t;
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
         if (tid == 0) s_min = 0xffffffffu;
         __syncthreads();
@@ -1171,7 +1173,6 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
                 s_prow[np] = piv; s_pinv[np] = inv;
                 used[piv] = 1; s_used[piv] = 1; ispiv[c] = 1;
             }
-            __threadfence();
             np++;
             misses = 0;
         } else {
@@ -1198,7 +1199,9 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
 {
     extern __shared__ __align__(16) uint32_t s_piv[];
     uint8_t *s_used = reinterpret_cast<uint8_t *>(s_piv + (size_t)nbmax * nrows4);
-    __shared__ uint32_t s_pc[kGeBatch], s_pr[kGeBatch], s_pi[kGeBatch], s_x[kGeBatch][kGeBatch];
+    __shared__ uint32_t s_pc[kGeBatchCached], s_pr[kGeBatchCached], s_pi[kGeBatchCached];
+    __shared__ uint32_t s_x[kGeBatchCached][kGeBatchCached + 1];      /* x[k][j] = piv_k[row of pivot j] */
+    __shared__ uint32_t s_neg[kUpdate2Threads / 32][kGeBatchCached]; /* per warp: negated multipliers of its column */
     const uint32_t k0 = st->cur_col, k1 = st->rank;
     if (k0 >= k1) return;
     const uint32_t nb = k1 - k0;
@@ -1217,8 +1220,8 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
     }
     for (uint32_t r = tid; r < nrows4; r += kUpdate2Threads) s_used[r] = r < nrows ? used[r] : (uint8_t)1;
     __syncthreads();
-    if (tid < kGeBatch * kGeBatch) {
-        const uint32_t k = tid / kGeBatch, j = tid % kGeBatch;
+    for (uint32_t q = tid; q < kGeBatchCached * kGeBatchCached; q += kUpdate2Threads) {
+        const uint32_t k = q / kGeBatchCached, j = q % kGeBatchCached;
         s_x[k][j] = (k < nb && j < nb) ? s_piv[(size_t)k * nrows4 + s_pr[j]] : 0u;
     }
     __syncthreads();
@@ -1226,37 +1229,35 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
     for (uint32_t c = first + 1 + gwarp; c < ncr; c += nwarps) {
         if (ispiv[c]) continue;
         uint32_t *g = D + (size_t)c * ld;
-        /* multipliers of the batch for this column (every lane computes the same values) */
-        uint32_t e[kGeBatch], neg[kGeBatch];
+        /* multipliers of the batch for this column: lane j tracks the column's entry in the row of
+         * pivot j; pivot k's multiplier ends up (negated) in lane k */
+        uint32_t e = lane < nb ? g[s_pr[lane]] : 0u, neg = 0;
         bool touched = false;
-#pragma unroll
-        for (int j = 0; j < (int)kGeBatch; ++j) e[j] = (uint32_t)j < nb ? g[s_pr[j]] : 0u;
-#pragma unroll
-        for (int k = 0; k < (int)kGeBatch; ++k) {
-            neg[k] = 0;
-            if ((uint32_t)k < nb && s_pc[k] < c) {           /* pivot columns ascend within a batch */
-                const uint32_t sc = mulmod(e[k], s_pi[k], p, pinv);
-                if (sc) {
-                    touched = true;
-                    neg[k] = p - sc;
-#pragma unroll
-                    for (int j = k + 1; j < (int)kGeBatch; ++j)
-                        if ((uint32_t)j < nb)
-                            e[j] = mod_u64((uint64_t)e[j] + (uint64_t)neg[k] * s_x[k][j], p, pinv);
-                }
-            }
+        for (uint32_t k = 0; k < nb; ++k) {
+            const uint32_t ek = __shfl_sync(0xffffffffu, e, k);
+            if (s_pc[k] >= c || ek == 0) continue;           /* pivot columns ascend within a batch; uniform */
+            const uint32_t ng = p - mulmod(ek, s_pi[k], p, pinv);
+            touched = true;
+            if (lane == k) neg = ng;
+            if (lane > k && lane < nb) e = mod_u64((uint64_t)e + (uint64_t)ng * s_x[k][lane], p, pinv);
         }
+        /* the lanes run different numbers of row iterations below: no warp collectives in that loop,
+         * the multipliers go through shared memory (the shuffles above re-converge the warp before
+         * the next column overwrites them) */
+        uint32_t *my_neg = s_neg[tid >> 5];
+        my_neg[lane] = neg;
+        __syncwarp();
         int any = 0;
         for (uint32_t r4 = lane * 4; r4 < nrows4; r4 += 128) {
             uint4 v = *reinterpret_cast<const uint4 *>(g + r4);
             if (touched) {
                 Acc a[4] = {{v.x, 0u, 0u}, {v.y, 0u, 0u}, {v.z, 0u, 0u}, {v.w, 0u, 0u}};
-#pragma unroll
-                for (int k = 0; k < (int)kGeBatch; ++k) {
-                    if (neg[k]) {                            /* uniform over the warp */
+                for (uint32_t k = 0; k < nb; ++k) {
+                    const uint32_t nk = my_neg[k];
+                    if (nk) {
                         const uint4 f = *reinterpret_cast<const uint4 *>(s_piv + (size_t)k * nrows4 + r4);
-                        mac<true>(a[0], f.x, neg[k]); mac<true>(a[1], f.y, neg[k]);
-                        mac<true>(a[2], f.z, neg[k]); mac<true>(a[3], f.w, neg[k]);
+                        mac<true>(a[0], f.x, nk); mac<true>(a[1], f.y, nk);
+                        mac<true>(a[2], f.z, nk); mac<true>(a[3], f.w, nk);
                     }
                 }
                 v.x = fold_acc<true>(a[0], 0u, p, pinv, two64); v.y = fold_acc<true>(a[1], 0u, p, pinv, two64);

@@ -315,6 +315,38 @@ def test_gpu_elimination_fallbacks(monkeypatch, mode):
         be.close()
 
 
+def test_gpu_compress_and_verify_paths(monkeypatch):
+    """Tall trailing blocks are eliminated on random row combinations and the result is verified exactly
+    (k_ge_compress / k_ge_verify).  With a small first attempt ($F4LA_B200_COMPRESS_ROWS=64) small matrices
+    reach every branch: accepted, escalated (rank too close to the number of combinations), rejected
+    verification (forced) and "no attempt fits" -- always the reference's rows."""
+    from msolve_b200.backend import Backend
+    monkeypatch.setenv("F4LA_B200_COMPRESS_ROWS", "64")
+    rng = np.random.default_rng(4242)
+    cases = [(P31, np.uint32, 120, 700, 40, 1), (P31, np.uint32, 120, 700, 100, 1 | 4), (P16, np.uint16, 90, 700, 400, 4),
+             (P8, np.uint8, 50, 300, 30, 1), (P31, np.uint32, 0, 600, 45, 1)]
+    mats = [(random_matrix(rng, p, nru, nrl, ncr, 0.1, dt), want) for p, dt, nru, nrl, ncr, want in cases]
+    be = Backend(0)
+    try:
+        for m, want in mats:
+            out, st = be.reduce(m)
+            ref, _, _ = oracle.reduce(m)
+            assert out.same_rows(ref)
+            assert st["echelon_path"] == want, (m.nru, m.nrl, m.ncr, st["echelon_path"], st["rank"])
+    finally:
+        be.close()
+    monkeypatch.setenv("F4LA_B200_COMPRESS_FAULT", "1")
+    be = Backend(0)
+    try:
+        for m, want in mats[:2]:
+            out, st = be.reduce(m)
+            ref, _, _ = oracle.reduce(m)
+            assert out.same_rows(ref)
+            assert st["echelon_path"] & 2 and not st["echelon_path"] & 1
+    finally:
+        be.close()
+
+
 def test_gpu_more_edge_cases(backend):
     """p = 2, empty lower rows, duplicate lower rows, a lower-row count beyond the shared-memory
     limit of the batched elimination (column-at-a-time fallback), resident-matrix API."""
@@ -420,6 +452,19 @@ def test_gpu_pivot_by_lead_random_independent_rows(backend):
         ref, _, _ = oracle.reduce(m)
         again, _, _, _ = rh.reference_la(m, laopt=2, threads=1)
         assert out.nrows == len(low) and out.same_rows(ref) and out.same_rows(again)
+    # every column is a lead (no non-pivot column at all): each row reduces to its lead term
+    p, k = P31, 12
+    dense = np.triu(rng.integers(1, p, size=(k, k)), 1) + np.eye(k, dtype=np.int64)
+    piv, low = [11, 9, 7, 3, 2, 0], [10, 8, 6, 5, 4, 1]      # the reference's order: a row only contains leads of earlier rows
+    rows = [np.nonzero(dense[i])[0] for i in piv + low]
+    cfs = [dense[i][np.nonzero(dense[i])[0]] for i in piv + low]
+    row_ptr = np.concatenate([[0], np.cumsum([len(x) for x in rows])])
+    m = FlatMatrix(p, len(piv), len(low), 0, k, row_ptr, np.concatenate(rows), np.arange(k), row_ptr.copy(),
+                   np.concatenate(cfs).astype(np.uint32), flags=FLAG_PIVOT_BY_LEAD)
+    out, _ = backend.reduce(m)
+    ref, _, _ = oracle.reduce(m)
+    assert out.same_rows(ref)
+    assert out.cols.tolist() == low and out.cf.tolist() == [1] * len(low)
 
 
 def low_rank_matrix(rng, p, nru, nrl, ncr, rank, dt):
