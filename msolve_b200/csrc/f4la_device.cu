@@ -270,7 +270,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
                 k_ge_discover_cached<<<1, kDiscoverThreads, disc_smem, s>>>(
                     Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
                     as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
-                    as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv);
+                    as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
                 k_ge_batch_update_cached<<<upd_grid, kUpdate2Threads, upd_smem, s>>>(
                     Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
                     as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),

@@ -1098,17 +1098,24 @@ constexpr int kUpdate2Threads = 1024;
 constexpr uint32_t kGeBatchCached = 32;      /* most pivots per batch (when nrows is small enough for shared memory) */
 constexpr uint32_t kGeMissLimit = 4;         /* consecutive empty visited columns that end a batch */
 
-/* dynamic smem: [nrows4] column | [nb][nrows4] pivot columns of the batch | [nrows4] used bytes */
+/* dynamic smem: [nrows4] column | [nb][nrows4] pivot columns of the batch (own pivot-row entry zeroed) |
+ * [nrows4] used bytes.  Per visited column the serial chain is: next flagged column (flags cached in a
+ * shared-memory window), column load, the multipliers of the batch's earlier pivots by one warp (the
+ * same lane-distributed recurrence as in the update pass), ONE fused pass applying them, pivot search. */
+constexpr uint32_t kFlagWindow = 4096;
+
 __global__ void __launch_bounds__(kDiscoverThreads)
 k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t ncr, uint32_t nb,
                      const uint8_t *colflag, uint8_t *used, uint8_t *ispiv, GEState *st,
-                     uint32_t *pivcol, uint32_t *pivrow, uint32_t *pivinv, uint32_t p, uint64_t pinv)
+                     uint32_t *pivcol, uint32_t *pivrow, uint32_t *pivinv, uint32_t p, uint64_t pinv, uint32_t two64)
 {
     extern __shared__ __align__(16) uint32_t s_col[];
     uint32_t *s_piv = s_col + nrows4;
     uint8_t *s_used = reinterpret_cast<uint8_t *>(s_piv + (size_t)nb * nrows4);
-    __shared__ uint32_t s_min, s_prow[kGeBatchCached], s_pinv[kGeBatchCached];
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_min, s_prow[kGeBatchCached], s_pinv[kGeBatchCached], s_neg[kGeBatchCached];
+    __shared__ uint32_t s_x[kGeBatchCached][kGeBatchCached + 1];      /* x[k][j] = piv_k[row of pivot j], k < j */
+    __shared__ uint8_t s_flag[kFlagWindow];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (st->done) {
         if (tid == 0) st->cur_col = st->rank;
         return;
@@ -1116,43 +1123,53 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
     const uint32_t k0 = st->rank;
     uint32_t c = st->next_col;
     for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_used[r] = used[r];
-    __syncthreads();
-    uint32_t np = 0, misses = 0;
+    uint32_t np = 0, misses = 0, win0 = c, win1 = c;
     bool exhausted = false;
     while (np < nb && misses < kGeMissLimit) {
-        if (tid == 0) s_min = 0xffffffffu;
-        __syncthreads();
-        for (uint32_t base = c; base < ncr; base += kDiscoverThreads) {
-            const uint32_t k = base + tid;
-            if (k < ncr && colflag[k]) atomicMin(&s_min, k);
+        /* next flagged column at or after c */
+        for (;;) {
+            if (c >= ncr) break;
+            if (c >= win1) {
+                win0 = c; win1 = min(ncr, c + kFlagWindow);
+                __syncthreads();
+                for (uint32_t i = tid; i < win1 - win0; i += kDiscoverThreads) s_flag[i] = colflag[win0 + i];
+            }
+            if (tid == 0) s_min = 0xffffffffu;
             __syncthreads();
-            if (s_min != 0xffffffffu) break;
+            for (uint32_t k = c + tid; k < win1; k += kDiscoverThreads)
+                if (s_flag[k - win0]) { atomicMin(&s_min, k); break; }
             __syncthreads();
+            const uint32_t found = s_min;
+            __syncthreads();
+            if (found != 0xffffffffu) { c = found; break; }
+            c = win1;
         }
-        __syncthreads();
-        c = s_min;
-        __syncthreads();
-        if (c == 0xffffffffu) { exhausted = true; break; }
+        if (c >= ncr) { exhausted = true; break; }
         uint32_t *g = D + (size_t)c * ld;
         for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_col[r] = __ldcg(&g[r]);
         __syncthreads();
-        for (uint32_t k = 0; k < np; ++k) {             /* pivots of this batch, all left of c */
-            const uint32_t piv = s_prow[k];
-            const uint32_t sc = mulmod(s_col[piv], s_pinv[k], p, pinv);
-            __syncthreads();
-            if (sc != 0) {
-                const uint32_t *fcol = s_piv + (size_t)k * nrows4;
-                const uint32_t w = shoup_pre(sc, p);
-                for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
-                    const uint32_t f = fcol[r];
-                    if (f && r != piv) {
-                        const uint32_t t = shoup_mul(f, sc, w, p);
-                        const uint32_t v = s_col[r];
-                        s_col[r] = v >= t ? v - t : v + p - t;
-                    }
+        if (np) {
+            if (tid < 32) {
+                uint32_t e = lane < np ? s_col[s_prow[lane]] : 0u, neg = 0;
+                for (uint32_t k = 0; k < np; ++k) {
+                    const uint32_t ek = __shfl_sync(0xffffffffu, e, k);
+                    if (ek == 0) continue;
+                    const uint32_t ng = p - mulmod(ek, s_pinv[k], p, pinv);
+                    if (lane == k) neg = ng;
+                    if (lane > k && lane < np) e = mod_u64((uint64_t)e + (uint64_t)ng * s_x[k][lane], p, pinv);
                 }
-                __syncthreads();
+                s_neg[lane] = neg;
             }
+            __syncthreads();
+            for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
+                Acc a = {s_col[r], 0u, 0u};
+                for (uint32_t k = 0; k < np; ++k) {
+                    const uint32_t nk = s_neg[k];
+                    if (nk) mac<true>(a, s_piv[(size_t)k * nrows4 + r], nk);
+                }
+                s_col[r] = fold_acc<true>(a, 0u, p, pinv, two64);
+            }
+            __syncthreads();
         }
         if (tid == 0) s_min = 0xffffffffu;
         __syncthreads();
@@ -1165,9 +1182,10 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
             for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
                 const uint32_t v = s_col[r];
                 g[r] = v;
-                keep[r] = v;
+                keep[r] = r == piv ? 0u : v;
             }
-            if (tid == 0) {
+            if (tid < np) s_x[tid][np] = s_piv[(size_t)tid * nrows4 + piv];
+            if (tid == 32) {                        /* a warp with no share in the s_x update above */
                 const uint32_t inv = modinv(s_col[piv], p);
                 pivcol[k0 + np] = c; pivrow[k0 + np] = piv; pivinv[k0 + np] = inv;
                 s_prow[np] = piv; s_pinv[np] = inv;
