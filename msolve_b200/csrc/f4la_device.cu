@@ -63,6 +63,8 @@ struct f4la_ctx {
     uint64_t      d2_ld = 0;
     uint64_t      compress_attempts = 0, compress_rejected = 0, compress_escalated = 0;
     uint32_t      compress_rows = 768;  /* F4LA_B200_COMPRESS_ROWS: combinations of the first attempt (x4 per escalation) */
+    uint32_t      ge_batch = 8, ge_miss_limit = 4;   /* F4LA_B200_GE_BATCH (<= 32), F4LA_B200_GE_MISSES: pivots per batch, empty visits that end one */
+    int           debug = 0;            /* F4LA_B200_DEBUG=1: statistics on stderr */
     int           compress_fault = 0;   /* F4LA_B200_COMPRESS_FAULT=1 (tests): treat every verification as failed */
     size_t        batch_smem_optin = 0;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
@@ -250,7 +252,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
     uint32_t nb_fit = 0;
     if ((size_t)nrows4 * 5 + 64 <= smem_cap)
         nb_fit = (uint32_t)((smem_cap - 64 - nrows4) / ((size_t)nrows4 * 4)) - 1;
-    if (nb_fit > kGeBatch) nb_fit = kGeBatch;
+    if (nb_fit > ctx->ge_batch) nb_fit = ctx->ge_batch;
     if (nb_fit >= 2 && ctx->ge_mode == 0) {
         /* batched, pivot columns of the batch cached in shared memory by both passes */
         const size_t disc_smem = ((size_t)nb_fit + 1) * nrows4 * 4 + nrows4, upd_smem = (size_t)nb_fit * nrows4 * 4 + nrows4;
@@ -268,7 +270,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             const int group = 4;
             for (int k = 0; k < group; ++k) {
                 k_ge_discover_cached<<<1, kDiscoverThreads, disc_smem, s>>>(
-                    Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
+                    Dm, ld, nrl, nrows4, ncr, nb_fit, ctx->ge_miss_limit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
                     as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
                     as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
                 k_ge_batch_update_cached<<<upd_grid, kUpdate2Threads, upd_smem, s>>>(
@@ -339,6 +341,9 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
     }
     }
+    if (ctx->debug)
+        fprintf(stderr, "[f4la debug] gauss-jordan %u x %u: rank %u, %u batches, %u columns visited\n", nrl, ncr,
+                h_state->rank, h_state->batches, h_state->visits);
     *rank_out = h_state->rank;
     return F4LA_OK;
 }
@@ -941,6 +946,12 @@ f4la_ctx *f4la_b200_create(int device)
     if (cr && atoi(cr) >= 16) ctx->compress_rows = (uint32_t)atoi(cr) / 8 * 8;
     const char *cf = getenv("F4LA_B200_COMPRESS_FAULT");
     ctx->compress_fault = cf && atoi(cf) != 0;
+    const char *gb = getenv("F4LA_B200_GE_BATCH");
+    if (gb && atoi(gb) >= 2 && atoi(gb) <= (int)kGeBatchCached) ctx->ge_batch = (uint32_t)atoi(gb);
+    const char *gm = getenv("F4LA_B200_GE_MISSES");
+    if (gm && atoi(gm) >= 1) ctx->ge_miss_limit = (uint32_t)atoi(gm);
+    const char *dbg = getenv("F4LA_B200_DEBUG");
+    ctx->debug = dbg && atoi(dbg) != 0;
     const char *bk = getenv("F4LA_B200_BULK");
     ctx->bulk = bk && atoi(bk) != 0;
     const char *tm = getenv("F4LA_B200_TMAX");

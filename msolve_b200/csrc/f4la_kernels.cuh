@@ -457,6 +457,14 @@ constexpr uint32_t kFlagAlwaysNZ = 0xffffffffu;
 constexpr uint32_t kSpinLimit  = 1u << 24;      /* polls before the watchdog gives up (seconds) */
 constexpr uint32_t kErrWatchdog = 16u;
 
+/* compile-time tuning knobs of k_pull_flow (A/B builds: tools/build_variants.sh) */
+#ifndef F4LA_FLOW_OCC
+#define F4LA_FLOW_OCC 4      /* resident CTAs per SM for T <= 2 (register budget 64) */
+#endif
+#ifndef F4LA_FLOW_U
+#define F4LA_FLOW_U 4        /* entries (source vectors) in flight per warp for T <= 2 */
+#endif
+
 struct FlowArgs {
     const uint32_t *col_ptr;
     const uint2    *ent;
@@ -510,7 +518,7 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                                                 uint32_t b0, uint32_t b1,
                                                 uint32_t lane, Acc (&acc)[T][4])
 {
-    constexpr int U = (T <= 2) ? 4 : 2;
+    constexpr int U = (T <= 2) ? F4LA_FLOW_U : 2;
     const uint32_t Rc = A.Rc;
     for (uint32_t b = b0; b < b1; b += 32) {
         const uint32_t n = min(32u, b1 - b);
@@ -689,7 +697,7 @@ __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const ui
 }
 
 template <int T, bool WIDE, bool BULK>
-__global__ void __launch_bounds__(kSolveThreads, BULK ? 2 : ((T <= 2) ? 4 : 2))
+__global__ void __launch_bounds__(kSolveThreads, BULK ? 2 : ((T <= 2) ? F4LA_FLOW_OCC : 2))
 k_pull_flow(const FlowArgs A)
 {
     __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];
@@ -834,6 +842,8 @@ struct GEState {
     uint32_t cur_row;
     uint32_t cur_inv;
     uint32_t active;     /* 1 when cur_* describe a pivot to be eliminated   */
+    uint32_t visits;     /* columns loaded by the discovery (statistics)     */
+    uint32_t batches;    /* non-empty batches (statistics)                   */
     uint32_t pad;
 };
 
@@ -1096,7 +1106,7 @@ k_ge_batch_update(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint32_
  *    v + sum_k (p - s_k) * piv_k[r] in one 96-bit accumulation and one reduction. */
 constexpr int kUpdate2Threads = 1024;
 constexpr uint32_t kGeBatchCached = 32;      /* most pivots per batch (when nrows is small enough for shared memory) */
-constexpr uint32_t kGeMissLimit = 4;         /* consecutive empty visited columns that end a batch */
+constexpr uint32_t kGeMissLimit = 32;        /* consecutive empty visited columns that end a batch (a visit costs a few us, a batch a full update pass) */
 
 /* dynamic smem: [nrows4] column | [nb][nrows4] pivot columns of the batch (own pivot-row entry zeroed) |
  * [nrows4] used bytes.  Per visited column the serial chain is: next flagged column (flags cached in a
@@ -1105,7 +1115,7 @@ constexpr uint32_t kGeMissLimit = 4;         /* consecutive empty visited column
 constexpr uint32_t kFlagWindow = 4096;
 
 __global__ void __launch_bounds__(kDiscoverThreads)
-k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t ncr, uint32_t nb,
+k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, uint32_t ncr, uint32_t nb, uint32_t miss_limit,
                      const uint8_t *colflag, uint8_t *used, uint8_t *ispiv, GEState *st,
                      uint32_t *pivcol, uint32_t *pivrow, uint32_t *pivinv, uint32_t p, uint64_t pinv, uint32_t two64)
 {
@@ -1123,9 +1133,9 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
     const uint32_t k0 = st->rank;
     uint32_t c = st->next_col;
     for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_used[r] = used[r];
-    uint32_t np = 0, misses = 0, win0 = c, win1 = c;
+    uint32_t np = 0, misses = 0, win0 = c, win1 = c, visits = 0;
     bool exhausted = false;
-    while (np < nb && misses < kGeMissLimit) {
+    while (np < nb && misses < miss_limit) {
         /* next flagged column at or after c */
         for (;;) {
             if (c >= ncr) break;
@@ -1145,6 +1155,7 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
             c = win1;
         }
         if (c >= ncr) { exhausted = true; break; }
+        ++visits;
         uint32_t *g = D + (size_t)c * ld;
         for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) s_col[r] = __ldcg(&g[r]);
         __syncthreads();
@@ -1204,6 +1215,8 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
         st->rank = k0 + np;
         st->next_col = exhausted ? ncr : c;
         if (exhausted) st->done = 1;
+        st->visits += visits;
+        st->batches += np != 0;
     }
 }
 
