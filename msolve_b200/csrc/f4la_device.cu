@@ -606,6 +606,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     if (G < 1) G = 1;
     if (G > nchunks) G = nchunks;
     ld = (uint64_t)nchunks * Rc;
+    if ((uint64_t)nc * Rc >= (1ull << 32))
+        return fail(ctx, F4LA_ERR_ARG, "matrix too wide: %u columns x %u rows per chunk", nc, Rc);
     OK(ensure(ctx, ctx->V, (size_t)G * nc * Rc * 4));
     OK(ensure(ctx, ctx->D, (size_t)ncr * ld * 4));
     OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));

@@ -416,24 +416,24 @@ __global__ void k_scatter_combos(const uint64_t *__restrict__ row_ptr, const uin
  * (tools/ubench/imad_wide.cu).  a2 counts carries: good for 2^32 products, more than a column
  * can hold (nnz < 2^32), so no intermediate folds are needed.
  * !WIDE (p < 2^16): products < 2^32, a plain 64-bit sum (one IMAD.WIDE) holds 2^32 of them. */
-struct Acc { uint32_t a0, a1, a2; };
+struct Acc { uint64_t lo; uint32_t a2; };     /* lo stays ONE 64-bit register: an aligned pair, accumulated in place */
 
 template <bool WIDE>
 __device__ __forceinline__ void mac(Acc &a, uint32_t v, uint32_t c)
 {
     if (WIDE)
-        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
-            : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2) : "r"(v), "r"(c));
+        asm("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmad.lo.cc.u32 l, %2, %3, l;\n\tmadc.hi.cc.u32 h, %2, %3, h;\n\t"
+            "addc.u32 %1, %1, 0;\n\tmov.b64 %0, {l, h};\n\t}"
+            : "+l"(a.lo), "+r"(a.a2) : "r"(v), "r"(c));
     else
-        asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
-            : "+r"(a.a0), "+r"(a.a1) : "r"(v), "r"(c));
+        a.lo += (uint64_t)v * c;
 }
 
 /* canonical residue of the accumulator plus extra (< 2^32); two64 = 2^64 mod p */
 template <bool WIDE>
 __device__ __forceinline__ uint32_t fold_acc(const Acc &a, uint32_t extra, uint32_t p, uint64_t pinv, uint32_t two64)
 {
-    uint64_t x = (uint64_t)mod_u64(((uint64_t)a.a1 << 32) | a.a0, p, pinv) + extra;
+    uint64_t x = (uint64_t)mod_u64(a.lo, p, pinv) + extra;
     if (WIDE) x += mod_u64((uint64_t)a.a2 * two64, p, pinv);
     return mod_u64(x, p, pinv);
 }
@@ -460,6 +460,9 @@ constexpr uint32_t kErrWatchdog = 16u;
 /* compile-time tuning knobs of k_pull_flow (A/B builds: tools/build_variants.sh) */
 #ifndef F4LA_FLOW_OCC
 #define F4LA_FLOW_OCC 4      /* resident CTAs per SM for T <= 2 (register budget 64) */
+#endif
+#ifndef F4LA_FLOW_OFF32
+#define F4LA_FLOW_OFF32 1
 #endif
 #ifndef F4LA_FLOW_U
 #define F4LA_FLOW_U 4        /* entries (source vectors) in flight per warp for T <= 2 */
@@ -519,7 +522,7 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                                                 uint32_t lane, Acc (&acc)[T][4])
 {
     constexpr int U = (T <= 2) ? F4LA_FLOW_U : 2;
-    const uint32_t Rc = A.Rc;
+    constexpr uint32_t Rc = T * kRowsPerT;         /* == A.Rc; a constant turns the address products into shifts */
     for (uint32_t b = b0; b < b1; b += 32) {
         const uint32_t n = min(32u, b1 - b);
         uint2 en = make_uint2(0, 0);
@@ -562,7 +565,13 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+#if F4LA_FLOW_OFF32
+                /* 32-bit element offset (nc * Rc < 2^32, checked by the host): shifts on the uniform / ALU pipes instead of
+                 * a 64-bit IMAD.WIDE on the multiplier pipe */
+                const uint4 *sp = reinterpret_cast<const uint4 *>(Vc + (uint32_t)(src[u] * Rc)) + lane;
+#else
                 const uint4 *sp = reinterpret_cast<const uint4 *>(Vc + (size_t)src[u] * Rc) + lane;
+#endif
 #pragma unroll
                 for (int t = 0; t < T; ++t) v[u][t] = __ldcg(sp + t * 32);
             }
@@ -627,7 +636,7 @@ __device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const ui
                                                      Acc (&acc)[T][4], BulkPipe &pp)
 {
     constexpr uint32_t kBytes = T * kRowsPerT * 4;
-    const uint32_t Rc = A.Rc;
+    constexpr uint32_t Rc = T * kRowsPerT;         /* == A.Rc; a constant turns the address products into shifts */
     for (uint32_t b = b0; b < b1; b += 32) {
         const uint32_t n = min(32u, b1 - b);
         uint2 en = make_uint2(0, 0);
@@ -736,7 +745,7 @@ k_pull_flow(const FlowArgs A)
 #pragma unroll
         for (int t = 0; t < T; ++t)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[t][k] = Acc{0u, 0u, 0u};
+            for (int k = 0; k < 4; ++k) acc[t][k] = Acc{0ull, 0u};
 
         if (!is_long) {
             if (warp < cnt) {
@@ -1173,7 +1182,7 @@ k_ge_discover_cached(uint32_t *D, uint64_t ld, uint32_t nrows, uint32_t nrows4, 
             }
             __syncthreads();
             for (uint32_t r = tid; r < nrows; r += kDiscoverThreads) {
-                Acc a = {s_col[r], 0u, 0u};
+                Acc a = {(uint64_t)s_col[r], 0u};
                 for (uint32_t k = 0; k < np; ++k) {
                     const uint32_t nk = s_neg[k];
                     if (nk) mac<true>(a, s_piv[(size_t)k * nrows4 + r], nk);
@@ -1282,7 +1291,7 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
         for (uint32_t r4 = lane * 4; r4 < nrows4; r4 += 128) {
             uint4 v = *reinterpret_cast<const uint4 *>(g + r4);
             if (touched) {
-                Acc a[4] = {{v.x, 0u, 0u}, {v.y, 0u, 0u}, {v.z, 0u, 0u}, {v.w, 0u, 0u}};
+                Acc a[4] = {{(uint64_t)v.x, 0u}, {(uint64_t)v.y, 0u}, {(uint64_t)v.z, 0u}, {(uint64_t)v.w, 0u}};
                 for (uint32_t k = 0; k < nb; ++k) {
                     const uint32_t nk = my_neg[k];
                     if (nk) {
@@ -1341,7 +1350,7 @@ k_ge_compress(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, uint3
         return;
     }
     for (uint32_t q = threadIdx.x; q < kc; q += blockDim.x) {
-        Acc a = {0u, 0u, 0u};
+        Acc a = {0ull, 0u};
         const uint32_t e1 = slot_ptr[q + 1];
         for (uint32_t e = slot_ptr[q]; e < e1; ++e) mac<true>(a, s_col[slot_row[e]], slot_rho[e]);
         o[q] = fold_acc<true>(a, 0u, p, pinv, two64);
@@ -1364,7 +1373,7 @@ k_ge_verify(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows_pad, uin
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = Acc{0u, 0u, 0u};
+        for (int b = 0; b < 4; ++b) acc[a][b] = Acc{0ull, 0u};
     for (uint32_t t0 = 0; t0 < rank; t0 += kVerK) {
         /* stage: 16 x 64 of each operand, 4 words per thread */
         {
