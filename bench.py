@@ -198,7 +198,7 @@ def run_gpu(args, rank, world):
 
     def pass_resident():
         agg = {"ms_prep": 0.0, "ms_reduce": 0.0, "ms_echelon": 0.0, "ms_d2h": 0.0, "kernel_launches": 0, "bytes_d2h": 0,
-               "ms_hot_kernel": 0.0, "hot_kernel_launches": 0}
+               "ms_hot_kernel": 0.0, "hot_kernel_launches": 0, "units": 0}
         for rm in resident:
             _, st = be.reduce_resident(rm, want_result=False)
             for k in agg:
@@ -301,6 +301,7 @@ def run_gpu(args, rank, world):
     ms_reduce = sum(a["ms_reduce"] for a in aggs_v) / steps
     ms_hot = sum(a["ms_hot_kernel"] for a in aggs_v) / steps
     n_hot = sum(a["hot_kernel_launches"] for a in aggs_v) / steps
+    dense_macs = sum(a["units"] for a in aggs_v) / steps
     peak, peak_src = measured_peaks()
     bytes_per_unit = 8
     # algorithmic bytes of all launches of the hot kernel in a step / their summed duration
@@ -331,9 +332,18 @@ def run_gpu(args, rank, world):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_pull_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch on the largest matrix
-                     # (profiles/r01_ncu_full_k_pull_flow_v3_raw.csv); its algorithmic bytes are 2.14e10
-                     "traffic": 2.95e8,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch: first group (15 of 20
+                     # row chunks) of the largest matrix, profiles/r01_ncu_full_k_pull_flow_v5_raw.csv; the
+                     # algorithmic bytes of that launch are 5.34e10 units x 8 B x 15/20 = 3.2e11
+                     "traffic": 2.36e10,
+                     # what actually bounds the kernel: the multiplier pipe.  One 31 x 31 -> 96-bit multiply-add
+                     # is one IMAD.WIDE.U32 (+ half an add-with-carry): 8.1e12/s measured on this GPU
+                     # (tools/ubench/imad_wide.cu, profiles/README.md).  "dense_macs" counts every (pull-list
+                     # entry, lower row) pair, including the all-zero source vectors the kernel skips.
+                     "pipe": {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "peak_mac_per_s": 8.1e12,
+                              "dense_macs_per_step": dense_macs,
+                              "achieved_mac_per_s": dense_macs / (ms_hot / 1e3),
+                              "frac": dense_macs / (ms_hot / 1e3) / 8.1e12},
                      "peak_source": peak_src, "bytes_per_unit": bytes_per_unit,
                      "launches_per_step": n_hot, "kernel_ms_per_step": ms_hot,
                      "algorithmic_bytes_per_launch": units * bytes_per_unit / max(n_hot, 1),

@@ -88,6 +88,9 @@ typedef struct f4la_flat_matrix {
  * their space; same unique reduced rows with overwhelming probability (p > 2^15 only, else
  * the exact path runs).  Ignored together with NORMALFORM / PIVOT_BY_LEAD / WANT_RBA. */
 #define F4LA_FLAG_PROBABILISTIC 8u
+/* f4la_b200_reduce() only: the column indices are already on the device, sent piecewise with
+ * f4la_b200_stage_cols() while the caller was still assembling them; `cols` is not read. */
+#define F4LA_FLAG_COLS_STAGED 16u
 
 /* Result: rows of the reduced row echelon form, as CSR over ALL columns
  * (column ids in 0..ncl+ncr-1, ascending inside a row).  In echelon mode the
@@ -158,6 +161,13 @@ void  f4la_b200_pinned_free(void *p);
  * (reference la_ff_32.c:2595-2770). */
 int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in,
                      f4la_flat_result *out, f4la_stats *stats);
+
+/* Overlap of the caller's assembly of `cols` (the bulk of the input, 4 B per non-zero) with the
+ * host->device copy: sends cols[first .. first+count) of a matrix with total_nnz non-zeros from a
+ * page-locked buffer, asynchronously, on the context's stream.  Call it for consecutive pieces as
+ * they become ready, then f4la_b200_reduce() with F4LA_FLAG_COLS_STAGED.  Used by the neogb
+ * adapter, which gathers the rows of a mat_t (one malloc block each) piece by piece. */
+int f4la_b200_stage_cols(f4la_ctx *ctx, const uint32_t *cols, uint64_t first, uint64_t count, uint64_t total_nnz);
 
 /* Same computation with the input already resident in HBM (bench: `value`). */
 f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in);

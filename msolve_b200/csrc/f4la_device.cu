@@ -863,7 +863,10 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
         return fail(ctx, F4LA_ERR_ARG, "field characteristic %u out of range (need 2 <= p < 2^31)", in->fc);
     if (in->cf_bytes != 1 && in->cf_bytes != 2 && in->cf_bytes != 4)
         return fail(ctx, F4LA_ERR_ARG, "cf_bytes must be 1, 2 or 4");
+    if ((in->flags & F4LA_FLAG_COLS_STAGED) && own)
+        return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_COLS_STAGED is for f4la_b200_reduce() only");
     r->dims = *in;
+    r->dims.flags &= ~F4LA_FLAG_COLS_STAGED;
     r->owned = own;
     r->nnz = n ? in->row_ptr[n] : 0;
     r->ncoef = in->ncf ? in->cf_ptr[in->ncf] : 0;
@@ -884,7 +887,8 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
     }
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(r->row_ptr, in->row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (r->nnz) CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
+    if (r->nnz && !(in->flags & F4LA_FLAG_COLS_STAGED))
+        CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
     if (n) CU(cudaMemcpyAsync(r->row_cf, in->row_cf, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(r->cf_ptr, in->cf_ptr, ((uint64_t)in->ncf + 1) * 8, cudaMemcpyHostToDevice, s));
     if (r->ncoef) CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
@@ -1022,6 +1026,17 @@ int f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m, f4la_flat_result 
     int rc = run_pipeline(ctx, m, out, stats);
     if (stats) stats->ms_total = now_ms() - t0;
     return rc;
+}
+
+int f4la_b200_stage_cols(f4la_ctx *ctx, const uint32_t *cols, uint64_t first, uint64_t count, uint64_t total_nnz)
+{
+    if (!ctx || !cols || first + count > total_nnz) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    /* same size as upload() asks for: the buffer is not reallocated between the pieces and the reduce call */
+    OK(ensure(ctx, ctx->in_cols, (total_nnz + 1) * 4));
+    if (count)
+        CU(cudaMemcpyAsync(as<uint32_t>(ctx->in_cols) + first, cols + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return F4LA_OK;
 }
 
 int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result *out, f4la_stats *stats)

@@ -151,10 +151,24 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     const int nthr = fld<int32_t>(st, L.md_nthrds) > 1 ? fld<int32_t>(st, L.md_nthrds) : 1;
     /* the bulk copy of the column indices is row-parallel (st->nthrds host
      * threads, like the reference's own row loops, e.g. convert.c:365-397) */
+    /* ... and pipelined with the host->device copy: as soon as a piece of `cols` is assembled it is
+     * sent (f4la_b200_stage_cols, asynchronous), the next piece is gathered meanwhile */
+    f4la_ctx *cx = ctx();
+    const bool staged = nnz >= (1u << 22);
+    {
+        const uint64_t piece = nnz / 8 > (1u << 21) ? nnz / 8 : (1u << 21);
+        for (uint32_t r0 = 0; r0 < n;) {
+            uint32_t r1 = r0;
+            while (r1 < n && row_ptr[r1] - row_ptr[r0] < piece) ++r1;
 #pragma omp parallel for num_threads(nthr) schedule(dynamic, 256)
-    for (uint32_t r = 0; r < n; ++r) {
-        const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
-        memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)row[L.row_length] * 4);
+            for (uint32_t r = r0; r < r1; ++r) {
+                const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+                memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)row[L.row_length] * 4);
+            }
+            if (staged && f4la_b200_stage_cols(cx, cols, row_ptr[r0], row_ptr[r1] - row_ptr[r0], nnz) != F4LA_OK)
+                die(f4la_b200_last_error(cx));
+            r0 = r1;
+        }
     }
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
@@ -184,6 +198,7 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
     fm.flags = nf_mode ? F4LA_FLAG_NORMALFORM : final_step ? F4LA_FLAG_PIVOT_BY_LEAD : F4LA_FLAG_NONE;
     if (learn) fm.flags |= F4LA_FLAG_WANT_RBA;
+    if (staged) fm.flags |= F4LA_FLAG_COLS_STAGED;
     /* -l 42 / 43 / 44: the reference's probabilistic variants (io.c:885-957); no tracer runs with
      * them (f4.c:365), the device decides whether random combinations pay off */
     const int32_t laopt = fld<int32_t>(st, L.md_laopt);
@@ -200,7 +215,6 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
      * been copied to the staging buffers, so a helper thread frees the ~10^4-10^5 input rows
      * (tens of milliseconds of free()) while the GPU works.  Not while learning a trace:
      * construct_trace() still reads the rows. */
-    f4la_ctx *cx = ctx();
     std::thread reaper;
     bool reaped = false;
     if (!learn && (uint64_t)n > 2048) {
