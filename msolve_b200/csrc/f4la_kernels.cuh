@@ -464,6 +464,9 @@ constexpr uint32_t kErrWatchdog = 16u;
 #ifndef F4LA_FLOW_OFF32
 #define F4LA_FLOW_OFF32 1
 #endif
+#ifndef F4LA_FLOW_LOAD
+#define F4LA_FLOW_LOAD __ldcg   /* source vectors: L2 only (A/B: ld_ca_u4 keeps them in L1 as well) */
+#endif
 #ifndef F4LA_FLOW_U
 #define F4LA_FLOW_U 4        /* entries (source vectors) in flight per warp for T <= 2 */
 #endif
@@ -504,6 +507,14 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *ptr)
 __device__ __forceinline__ void st_release(uint32_t *ptr, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(ptr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_ca_u4(const uint4 *ptr)
+{
+    uint4 v;
+    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ uint4 ld_cg_u4(const uint4 *ptr)
@@ -573,7 +584,7 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                 const uint4 *sp = reinterpret_cast<const uint4 *>(Vc + (size_t)src[u] * Rc) + lane;
 #endif
 #pragma unroll
-                for (int t = 0; t < T; ++t) v[u][t] = __ldcg(sp + t * 32);
+                for (int t = 0; t < T; ++t) v[u][t] = F4LA_FLOW_LOAD(sp + t * 32);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
