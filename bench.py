@@ -344,12 +344,11 @@ def run_gpu(args, rank, world):
                               "dense_macs_per_step": dense_macs,
                               "achieved_mac_per_s": dense_macs / (ms_hot / 1e3),
                               "frac": dense_macs / (ms_hot / 1e3) / 8.1e12},
-                     # second limit, from the same ncu capture: every multiply-add needs its own 4-byte vector
-                     # element from L2 (the pivots' vectors are shared by the whole grid, so L2 is their home):
-                     # 7.18e9 sectors x 32 B in 16.1 ms = 14 TB/s, at the L2->SM ceiling of the chip
-                     # (~6 300 B/clk, /opt/skills/guides/B300_MICROARCH.md) -- the multiplier pipe cannot be
-                     # filled beyond ~55 % through this memory path
-                     "l2": {"ncu_bytes_per_launch": 2.30e11, "ncu_TB_per_s": 14.3, "ceiling_TB_per_s": 12.4,
+                     # L2 -> SM traffic of the same capture (every multiply-add needs its own 4-byte vector element):
+                     # 7.18e9 sectors x 32 B in 16.1 ms = 14 TB/s, about the chip's L2 ceiling -- but cutting that
+                     # traffic (column groups sharing vector loads) did not help: the kernel is bound by
+                     # instruction issue on the multiplier-pipe path
+                     "l2": {"ncu_bytes_per_launch": 2.30e11, "ncu_TB_per_s": 14.3,
                             "source": "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv (lts__t_sectors_srcunit_tex_op_read)"},
                      "peak_source": peak_src, "bytes_per_unit": bytes_per_unit,
                      "launches_per_step": n_hot, "kernel_ms_per_step": ms_hot,
