@@ -45,6 +45,10 @@ constexpr int kMaxFlowEvents = 512;
 struct f4la_ctx {
     int           device = 0;
     cudaStream_t  stream = nullptr;
+    cudaStream_t  copy_stream = nullptr;  /* f4la_b200_reduce(): the lower rows travel while the pull lists are built */
+    cudaEvent_t   ev_copy = nullptr;
+    bool          copy_pending = false;
+    int           split_h2d = 1;          /* F4LA_B200_SPLIT_H2D=0: one copy on the compute stream */
     cudaEvent_t   ev[8] = {};
     cudaEvent_t   flow_ev[kMaxFlowEvents] = {};   /* around every launch of the hot kernel */
     int           sm_count = 0;
@@ -655,6 +659,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                                                                as<uint32_t>(ctx->flowflags));
             ctx->launches++;
         }
+        if (ctx->copy_pending) {                  /* the lower rows of a split host->device copy */
+            CU(cudaStreamWaitEvent(s, ctx->ev_copy, 0));
+            ctx->copy_pending = false;
+        }
         const uint32_t rows_here = ((c0 + g) * Rc <= nrl ? (c0 + g) * Rc : nrl) - c0 * Rc;
         if (by_lead)
             k_scatter_units<<<(rows_here + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, nc, c0, g, Rc, colmap,
@@ -886,12 +894,37 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
         r->row_cf = as<uint32_t>(ctx->in_row_cf); r->cf_ptr = as<uint64_t>(ctx->in_cf_ptr); r->cf = ctx->in_cf.p;
     }
     cudaStream_t s = ctx->stream;
+    if (ctx->copy_pending) { CU(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
     CU(cudaMemcpyAsync(r->row_ptr, in->row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (r->nnz && !(in->flags & F4LA_FLAG_COLS_STAGED))
-        CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
     if (n) CU(cudaMemcpyAsync(r->row_cf, in->row_cf, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(r->cf_ptr, in->cf_ptr, ((uint64_t)in->ncf + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (r->ncoef) CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
+    /* The pull lists and levels (steps 1-2 of the pipeline) read the pivot rows only.  From host buffers the
+     * lower rows' column indices and coefficient arrays therefore travel on a second stream while those
+     * steps run; the pipeline waits for them just before it scatters the lower rows. */
+    const bool split = !own && ctx->split_h2d && in->nrl && in->nru && r->nnz >= (1u << 20) &&
+                       !(in->flags & (F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_COLS_STAGED));
+    if (split) {
+        const uint64_t nz_up = in->row_ptr[in->nru];
+        uint32_t k_up = 0;                                   /* coefficient arrays 0 .. k_up-1 serve the pivot rows */
+        for (uint32_t i = 0; i < in->nru; ++i) k_up = in->row_cf[i] >= k_up ? in->row_cf[i] + 1 : k_up;
+        if (k_up > in->ncf) return fail(ctx, F4LA_ERR_ARG, "row_cf out of range");
+        const uint64_t cf_up = in->cf_ptr[k_up];
+        const size_t w = in->cf_bytes;
+        if (nz_up) CU(cudaMemcpyAsync(r->cols, in->cols, nz_up * 4, cudaMemcpyHostToDevice, s));
+        if (cf_up) CU(cudaMemcpyAsync(r->cf, in->cf, cf_up * w, cudaMemcpyHostToDevice, s));
+        cudaStream_t cs = ctx->copy_stream;
+        if (r->nnz > nz_up)
+            CU(cudaMemcpyAsync(r->cols + nz_up, in->cols + nz_up, (r->nnz - nz_up) * 4, cudaMemcpyHostToDevice, cs));
+        if (r->ncoef > cf_up)
+            CU(cudaMemcpyAsync((char *)r->cf + cf_up * w, (const char *)in->cf + cf_up * w, (r->ncoef - cf_up) * w,
+                               cudaMemcpyHostToDevice, cs));
+        CU(cudaEventRecord(ctx->ev_copy, cs));
+        ctx->copy_pending = true;
+    } else {
+        if (r->nnz && !(in->flags & F4LA_FLAG_COLS_STAGED))
+            CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
+        if (r->ncoef) CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
+    }
     r->bytes = (n + 1) * 8 + r->nnz * 4 + n * 4 + ((uint64_t)in->ncf + 1) * 8 + r->ncoef * in->cf_bytes;
     return F4LA_OK;
 }
@@ -942,6 +975,9 @@ f4la_ctx *f4la_b200_create(int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    { const char *sp = getenv("F4LA_B200_SPLIT_H2D"); if (sp) ctx->split_h2d = atoi(sp) != 0; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
@@ -984,6 +1020,9 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     if (ctx->h_combo.p) cudaFreeHost(ctx->h_combo.p);
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->flow_ev) cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_copy);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1053,6 +1092,10 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result
     cudaEventRecord(ctx->ev[5], ctx->stream);
     if (rc == F4LA_OK) rc = run_pipeline(ctx, &r, out, stats);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_pending) {                  /* the pipeline returned before it needed the lower rows */
+        cudaStreamSynchronize(ctx->copy_stream);
+        ctx->copy_pending = false;
+    }
     if (stats) {
         float ms = 0;
         if (rc == F4LA_OK && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[5]) == cudaSuccess) stats->ms_h2d = ms;
