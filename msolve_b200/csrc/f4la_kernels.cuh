@@ -1299,8 +1299,11 @@ k_ge_batch_update_cached(uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows, 
         my_neg[lane] = neg;
         __syncwarp();
         int any = 0;
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (lane * 4 < nrows4) nxt = *reinterpret_cast<const uint4 *>(g + lane * 4);
         for (uint32_t r4 = lane * 4; r4 < nrows4; r4 += 128) {
-            uint4 v = *reinterpret_cast<const uint4 *>(g + r4);
+            uint4 v = nxt;
+            if (r4 + 128 < nrows4) nxt = *reinterpret_cast<const uint4 *>(g + r4 + 128);      /* next piece in flight */
             if (touched) {
                 Acc a[4] = {{(uint64_t)v.x, 0u}, {(uint64_t)v.y, 0u}, {(uint64_t)v.z, 0u}, {(uint64_t)v.w, 0u}};
                 for (uint32_t k = 0; k < nb; ++k) {
