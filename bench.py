@@ -368,7 +368,7 @@ def run_gpu(args, rank, world):
         "probabilistic": prob,
         "qq": qq,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -523,10 +523,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": gops, "unit": "Gop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath print there too (NCCL's version banner,
+    the reference's verbose lines), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    written to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
