@@ -76,6 +76,8 @@ def load_library() -> C.CDLL:
     L.f4la_b200_pinned_free.argtypes = [C.c_void_p]
     L.f4la_b200_reduce.restype = C.c_int
     L.f4la_b200_reduce.argtypes = [C.c_void_p, C.POINTER(CFlatMatrix), C.POINTER(CFlatResult), C.POINTER(CStats)]
+    L.f4la_b200_stage_cols.restype = C.c_int
+    L.f4la_b200_stage_cols.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
     L.f4la_b200_upload.restype = C.c_void_p
     L.f4la_b200_upload.argtypes = [C.c_void_p, C.POINTER(CFlatMatrix)]
     L.f4la_b200_reduce_resident.restype = C.c_int
@@ -138,6 +140,24 @@ class Backend:
         self._check(self.lib.f4la_b200_reduce(self.ctx, C.byref(cm), C.byref(res), C.byref(st)))
         out = FlatResult.from_c(res)
         out.attach_rba(res, m.nrl)
+        self.lib.f4la_b200_free_result(C.byref(res))
+        return out, st.as_dict()
+
+    def reduce_staged(self, pm: "PinnedMatrix", pieces: int = 4):
+        """Same as :meth:`reduce`, with the column indices sent piecewise beforehand
+        (``f4la_b200_stage_cols`` + ``F4LA_FLAG_COLS_STAGED``), the way the neogb adapter overlaps its
+        gathering of the rows with the host->device copy.  ``pm`` must be pinned."""
+        from .flat import FLAG_COLS_STAGED
+        m = pm.matrix
+        nnz = m.nnz
+        step = max(1, (nnz + pieces - 1) // pieces)
+        for first in range(0, nnz, step):
+            self._check(self.lib.f4la_b200_stage_cols(self.ctx, m.cols.ctypes.data, first, min(step, nnz - first), nnz))
+        cm, res, st = m.c_struct(), CFlatResult(), CStats()
+        cm.flags |= FLAG_COLS_STAGED
+        cm.cols = None                      # not read in this mode
+        self._check(self.lib.f4la_b200_reduce(self.ctx, C.byref(cm), C.byref(res), C.byref(st)))
+        out = FlatResult.from_c(res)
         self.lib.f4la_b200_free_result(C.byref(res))
         return out, st.as_dict()
 

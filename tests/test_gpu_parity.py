@@ -347,6 +347,55 @@ def test_gpu_compress_and_verify_paths(monkeypatch):
         be.close()
 
 
+def big_sparse_matrix(rng, p, nru, nrl, ncr, per_row):
+    """[A B; C D] with about nru * per_row non-zeros (vectorised, for matrices beyond 10^6 non-zeros)."""
+    nc = nru + ncr
+    rows, cfs = [], []
+    for i in range(nru):
+        k = min(per_row, nc - i - 1)
+        others = i + 1 + rng.choice(nc - i - 1, size=k, replace=False)
+        rows.append(np.concatenate([[i], others]))
+        cfs.append(np.concatenate([[1], rng.integers(1, p, size=k)]))
+    for r in range(nrl):
+        c = np.sort(rng.choice(nc, size=min(3 * per_row, nc), replace=False))
+        rows.append(c)
+        cfs.append(rng.integers(1, p, size=len(c)))
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    return FlatMatrix(p, nru, nrl, nru, ncr, row_ptr, np.concatenate(rows), np.arange(nru + nrl), row_ptr.copy(),
+                      np.concatenate(cfs).astype(np.uint32))
+
+
+def test_gpu_host_copy_variants_agree(monkeypatch):
+    """f4la_b200_reduce() from host buffers copies the lower rows on a second stream while the pull lists are
+    built (matrices beyond 2^20 non-zeros), or takes the column indices staged piecewise beforehand
+    (f4la_b200_stage_cols); both must give the rows of the plain single-copy path and of the resident path."""
+    from msolve_b200.backend import Backend
+    rng = np.random.default_rng(777)
+    m = big_sparse_matrix(rng, P31, 6000, 300, 400, 200)
+    assert m.nnz >= 1 << 20
+    be = Backend(0)
+    try:
+        pm = be.pin(m)
+        split, _ = be.reduce(pm.matrix)                      # default: split copy
+        staged, _ = be.reduce_staged(pm, pieces=5)
+        rm = be.upload(m)
+        resident, _ = be.reduce_resident(rm)
+        rm.release()
+        pm.free()
+    finally:
+        be.close()
+    monkeypatch.setenv("F4LA_B200_SPLIT_H2D", "0")
+    be = Backend(0)
+    try:
+        single, _ = be.reduce(m)
+    finally:
+        be.close()
+    assert single.nrows > 0
+    assert split.same_rows(single) and staged.same_rows(single) and resident.same_rows(single)
+    ref, _, _ = oracle.reduce(m)
+    assert single.same_rows(ref)
+
+
 def test_gpu_more_edge_cases(backend):
     """p = 2, empty lower rows, duplicate lower rows, a lower-row count beyond the shared-memory
     limit of the batched elimination (column-at-a-time fallback), resident-matrix API."""
