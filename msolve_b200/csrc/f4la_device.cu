@@ -68,6 +68,7 @@ struct f4la_ctx {
     uint64_t      compress_attempts = 0, compress_rejected = 0, compress_escalated = 0;
     uint32_t      compress_rows = 768;  /* F4LA_B200_COMPRESS_ROWS: combinations of the first attempt (x4 per escalation) */
     uint32_t      ge_batch = 8, ge_miss_limit = 4;   /* F4LA_B200_GE_BATCH (<= 32), F4LA_B200_GE_MISSES: pivots per batch, empty visits that end one */
+    int           zerocopy = 1;         /* F4LA_B200_ZEROCOPY=0: result rows through a device buffer + copy */
     int           debug = 0;            /* F4LA_B200_DEBUG=1: statistics on stderr */
     int           compress_fault = 0;   /* F4LA_B200_COMPRESS_FAULT=1 (tests): treat every verification as failed */
     size_t        batch_smem_optin = 0;
@@ -735,6 +736,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     const uint32_t ndense = (nf_mode || by_lead) ? nrl : rank;       /* dense rows produced on the device */
     const uint32_t nout = (nf_mode || by_lead) ? nrl : rank;
     uint64_t d2h_bytes = 0;
+    double dbg_copy_ms = 0, dbg_t1 = now_ms();
     if (nout == 0) {
         empty_result(out, d.cf_bytes);
     } else {
@@ -742,24 +744,31 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         const size_t aux_words = 2 * (size_t)rank + (by_lead ? (size_t)nc + nrl : 0) + 16;
         OK(ensure(ctx, ctx->dense_out, dense_bytes + 16));
         OK(ensure_host(ctx, ctx->h_dense, dense_bytes + aux_words * 4));
+        /* The dense result rows are written by the extraction kernel straight into the page-locked host buffer
+         * (it is mapped into the device's address space): 128-byte coalesced stores over PCIe instead of a
+         * device buffer plus a copy-engine transfer, which ran at 5-10 GB/s here after the link had idled
+         * through the compute phases.  F4LA_B200_ZEROCOPY=0 restores the copy. */
+        uint32_t *dense_dst = ctx->zerocopy ? (uint32_t *)ctx->h_dense.p : as<uint32_t>(ctx->dense_out);
         if ((nf_mode || by_lead) && ncr) {
             /* by_lead: the rows of A^-1 B are the NEGATED solve results */
             dim3 grid((ncr + 31) / 32, (nrl + 31) / 32), block(32, 8);
-            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, by_lead ? p : 0u, as<uint32_t>(ctx->dense_out));
+            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, by_lead ? p : 0u, dense_dst);
             ctx->launches++;
         } else if (rank) {
             dim3 grid((ncr + 255) / 256, rank);
             k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
-                                              as<uint32_t>(ctx->dense_out), p, pinv);
+                                              dense_dst, p, pinv);
             ctx->launches++;
         }
+        if (ctx->debug) CU(cudaEventRecord(ctx->ev[7], s));
         uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
         uint32_t *h_pivrow = h_dense + (size_t)ndense * ncr;
         uint32_t *h_pivcol = h_pivrow + rank;
         uint32_t *h_invmap = h_pivcol + rank;
         uint32_t *h_leads = h_invmap + (by_lead ? nc : 0);
-        if (dense_bytes) CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
+        if (dense_bytes && !ctx->zerocopy)
+            CU(cudaMemcpyAsync(h_dense, ctx->dense_out.p, dense_bytes, cudaMemcpyDeviceToHost, s));
         if (rank) {
             CU(cudaMemcpyAsync(h_pivrow, ctx->pivrow.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(h_pivcol, ctx->pivcol.p, (size_t)rank * 4, cudaMemcpyDeviceToHost, s));
@@ -772,7 +781,17 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
         }
         CU(cudaGetLastError());
+        if (ctx->debug) CU(cudaEventRecord(ctx->ev[6], s));
+        const double t_copy0 = now_ms();
         CU(cudaStreamSynchronize(s));
+        const double t_copy1 = now_ms();
+        if (ctx->debug) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->ev[3], ctx->ev[7]);
+            cudaEventElapsedTime(&b, ctx->ev[7], ctx->ev[6]);
+            fprintf(stderr, "[f4la debug] extract kernel %.3f ms, copies %.3f ms (%zu bytes)\n", a, b, dense_bytes);
+        }
+        dbg_copy_ms = t_copy1 - t_copy0; dbg_t1 = t_copy1;
         d2h_bytes = dense_bytes + aux_words * 4;
 
         /* which dense row answers output row i (or -1: the row is zero) */
@@ -830,6 +849,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             }
         }
     }
+    if (ctx->debug) fprintf(stderr, "[f4la debug] result: %u rows, wait for extract + D2H %.3f ms, host compaction %.3f ms\n", nout, dbg_copy_ms, now_ms() - dbg_t1);
     if (want_rba && rba_words) {
         out->rba_words = rba_words;
         out->rba = (uint32_t *)malloc((size_t)nrl * rba_words * 4);
@@ -992,6 +1012,8 @@ f4la_ctx *f4la_b200_create(int device)
     if (gb && atoi(gb) >= 2 && atoi(gb) <= (int)kGeBatchCached) ctx->ge_batch = (uint32_t)atoi(gb);
     const char *gm = getenv("F4LA_B200_GE_MISSES");
     if (gm && atoi(gm) >= 1) ctx->ge_miss_limit = (uint32_t)atoi(gm);
+    const char *zc = getenv("F4LA_B200_ZEROCOPY");
+    if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
     ctx->debug = dbg && atoi(dbg) != 0;
     const char *bk = getenv("F4LA_B200_BULK");
