@@ -104,7 +104,10 @@ typedef struct f4la_flat_result {
     uint32_t *cols;      /* [row_ptr[nrows]]                                  */
     void     *cf;        /* [row_ptr[nrows]] coefficients, cf_bytes wide      */
     uint32_t *src_row;   /* [nrows] index of an input lower row whose
-                            reduction produced this pivot (BINDEX/MULT donor) */
+                            reduction produced this pivot (BINDEX/MULT donor);
+                            0xffffffff when the pivot came out of random combinations
+                            of the lower rows (probabilistic mode, compress-and-verify:
+                            never while F4LA_FLAG_WANT_RBA / tracing is on)          */
     uint32_t *rba;       /* F4LA_FLAG_WANT_RBA: [nrl][rba_words] bit i%32 of
                             word i/32 set iff pivot i was used; else NULL     */
     uint32_t  rba_words; /* ceil(nru / 32)                                    */
@@ -119,9 +122,11 @@ typedef struct f4la_stats {
     double   ms_reduce;       /* sparse reduction by known pivots (hot kernel)*/
     double   ms_echelon;      /* trailing block echelon form                  */
     double   ms_d2h;          /* device->host copies + host materialisation   */
-    uint64_t units;           /* coefficient applications done by the hot
-                                 kernel (1 mul + 1 add each)                  */
-    uint64_t pivot_applications;
+    uint64_t units;           /* coefficient applications of the REFERENCE algorithm for this reduction by the
+                                 known pivots: sum over the pivots of (row length) x (lower rows with a non-zero
+                                 multiplier) -- what la_ff_32.c:1214-1216 counts per application, 1 mul + 1 add
+                                 each; the order-dependent new-pivot part of the reference's count is not in it */
+    uint64_t pivot_applications; /* entries of the pull lists (non-lead non-zeros of the pivot rows) */
     uint64_t bytes_h2d;
     uint64_t bytes_d2h;
     uint32_t kernel_launches; /* kernels launched by this library in the call */
@@ -132,6 +137,10 @@ typedef struct f4la_stats {
     uint32_t echelon_path;    /* trailing block: bit 0 result from compress-and-verify, bit 1 a verification
                                  failed (direct elimination used instead), bit 2 the number of combinations was
                                  escalated at least once                                                   */
+    uint64_t dense_macs;      /* multiply-adds of the transposed formulation: (pull-list entries) x (lower rows),
+                                 all-zero source vectors included (the hot kernel skips those)             */
+    uint64_t ref_applications;/* (known pivot, lower row) pairs with a non-zero multiplier: the reference's
+                                 application_nr_red for the reduction by the known pivots                 */
 } f4la_stats;
 
 typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */

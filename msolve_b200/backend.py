@@ -158,6 +158,7 @@ class Backend:
         cm.cols = None                      # not read in this mode
         self._check(self.lib.f4la_b200_reduce(self.ctx, C.byref(cm), C.byref(res), C.byref(st)))
         out = FlatResult.from_c(res)
+        out.attach_rba(res, m.nrl)
         self.lib.f4la_b200_free_result(C.byref(res))
         return out, st.as_dict()
 

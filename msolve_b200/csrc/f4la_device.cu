@@ -50,6 +50,7 @@ struct f4la_ctx {
     bool          copy_pending = false;
     int           split_h2d = 1;          /* F4LA_B200_SPLIT_H2D=0: one copy on the compute stream */
     cudaEvent_t   ev[8] = {};
+    cudaEvent_t   dbg_ev[2] = {};                /* F4LA_B200_DEBUG only */
     cudaEvent_t   flow_ev[kMaxFlowEvents] = {};   /* around every launch of the hot kernel */
     int           sm_count = 0;
     char          err[512] = {0};
@@ -76,8 +77,8 @@ struct f4la_ctx {
     DevBuf is_piv, pividx, colmap, invmap, leads, rba;
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
+    double        watchdog_ms = 20000.0; /* F4LA_B200_WATCHDOG_MS: longest wait for a source column in the dataflow kernel */
     uint64_t      seed = 0x9e3779b97f4a7c15ull;   /* random combinations of the probabilistic mode */
-    int           bulk = 0;             /* F4LA_B200_BULK=1: bulk-copy (TMA engine) staging of the source vectors */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense, h_combo;
 };
@@ -154,29 +155,19 @@ inline unsigned blocks_for_warps(uint64_t nwarps, int threads = 256)
     return (unsigned)b;
 }
 
-template <int T, bool WIDE, bool BULK>
-int flow_occupancy(size_t smem)
+template <int T, bool WIDE>
+int flow_occupancy()
 {
     int n = 0;
-    if (BULK && smem > 48 * 1024)
-        cudaFuncSetAttribute(k_pull_flow<T, WIDE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pull_flow<T, WIDE, BULK>, kSolveThreads, smem) != cudaSuccess) n = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pull_flow<T, WIDE>, kSolveThreads, 0) != cudaSuccess) n = 2;
     return n < 1 ? 1 : n;
-}
-
-size_t flow_smem(int T, bool bulk)
-{
-    return bulk ? (size_t)kWarpsPerBlock * kBulkStages * ((size_t)T * kRowsPerT * 4 + 8) : 0;
 }
 
 int flow_blocks(f4la_ctx *ctx, int T, bool wide)
 {
     int &c = ctx->flow_blocks_per_sm[wide ? 1 : 0][T];
     if (c == 0) {
-        const bool b = ctx->bulk != 0;
-        const size_t sm = flow_smem(T, b);
-#define OCC(TT) (b ? (wide ? flow_occupancy<TT, true, true>(sm) : flow_occupancy<TT, false, true>(sm))          \
-                   : (wide ? flow_occupancy<TT, true, false>(sm) : flow_occupancy<TT, false, false>(sm)))
+#define OCC(TT) (wide ? flow_occupancy<TT, true>() : flow_occupancy<TT, false>())
         switch (T) {
             case 1: c = OCC(1); break;
             case 2: c = OCC(2); break;
@@ -195,13 +186,9 @@ void launch_flow(f4la_ctx *ctx, int T, const FlowArgs &a, bool wide)
     uint64_t g = (uint64_t)ctx->sm_count * flow_blocks(ctx, T, wide);
     if (g > total) g = total;
     const unsigned grid = (unsigned)g;
-    const bool b = ctx->bulk != 0;
-    const size_t sm = flow_smem(T, b);
-#define FLOW(TT)                                                                                          \
-    if (b) { if (wide) k_pull_flow<TT, true, true><<<grid, kSolveThreads, sm, ctx->stream>>>(a);           \
-             else      k_pull_flow<TT, false, true><<<grid, kSolveThreads, sm, ctx->stream>>>(a); }        \
-    else   { if (wide) k_pull_flow<TT, true, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a);           \
-             else      k_pull_flow<TT, false, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a); }
+#define FLOW(TT)                                                                                   \
+    if (wide) k_pull_flow<TT, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);                    \
+    else      k_pull_flow<TT, false><<<grid, kSolveThreads, 0, ctx->stream>>>(a);
     switch (T) {
         case 1: FLOW(1); break;
         case 2: FLOW(2); break;
@@ -407,7 +394,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         if (rank + slack > kc) { ctx->compress_escalated++; continue; }   /* too close to the number of combinations */
         OK(ensure(ctx, ctx->dense_out, (size_t)(rank ? rank : 1) * ncr * 4 + 16));
         if (rank) {
-            dim3 grid((ncr + 255) / 256, rank);
+            dim3 grid(rank, (ncr + 255) / 256);
             k_ge_extract<<<grid, 256, 0, s>>>(D2, kc, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
                                               as<uint32_t>(ctx->dense_out), p, pinv);
@@ -595,6 +582,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint32_t *Dm = nullptr;
     uint64_t ge_ld = 0;               /* leading dimension of the block the reduced rows are read from */
     uint32_t echelon_path = 0;
+    bool rows_are_combinations = false;   /* the block that was eliminated holds random combinations, not lower rows */
     const uint32_t rba_words = (nru + 31) / 32;
 
     for (;;) {
@@ -688,6 +676,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.ncl = ncl; f.out = as<uint32_t>(ctx->D); f.out_ld = ld; f.chunk0 = c0;
         f.p = p; f.pinv = pinv;
         f.two64 = (uint32_t)(((~0ull) % p + 1) % p);
+        f.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6);
+        /* reference-equivalent unit count: pivots keyed by row index, true lower rows only */
+        f.piv_row_ptr = (!by_lead && !combos) ? m->row_ptr : nullptr;
+        f.ref_units = reinterpret_cast<unsigned long long *>(d_err + 12);
         CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
@@ -715,6 +707,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                            (ctx->compress_escalated != esc0 ? 4u : 0u);
         }
         ge_ld = ld;
+        rows_are_combinations = compressed || combos;
         if (compressed) { Dm = as<uint32_t>(ctx->D2); ge_ld = ctx->d2_ld; }
         else OK(gauss_jordan(ctx, Dm, ld, nrl, ncr, p, pinv, &rank));
     }
@@ -722,10 +715,13 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     if (!combos || rank + kProbSlack <= nvr) break;
     nvr = (uint64_t)nvr * 4 >= nrl_in / 2 ? nrl_in : nvr * 4;
     }   /* attempts */
+    uint64_t ref_units = 0, ref_apps = 0;
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
-        CU(cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_err, d_err, 64, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        memcpy(&ref_units, h_err + 12, 8);
+        memcpy(&ref_apps, h_err + 14, 8);
         if (*h_err)
             return fail(ctx, F4LA_ERR_CUDA, "device pipeline reported error bits 0x%x (4: column out of range in a lower "
                         "row, 16: dataflow watchdog expired)", *h_err);
@@ -755,13 +751,13 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, by_lead ? p : 0u, dense_dst);
             ctx->launches++;
         } else if (rank) {
-            dim3 grid((ncr + 255) / 256, rank);
+            dim3 grid(rank, (ncr + 255) / 256);
             k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
                                               dense_dst, p, pinv);
             ctx->launches++;
         }
-        if (ctx->debug) CU(cudaEventRecord(ctx->ev[7], s));
+        if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[0], s));
         uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
         uint32_t *h_pivrow = h_dense + (size_t)ndense * ncr;
         uint32_t *h_pivcol = h_pivrow + rank;
@@ -781,14 +777,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
         }
         CU(cudaGetLastError());
-        if (ctx->debug) CU(cudaEventRecord(ctx->ev[6], s));
+        if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[1], s));
         const double t_copy0 = now_ms();
         CU(cudaStreamSynchronize(s));
         const double t_copy1 = now_ms();
         if (ctx->debug) {
             float a = 0, b = 0;
-            cudaEventElapsedTime(&a, ctx->ev[3], ctx->ev[7]);
-            cudaEventElapsedTime(&b, ctx->ev[7], ctx->ev[6]);
+            cudaEventElapsedTime(&a, ctx->ev[3], ctx->dbg_ev[0]);
+            cudaEventElapsedTime(&b, ctx->dbg_ev[0], ctx->dbg_ev[1]);
             fprintf(stderr, "[f4la debug] extract kernel %.3f ms, copies %.3f ms (%zu bytes)\n", a, b, dense_bytes);
         }
         dbg_copy_ms = t_copy1 - t_copy0; dbg_t1 = t_copy1;
@@ -820,7 +816,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         uint64_t nnz = 0;
         for (uint32_t t = 0; t < nout; ++t) {
             out->row_ptr[t] = nnz;
-            out->src_row[t] = (nf_mode || by_lead) ? t : h_pivrow[rank - 1 - t];
+            /* a pivot row of a block of random combinations has no single donor among the lower rows */
+            out->src_row[t] = (nf_mode || by_lead) ? t : rows_are_combinations ? 0xffffffffu : h_pivrow[rank - 1 - t];
             nnz += rnz[t];
         }
         out->row_ptr[nout] = nnz;
@@ -871,7 +868,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             st->ms_hot_kernel += ms;
         }
         st->hot_kernel_launches = (uint32_t)(n_flow_ev / 2);
-        st->units = (uint64_t)nnz_pull * nrl;
+        st->units = ref_units;
+        st->ref_applications = ref_apps;
+        st->dense_macs = (uint64_t)nnz_pull * nrl;
         st->pivot_applications = (uint64_t)nnz_pull;
         st->bytes_d2h = d2h_bytes;
         st->kernel_launches = ctx->launches - launches0;
@@ -999,6 +998,7 @@ f4la_ctx *f4la_b200_create(int device)
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     { const char *sp = getenv("F4LA_B200_SPLIT_H2D"); if (sp) ctx->split_h2d = atoi(sp) != 0; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &e : ctx->dbg_ev) cudaEventCreate(&e);
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
     ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : 0;
@@ -1016,8 +1016,8 @@ f4la_ctx *f4la_b200_create(int device)
     if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
     ctx->debug = dbg && atoi(dbg) != 0;
-    const char *bk = getenv("F4LA_B200_BULK");
-    ctx->bulk = bk && atoi(bk) != 0;
+    const char *wd = getenv("F4LA_B200_WATCHDOG_MS");
+    ctx->watchdog_ms = wd && atof(wd) > 0 ? atof(wd) : 20000.0;
     const char *tm = getenv("F4LA_B200_TMAX");
     if (tm && atoi(tm) >= 1 && atoi(tm) <= kMaxT) ctx->tmax = atoi(tm);
     const char *bud = getenv("F4LA_B200_L2_MB");
@@ -1041,6 +1041,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
     if (ctx->h_combo.p) cudaFreeHost(ctx->h_combo.p);
     for (auto &e : ctx->ev) cudaEventDestroy(e);
+    for (auto &e : ctx->dbg_ev) cudaEventDestroy(e);
     for (auto &e : ctx->flow_ev) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);

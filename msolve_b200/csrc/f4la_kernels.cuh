@@ -25,10 +25,10 @@
  *   reduced row echelon form by Gauss-Jordan elimination (trailing block,
  *   reference la_ff_32.c:3390-3500 + :3354-3388 compute the same unique RREF).
  *
- * Arithmetic is exact: residues are kept canonical in [0,p) as uint32, sums of
- * products are accumulated in uint64 with the coefficient split in two 16-bit
- * halves (v * c_lo < 2^47, v * c_hi < 2^46: 2^16 terms cannot overflow), and
- * reduced with a Barrett step (floor(2^64/p)) once per column.
+ * Arithmetic is exact: residues are kept canonical in [0,p) as uint32.  For p >= 2^16 a dot
+ * product is accumulated in 96 bits (one IMAD.WIDE.U32 with carry-out per product plus an
+ * add-with-carry into a third word, see struct Acc below), for p < 2^16 in a plain uint64; one
+ * Barrett reduction (floor(2^64/p)) per row and column at the end.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -454,7 +454,7 @@ __device__ __forceinline__ uint32_t fold_acc(const Acc &a, uint32_t extra, uint3
  * are always ready: kFlagAlwaysZ when no lower row of the chunk touches them, else kFlagAlwaysNZ */
 constexpr uint32_t kFlagAlwaysZ  = 0xfffffffeu;
 constexpr uint32_t kFlagAlwaysNZ = 0xffffffffu;
-constexpr uint32_t kSpinLimit  = 1u << 24;      /* polls before the watchdog gives up (seconds) */
+constexpr uint32_t kSpinLimit  = 1u << 24;      /* polls before the level pass gives up (seconds) */
 constexpr uint32_t kErrWatchdog = 16u;
 
 /* compile-time tuning knobs of k_pull_flow (A/B builds: tools/build_variants.sh) */
@@ -490,6 +490,9 @@ struct FlowArgs {
     uint32_t        p;
     uint32_t        two64;      /* 2^64 mod p                                     */
     uint64_t        pinv;
+    uint64_t        watchdog_ns; /* a wait for a source column longer than this sets kErrWatchdog */
+    const uint64_t *piv_row_ptr; /* row_ptr of the pivot rows (pivot j = row j): row length = cost of one application; or NULL */
+    unsigned long long *ref_units; /* [0] += reference-equivalent coefficient applications, [1] += pivot applications; or NULL */
 };
 
 /* Ready words are polled with a relaxed, L1-bypassing load.  An acquire load would
@@ -497,11 +500,18 @@ struct FlowArgs {
  * nothing read through L1 can be stale: the vectors V[src] are fetched with ld.cg straight from
  * L2, the point of coherence, and only after the branch that consumed the ready word, while the
  * producer makes its stores visible (fence) before the release store of that word. */
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *ptr)
+__device__ __forceinline__ uint32_t ld_relaxed_flag(const uint32_t *ptr)
 {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
     return v;
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ void st_release(uint32_t *ptr, uint32_t v)
@@ -540,22 +550,30 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
         uint32_t f = kFlagAlwaysZ;
         if (lane < n) {
             en = __ldg(&A.ent[b + lane]);
-            f = ld_acquire(&flagc[en.x]);
+            f = ld_relaxed_flag(&flagc[en.x]);
         }
         bool ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
         uint32_t spins = 0;
+        uint64_t t_wait0 = 0;
         while (!__all_sync(0xffffffffu, ready)) {
             if (!ready) {
                 __nanosleep(64);
-                f = ld_acquire(&flagc[en.x]);
+                f = ld_relaxed_flag(&flagc[en.x]);
                 ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
-                if (++spins > kSpinLimit) {          /* watchdog: never hang the GPU */
-                    atomicOr(A.err, kErrWatchdog);
-                    ready = true;
+                if ((++spins & 1023u) == 0) {        /* watchdog on wall time: never hang the GPU */
+                    const uint64_t now = global_timer_ns();
+                    if (t_wait0 == 0) t_wait0 = now;
+                    else if (now - t_wait0 > A.watchdog_ns) {
+                        atomicOr(A.err, kErrWatchdog);
+                        ready = true;
+                    }
                 }
             }
         }
-        __syncwarp();       /* order every lane's V loads after the lanes' acquires */
+        /* relaxed polls + ONE fence per batch make the acquire pattern of the PTX memory model: the
+         * producer's stores of V[src] (fence + st.release of the ready word) happen before the loads below */
+        __threadfence();
+        __syncwarp();
         /* Sources whose vector is entirely zero in this chunk contribute nothing:
          * the lower rows come clustered, 15-60 % of the (pivot, chunk) vectors are
          * zero, so their loads and multiplies are skipped altogether. */
@@ -598,153 +616,25 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
     }
 }
 
-/* ---- bulk-copy (TMA engine) variant of the inner loop ------------------------------------ */
-/* The register file bounds the bytes a warp can keep in flight with LDG (4 registers per lane
- * and 16-byte load).  Here the source vectors (one contiguous 128*T*4-byte line each) are
- * fetched by the bulk-copy engine straight into a per-warp ring in shared memory
- * (cp.async.bulk.shared.global, completion on an mbarrier per stage), lanes read them back
- * with conflict-free LDS.128.  kBulkStages copies are in flight per warp. */
-constexpr int kBulkStages = 8;
-
-struct BulkPipe {
-    uint32_t stage_base;   /* shared address of this warp's ring                  */
-    uint32_t bar_base;     /* shared address of this warp's kBulkStages mbarriers */
-    uint32_t issued;
-    uint32_t consumed;
-};
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void bulk_issue(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
 template <int T, bool WIDE>
-__device__ __forceinline__ void flow_accumulate_bulk(const FlowArgs &A, const uint32_t *__restrict__ Vc,
-                                                     const uint32_t *__restrict__ flagc,
-                                                     uint32_t b0, uint32_t b1, uint32_t lane,
-                                                     Acc (&acc)[T][4], BulkPipe &pp)
-{
-    constexpr uint32_t kBytes = T * kRowsPerT * 4;
-    constexpr uint32_t Rc = T * kRowsPerT;         /* == A.Rc; a constant turns the address products into shifts */
-    for (uint32_t b = b0; b < b1; b += 32) {
-        const uint32_t n = min(32u, b1 - b);
-        uint2 en = make_uint2(0, 0);
-        uint32_t f = kFlagAlwaysZ;
-        if (lane < n) {
-            en = __ldg(&A.ent[b + lane]);
-            f = ld_acquire(&flagc[en.x]);
-        }
-        bool ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
-        uint32_t spins = 0;
-        while (!__all_sync(0xffffffffu, ready)) {
-            if (!ready) {
-                __nanosleep(64);
-                f = ld_acquire(&flagc[en.x]);
-                ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
-                if (++spins > kSpinLimit) { atomicOr(A.err, kErrWatchdog); ready = true; }
-            }
-        }
-        __syncwarp();
-        /* the vectors were written through the generic proxy (by other SMs), the bulk engine reads
-         * through the async proxy */
-        asm volatile("fence.proxy.async;" ::: "memory");
-        const uint32_t live = __ballot_sync(0xffffffffu, lane < n && (f & 1u));
-        const uint32_t nl = __popc(live);
-        /* compact: lane k holds the k-th live entry */
-        const uint32_t from = __fns(live, 0, lane + 1) & 31u;
-        const uint32_t csrc = __shfl_sync(0xffffffffu, en.x, from);
-        const uint32_t ccf  = __shfl_sync(0xffffffffu, en.y, from);
-
-        const uint32_t npro = min((uint32_t)kBulkStages, nl);
-        for (uint32_t k = 0; k < npro; ++k) {
-            const uint32_t s = __shfl_sync(0xffffffffu, csrc, k);
-            if (lane == 0) {
-                const uint32_t st = pp.issued % kBulkStages;
-                bulk_issue(pp.stage_base + st * kBytes, Vc + (size_t)s * Rc, kBytes, pp.bar_base + st * 8);
-            }
-            pp.issued++;
-        }
-        for (uint32_t k = 0; k < nl; ++k) {
-            const uint32_t st = pp.consumed % kBulkStages;
-            const uint32_t parity = (pp.consumed / kBulkStages) & 1u;
-            uint32_t tries = 0;
-            while (!mbar_try_wait(pp.bar_base + st * 8, parity)) {
-                if (++tries > kSpinLimit) { atomicOr(A.err, kErrWatchdog); break; }
-            }
-            uint4 v[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) v[t] = lds_u4(pp.stage_base + st * kBytes + t * 512 + lane * 16);
-            const uint32_t cf = __shfl_sync(0xffffffffu, ccf, k);
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                mac<WIDE>(acc[t][0], v[t].x, cf); mac<WIDE>(acc[t][1], v[t].y, cf);
-                mac<WIDE>(acc[t][2], v[t].z, cf); mac<WIDE>(acc[t][3], v[t].w, cf);
-            }
-            pp.consumed++;
-            __syncwarp();                 /* every lane has read the stage before it is refilled */
-            if (k + kBulkStages < nl) {
-                const uint32_t s = __shfl_sync(0xffffffffu, csrc, k + kBulkStages);
-                if (lane == 0) {
-                    const uint32_t st2 = pp.issued % kBulkStages;
-                    bulk_issue(pp.stage_base + st2 * kBytes, Vc + (size_t)s * Rc, kBytes, pp.bar_base + st2 * 8);
-                }
-                pp.issued++;
-            }
-        }
-    }
-}
-
-template <int T, bool WIDE, bool BULK>
-__global__ void __launch_bounds__(kSolveThreads, BULK ? 2 : ((T <= 2) ? F4LA_FLOW_OCC : 2))
+__global__ void __launch_bounds__(kSolveThreads, (T <= 2) ? F4LA_FLOW_OCC : 2)
 k_pull_flow(const FlowArgs A)
 {
     __shared__ uint32_t part[kWarpsPerBlock][T * kRowsPerT];
     __shared__ uint32_t s_id;
-    extern __shared__ __align__(128) uint8_t dyn_smem[];      /* BULK: rings + mbarriers */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t total = A.n_items * A.G;
-
-    BulkPipe pp = {0, 0, 0, 0};
-    if (BULK) {
-        constexpr uint32_t kBytes = T * kRowsPerT * 4;
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(dyn_smem);
-        pp.stage_base = base + warp * kBulkStages * kBytes;
-        pp.bar_base = base + kWarpsPerBlock * kBulkStages * kBytes + warp * kBulkStages * 8;
-        if (lane == 0) {
-            for (int st = 0; st < kBulkStages; ++st) mbar_init(pp.bar_base + st * 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
+    /* coefficient applications of the REFERENCE algorithm done by this thread's columns: a known pivot j
+     * is applied to every lower row with a non-zero multiplier V[j][r], at the cost of its row length
+     * (the reference counts len per application, la_ff_32.c:1214-1216) */
+    uint64_t ref_units = 0, ref_apps = 0;
 
     for (;;) {
         if (threadIdx.x == 0) s_id = atomicAdd(A.counter, 1u);
         __syncthreads();
         const uint32_t id = s_id;
         __syncthreads();
-        if (id >= total) return;
+        if (id >= total) break;
         const uint32_t chunk = id % A.G;
         const uint32_t it = A.items[id / A.G];
         const uint32_t pos = it >> 5, cnt = (it >> 1) & 15u;
@@ -762,13 +652,12 @@ k_pull_flow(const FlowArgs A)
             if (warp < cnt) {
                 const uint32_t j = A.sched[pos + warp];
                 const uint32_t e0 = A.col_ptr[j], e1 = A.col_ptr[j + 1];
-                if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, e0, e1, lane, acc, pp);
-                else flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, acc);
+                flow_accumulate<T, WIDE>(A, Vc, flagc, e0, e1, lane, acc);
                 const bool to_out = j >= A.ncl;
                 uint32_t *dst = to_out ? A.out + (size_t)(j - A.ncl) * A.out_ld + (size_t)(A.chunk0 + chunk) * A.Rc
                                        : Vc + (size_t)j * A.Rc;
                 const uint4 *init = reinterpret_cast<const uint4 *>(Vc + (size_t)j * A.Rc) + lane;
-                uint32_t nonzero = 0;
+                uint32_t nonzero = 0, nnz = 0;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
                     const uint4 x = init[t * 32];
@@ -779,8 +668,10 @@ k_pull_flow(const FlowArgs A)
                     r.w = fold_acc<WIDE>(acc[t][3], x.w, A.p, A.pinv, A.two64);
                     reinterpret_cast<uint4 *>(dst)[lane + t * 32] = r;
                     nonzero |= r.x | r.y | r.z | r.w;
+                    nnz += (r.x != 0) + (r.y != 0) + (r.z != 0) + (r.w != 0);
                 }
                 if (!to_out) {
+                    if (A.piv_row_ptr) { ref_units += (uint64_t)nnz * (A.piv_row_ptr[j + 1] - A.piv_row_ptr[j]); ref_apps += nnz; }
                     const bool any = __any_sync(0xffffffffu, nonzero != 0);
                     __threadfence();
                     __syncwarp();
@@ -796,8 +687,7 @@ k_pull_flow(const FlowArgs A)
             /* equal contiguous shares of the entries for the 8 warps */
             const uint32_t seg = (e1 - e0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
             const uint32_t b0 = min(e1, e0 + warp * seg), b1 = min(e1, b0 + seg);
-            if (BULK) flow_accumulate_bulk<T, WIDE>(A, Vc, flagc, b0, b1, lane, acc, pp);
-            else flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, acc);
+            flow_accumulate<T, WIDE>(A, Vc, flagc, b0, b1, lane, acc);
         }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -819,12 +709,23 @@ k_pull_flow(const FlowArgs A)
             for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w][r];
             const uint32_t v = mod_u64(s, A.p, A.pinv);
             dst[r] = v;
-            nonzero |= v != 0;
+            nonzero += v != 0;
         }
         if (!to_out) {
+            if (A.piv_row_ptr) { ref_units += (uint64_t)nonzero * (A.piv_row_ptr[j + 1] - A.piv_row_ptr[j]); ref_apps += nonzero; }
             __threadfence();
             nonzero = __syncthreads_or(nonzero);
             if (threadIdx.x == 0) st_release(&flagc[j], (A.epoch << 1) | (nonzero ? 1u : 0u));
+        }
+    }
+    if (A.ref_units) {
+        for (int o = 16; o; o >>= 1) {
+            ref_units += __shfl_xor_sync(0xffffffffu, ref_units, o);
+            ref_apps += __shfl_xor_sync(0xffffffffu, ref_apps, o);
+        }
+        if (lane == 0 && ref_apps) {
+            atomicAdd(A.ref_units, (unsigned long long)ref_units);
+            atomicAdd(A.ref_units + 1, (unsigned long long)ref_apps);
         }
     }
 }
@@ -1442,8 +1343,8 @@ __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32
                              const uint32_t *__restrict__ pivinv, const uint8_t *__restrict__ ispiv,
                              uint32_t *__restrict__ out, uint32_t p, uint64_t pinv)
 {
-    const uint32_t t = blockIdx.y;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = blockIdx.x;                     /* rank can exceed the 65535 limit of grid.y */
+    const uint32_t c = blockIdx.y * blockDim.x + threadIdx.x;
     if (t >= rank || c >= ncr) return;
     const uint32_t k = rank - 1 - t;
     const uint32_t ck = pivcol[k];

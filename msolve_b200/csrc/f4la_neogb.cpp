@@ -242,7 +242,10 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
      * independent subset gives the same reduced rows). */
     if (learn) {
         std::vector<char> kept(nrl, 0);
-        for (uint32_t t = 0; t < res.nrows; ++t) kept[res.src_row[t]] = 1;
+        for (uint32_t t = 0; t < res.nrows; ++t) {
+            if (res.src_row[t] >= nrl) die("tracing needs a donor row for every new pivot");
+            kept[res.src_row[t]] = 1;
+        }
         uint32_t **rba = fld<uint32_t **>(mat, L.mat_rba);
         const uint32_t words = res.rba_words;
         for (uint32_t i = 0; i < nrl; ++i) {
@@ -308,10 +311,13 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
             void *cf = malloc((size_t)(len ? len : 1) * w);
             memcpy(row + L.row_offset, res.cols + a, (size_t)len * 4);
             memcpy(cf, (unsigned char *)res.cf + a * w, (size_t)len * w);
+            /* BINDEX / MULT of the donor row (la_ff_32.c:1234-1235); rows born from random combinations have
+             * none -- the reference's 16-bit reducer leaves the two words unset as well (la_ff_16.c:407-409),
+             * only the tracer reads them and it never runs in those modes */
             const uint32_t src = res.src_row[t];
             row[L.row_deg] = 0;
-            row[L.row_bindex] = src_bindex[src];
-            row[L.row_mult] = src_mult[src];
+            row[L.row_bindex] = src < nrl ? src_bindex[src] : 0;
+            row[L.row_mult] = src < nrl ? src_mult[src] : 0;
             row[L.row_coeffs] = t;
             row[L.row_preloop] = len % L.unroll;
             row[L.row_length] = len;
@@ -330,9 +336,12 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     fld<double>(st, L.md_la_ctime) += cpu_s() - ct0;
     fld<double>(st, L.md_la_rtime) += wall_s() - rt0;
     fld<int64_t>(st, L.md_num_zerored) += (int64_t)nrl - (int64_t)np;
+    /* application_nr_* (la_ff_32.c:1214-1216): per applied pivot its row length / 1000 and one reduction.
+     * The device counts exactly these for the known pivots (stats.units); msolve prints them as Gops/sec
+     * (msolve.c:2666-2673) */
     fld<double>(st, L.md_application_nr_mult) += (double)stats.units / 1000.0;
     fld<double>(st, L.md_application_nr_add) += (double)stats.units / 1000.0;
-    fld<uint64_t>(st, L.md_application_nr_red) += stats.pivot_applications;
+    fld<uint64_t>(st, L.md_application_nr_red) += stats.ref_applications;
     if (fld<int32_t>(st, L.md_info_level) > 1) {
         fprintf(stderr, "%9d new %7d zero", (int)np, (int)(nrl - np));
         fflush(stderr);

@@ -51,6 +51,7 @@ class CStats(C.Structure):
         ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("rank", C.c_uint32),
         ("ms_hot_kernel", C.c_double), ("hot_kernel_launches", C.c_uint32), ("echelon_path", C.c_uint32),
+        ("dense_macs", C.c_uint64), ("ref_applications", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -64,9 +64,13 @@ static int    g_verbose          = 0;
 
 typedef void (*la_fn_t)(mat_t *, const bs_t *const, const bs_t *const, md_t *);
 typedef void (*ir_fn_t)(mat_t *, bs_t *, md_t *, int);
-static la_fn_t g_backend_la       = NULL;
-static la_fn_t g_backend_exact_la = NULL;
-static ir_fn_t g_backend_interred = NULL;
+typedef int  (*app_fn_t)(mat_t *, const bs_t *const, md_t *);
+typedef void (*tr_fn_t)(trace_t *, mat_t *, const bs_t *const, md_t *);
+static la_fn_t  g_backend_la       = NULL;
+static la_fn_t  g_backend_exact_la = NULL;
+static ir_fn_t  g_backend_interred = NULL;
+static app_fn_t g_backend_app      = NULL;
+static tr_fn_t  g_backend_trace    = NULL;
 
 static size_t cf_width(int ff_bits) { return ff_bits == 8 ? 1 : ff_bits == 16 ? 2 : 4; }
 
@@ -317,9 +321,28 @@ static void hook_exact_la(mat_t *mat, const bs_t *const tbr, const bs_t *const b
 static void hook_interred(mat_t *mat, bs_t *bs, md_t *st, int free_basis)
 {
     const double t0 = realtime();
-    if (g_mode == 1 && g_backend_interred) g_backend_interred(mat, bs, st, free_basis);
+    if ((g_mode == 1 || g_mode == 4) && g_backend_interred) g_backend_interred(mat, bs, st, free_basis);
     else dispatch_interreduce_matrix_rows(mat, bs, st, free_basis);
     g_la_seconds += realtime() - t0;
+}
+
+/* application_linear_algebra / trace_linear_algebra (data.h:559-576): only the legacy tracer
+ * functions of modular.c call them; served by the backend whenever one is installed */
+static int hook_app(mat_t *mat, const bs_t *const bs, md_t *st)
+{
+    const double t0 = realtime();
+    const int r = ((g_mode == 1 || g_mode == 4) && g_backend_app) ? g_backend_app(mat, bs, st)
+                                                                   : dispatch_application_linear_algebra(mat, bs, st);
+    g_la_seconds += realtime() - t0; g_la_calls++;
+    return r;
+}
+
+static void hook_trace(trace_t *trace, mat_t *mat, const bs_t *const bs, md_t *st)
+{
+    const double t0 = realtime();
+    if ((g_mode == 1 || g_mode == 4) && g_backend_trace) g_backend_trace(trace, mat, bs, st);
+    else dispatch_trace_linear_algebra(trace, mat, bs, st);
+    g_la_seconds += realtime() - t0; g_la_calls++;
 }
 
 /* ------------------------------------------------------------------ */
@@ -330,9 +353,12 @@ void refh_set_mode(int mode, int max_records, int verbose)
 {
     g_mode = mode; g_max_records = max_records > 0 ? max_records : (1 << 30);
     g_verbose = verbose;
+    /* all five matrix-level pointers of data.h:529-595 go through the harness */
     linear_algebra = hook_la;
     exact_linear_algebra = hook_exact_la;
     interreduce_matrix_rows = hook_interred;
+    application_linear_algebra = hook_app;
+    trace_linear_algebra = hook_trace;
 }
 
 void refh_set_backend(void *la, void *exact_la, void *interred)
@@ -340,6 +366,20 @@ void refh_set_backend(void *la, void *exact_la, void *interred)
     g_backend_la = (la_fn_t)la;
     g_backend_exact_la = (la_fn_t)exact_la;
     g_backend_interred = (ir_fn_t)interred;
+}
+
+void refh_set_backend_tracer(void *app, void *trace)
+{
+    g_backend_app = (app_fn_t)app;
+    g_backend_trace = (tr_fn_t)trace;
+}
+
+/* which of the five pointers currently point at the harness hooks (bit i set), for the tests */
+int refh_hooked_pointers(void)
+{
+    return (linear_algebra == hook_la) | (exact_linear_algebra == hook_exact_la) << 1 |
+           (interreduce_matrix_rows == hook_interred) << 2 | (application_linear_algebra == hook_app) << 3 |
+           (trace_linear_algebra == hook_trace) << 4;
 }
 
 void refh_reset(void)
@@ -454,6 +494,18 @@ int refh_reference_la(const f4la_flat_matrix *in, int32_t laopt, int32_t threads
     return 0;
 }
 
+/* side channels of the last refh_call_entry() (SURVEY 8b "side channels to honour"):
+ * st->np, mat->np, mat->nr, mat->sz, st->num_zerored, st->la_rtime, st->la_ctime,
+ * st->application_nr_mult, _add, _red */
+static double g_side[10];
+static void snapshot_side(const mat_t *mat, const md_t *st)
+{
+    g_side[0] = st->np; g_side[1] = mat->np; g_side[2] = mat->nr; g_side[3] = mat->sz;
+    g_side[4] = (double)st->num_zerored; g_side[5] = st->la_rtime; g_side[6] = st->la_ctime;
+    g_side[7] = st->application_nr_mult; g_side[8] = st->application_nr_add; g_side[9] = (double)st->application_nr_red;
+}
+void refh_last_side(double *o) { memcpy(o, g_side, sizeof(g_side)); }
+
 /* Generic driver for the matrix-level entry points on a flat matrix.
  *   which 0: fn(mat, tbr, bs, st)            linear_algebra / exact_linear_algebra signature
  *   which 1: int fn(mat, bs, st)             application_linear_algebra signature
@@ -499,7 +551,6 @@ int refh_call_entry(const f4la_flat_matrix *in, int32_t which, void *fn, int32_t
         memcpy(mat->tr, rows + in->nru, in->nrl * sizeof(hm_t *));
         free(rows);
         if (which == 1) {
-            typedef int (*app_fn_t)(mat_t *, const bs_t *const, md_t *);
             const int r = fn ? ((app_fn_t)fn)(mat, bs, st) : 0;
             if (!fn) dispatch_linear_algebra(mat, bs, bs, st);      /* the reference's own app variant is stale */
             if (ret) *ret = fn ? r : (mat->np != in->nrl);
@@ -509,6 +560,7 @@ int refh_call_entry(const f4la_flat_matrix *in, int32_t which, void *fn, int32_t
             else dispatch_linear_algebra(mat, bs, bs, st);
         }
     }
+    snapshot_side(mat, st);
     uint32_t *bi, *mu;
     flatten_output(out, &bi, &mu, mat, st);
     out->src_row = bi;
@@ -519,6 +571,86 @@ int refh_call_entry(const f4la_flat_matrix *in, int32_t which, void *fn, int32_t
     int bad = 0;
     if (fn) for (len_t i = 0; i < mat->np; ++i) if (mat->tr[i] && mu[i] != 7 * bi[i] + 1) bad = 1;
     free(mu);
+    for (len_t i = 0; i < mat->np; ++i) {
+        if (!mat->tr || !mat->tr[i]) continue;
+        hm_t ci = mat->tr[i][COEFFS];
+        if (ff_bits == 8) free(mat->cf_8[ci]); else if (ff_bits == 16) free(mat->cf_16[ci]); else free(mat->cf_32[ci]);
+        free(mat->tr[i]);
+    }
+    free(mat->rr); free(mat->tr); free(mat->cf_8); free(mat->cf_16); free(mat->cf_32);
+    free(mat); free(cfarr); free(bs); free(st);
+    return bad ? -2 : 0;
+}
+
+/* trace_linear_algebra signature (data.h:571-576) on a flat matrix: mat_t with the reducer bit arrays
+ * symbolic preprocessing allocates for a learning run (symbol.c:625-629) and a fresh trace_t
+ * (initialize_trace, modular.c:45-64).  fn == NULL runs the reference's dispatcher.  Besides the rows the
+ * trace entry td[0] written by construct_trace (tools.c:63-183) is returned in tinfo (capacity tcap words):
+ *   tinfo[0] = ntr (kept lower rows), tinfo[1] = nrr (reducers used by them), tinfo[2] = words per row,
+ *   then ntr BINDEX values of the kept rows, nrr BINDEX values of the reducers, ntr x words bit arrays. */
+int refh_call_trace_entry(const f4la_flat_matrix *in, void *fn, int32_t threads,
+                          f4la_flat_result *out, uint32_t *tinfo, uint64_t tcap)
+{
+    const uint32_t n = in->nru + in->nrl;
+    const size_t w = in->cf_bytes;
+    const int ff_bits = w == 1 ? 8 : w == 2 ? 16 : 32;
+    mat_t *mat = calloc(1, sizeof(mat_t));
+    bs_t  *bs  = calloc(1, sizeof(bs_t));
+    md_t  *st  = calloc(1, sizeof(md_t));
+    st->fc = in->fc; st->gfc = in->fc; st->nthrds = threads; st->laopt = 2;
+    st->ff_bits = ff_bits; st->trace_level = LEARN_TRACER; st->info_level = 0;
+    bs->ld = bs->sz = in->ncf;
+    void **cfarr = calloc(in->ncf ? in->ncf : 1, sizeof(void *));
+    for (uint32_t c = 0; c < in->ncf; ++c) cfarr[c] = (unsigned char *)in->cf + in->cf_ptr[c] * w;
+    bs->cf_8 = (cf8_t **)cfarr; bs->cf_16 = (cf16_t **)cfarr; bs->cf_32 = (cf32_t **)cfarr;
+    mat->ncl = in->ncl; mat->ncr = in->ncr; mat->nc = in->ncl + in->ncr;
+    mat->nru = in->nru; mat->nrl = in->nrl; mat->nr = mat->sz = n;
+    mat->rr = malloc((in->nru ? in->nru : 1) * sizeof(hm_t *));
+    mat->tr = malloc((in->nrl ? in->nrl : 1) * sizeof(hm_t *));
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint64_t len = in->row_ptr[r + 1] - in->row_ptr[r];
+        hm_t *row = malloc((len + OFFSET) * sizeof(hm_t));
+        row[DEG] = 0; row[BINDEX] = r; row[MULT] = 7 * r + 1; row[COEFFS] = in->row_cf[r];
+        row[PRELOOP] = (hm_t)(len % UNROLL); row[LENGTH] = (hm_t)len;
+        memcpy(row + OFFSET, in->cols + in->row_ptr[r], len * sizeof(hm_t));
+        if (r < in->nru) mat->rr[r] = row; else mat->tr[r - in->nru] = row;
+    }
+    const uint64_t lrba = in->nru / 32 + ((in->nru % 32) != 0);
+    mat->rbal = in->nrl;
+    mat->rba = malloc((in->nrl ? in->nrl : 1) * sizeof(rba_t *));
+    for (uint32_t i = 0; i < in->nrl; ++i) mat->rba[i] = calloc(lrba ? lrba : 1, sizeof(rba_t));
+    trace_t *trace = calloc(1, sizeof(trace_t));
+    trace->std = 8; trace->sts = 8;
+    trace->td = calloc(trace->std, sizeof(td_t));
+    trace->ts = calloc(trace->sts, sizeof(ts_t));
+
+    if (fn) ((tr_fn_t)fn)(trace, mat, bs, st); else dispatch_trace_linear_algebra(trace, mat, bs, st);
+
+    uint32_t *bi, *mu;
+    flatten_output(out, &bi, &mu, mat, st);
+    out->src_row = bi;
+    int bad = 0;
+    for (len_t i = 0; i < mat->np; ++i) if (fn && mat->tr[i] && mu[i] != 7 * bi[i] + 1) bad = 1;
+    free(mu);
+    /* the trace entry of this matrix (the caller of trace_linear_algebra bumps ltd afterwards) */
+    const td_t *td = &trace->td[0];
+    const uint32_t ntr = td->tld / 2, nrr = td->rld / 2;
+    const uint32_t words = nrr / 32 + ((nrr % 32) != 0);
+    if (tinfo && tcap >= 3 + (uint64_t)ntr + nrr + (uint64_t)ntr * words) {
+        tinfo[0] = ntr; tinfo[1] = nrr; tinfo[2] = words;
+        uint32_t *q = tinfo + 3;
+        for (uint32_t i = 0; i < ntr; ++i) { *q++ = td->tri[2 * i]; if (td->tri[2 * i + 1] != 7 * td->tri[2 * i] + 1) bad = 1; }
+        for (uint32_t i = 0; i < nrr; ++i) { *q++ = td->rri[2 * i]; if (td->rri[2 * i + 1] != 7 * td->rri[2 * i] + 1) bad = 1; }
+        for (uint32_t i = 0; i < ntr; ++i) { memcpy(q, td->rba[i], (size_t)words * sizeof(rba_t)); q += words; }
+    } else if (tinfo && tcap >= 3) {
+        tinfo[0] = ntr; tinfo[1] = nrr; tinfo[2] = 0xffffffffu;
+    }
+    /* construct_trace compacts mat->rba to the kept rows (or leaves it alone when every row vanished) */
+    for (len_t i = 0; i < mat->rbal; ++i) free(mat->rba[i]);
+    free(mat->rba);
+    for (uint32_t i = 0; i < ntr; ++i) free(td->rba[i]);
+    free(td->rba); free(td->tri); free(td->rri);
+    free(trace->td); free(trace->ts); free(trace);
     for (len_t i = 0; i < mat->np; ++i) {
         if (!mat->tr || !mat->tr[i]) continue;
         hm_t ci = mat->tr[i][COEFFS];
@@ -598,6 +730,10 @@ void refh_fill_layout(f4la_neogb_layout *l)
  * stub passes its address to the backend. */
 static void construct_trace_thunk(void *trace, void *mat) { construct_trace((trace_t *)trace, (mat_t *)mat); }
 void *refh_construct_trace_ptr(void) { return (void *)construct_trace_thunk; }
+
+/* likewise free_basis_elements() (basis.c:24-70), which interreduce_matrix_rows(free_basis != 0) calls */
+static void free_basis_elements_thunk(void *bs) { free_basis_elements((bs_t *)bs); }
+void *refh_free_basis_elements_ptr(void) { return (void *)free_basis_elements_thunk; }
 
 /* ------------------------------------------------------------------ */
 /* QQ multi-modular tracer flow (learn once, apply per prime)          */

@@ -120,13 +120,24 @@ def set_mode(mode: int, max_records: int = 0, verbose: int = 0) -> None:
     lib().refh_set_mode(mode, max_records, verbose)
 
 
-def set_backend(la=None, exact_la=None, interred=None) -> None:
-    """Addresses (ints / ctypes function pointers) of the backend entry points."""
+def set_backend(la=None, exact_la=None, interred=None, app=None, trace=None) -> None:
+    """Addresses (ints / ctypes function pointers) of the backend entry points: the five
+    matrix-level pointers of data.h:529-595."""
     def addr(f):
         if f is None:
             return None
         return C.cast(f, C.c_void_p).value if not isinstance(f, int) else f
-    lib().refh_set_backend(addr(la), addr(exact_la), addr(interred))
+    L = lib()
+    L.refh_set_backend(addr(la), addr(exact_la), addr(interred))
+    L.refh_set_backend_tracer.argtypes = [C.c_void_p, C.c_void_p]
+    L.refh_set_backend_tracer(addr(app), addr(trace))
+
+
+def hooked_pointers() -> int:
+    """Bit i set: pointer i (linear_algebra, exact_linear_algebra, interreduce_matrix_rows,
+    application_linear_algebra, trace_linear_algebra) goes through the harness."""
+    lib().refh_hooked_pointers.restype = C.c_int
+    return int(lib().refh_hooked_pointers())
 
 
 def reset() -> None:
@@ -260,6 +271,40 @@ def call_entry(m: FlatMatrix, which: int, fn=None, threads: int = 1):
     out = FlatResult.from_c(res)
     L.refh_free_result(C.byref(res))
     return out, int(ret.value), cidx[:out.nrows].copy()
+
+
+def call_trace_entry(m: FlatMatrix, fn=None, threads: int = 1):
+    """Drive the trace_linear_algebra signature (data.h:571-576) on a flat matrix.
+    -> (FlatResult, kept lower rows (flat row ids), reducers used (pivot ids), bit arrays [kept][words])"""
+    L = lib()
+    L.refh_call_trace_entry.restype = C.c_int
+    L.refh_call_trace_entry.argtypes = [C.POINTER(CFlatMatrix), C.c_void_p, C.c_int32, C.POINTER(CFlatResult),
+                                        C.c_void_p, C.c_uint64]
+    cm = m.c_struct()
+    res = CFlatResult()
+    cap = 3 + m.nrl + m.nru + m.nrl * ((m.nru + 31) // 32 + 1)
+    info = np.zeros(cap, dtype=np.uint32)
+    addr = None if fn is None else (fn if isinstance(fn, int) else C.cast(fn, C.c_void_p).value)
+    rc = L.refh_call_trace_entry(C.byref(cm), addr, threads, C.byref(res), info.ctypes.data, cap)
+    if rc != 0:
+        raise RuntimeError(f"refh_call_trace_entry failed: {rc} (-2: BINDEX/MULT not carried over together)")
+    out = FlatResult.from_c(res)
+    L.refh_free_result(C.byref(res))
+    ntr, nrr, words = int(info[0]), int(info[1]), int(info[2])
+    assert words != 0xffffffff
+    kept = info[3:3 + ntr].astype(np.int64) - m.nru
+    reds = info[3 + ntr:3 + ntr + nrr].astype(np.int64)
+    bits = info[3 + ntr + nrr:3 + ntr + nrr + ntr * words].reshape(ntr, words).copy()
+    return out, kept, reds, bits
+
+
+def last_side() -> dict:
+    """Side channels (md_t / mat_t fields) left by the last call_entry()."""
+    buf = (C.c_double * 10)()
+    lib().refh_last_side(buf)
+    names = ["st_np", "mat_np", "mat_nr", "mat_sz", "num_zerored", "la_rtime", "la_ctime",
+             "application_nr_mult", "application_nr_add", "application_nr_red"]
+    return dict(zip(names, [float(x) for x in buf]))
 
 
 def struct_layout() -> List[int]:

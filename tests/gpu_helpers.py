@@ -18,16 +18,21 @@ def install_backend(mode=rh.MODE_BACKEND, verbose=0):
     L.f4la_b200_neogb_set_construct_trace.argtypes = [C.c_void_p]
     L.f4la_b200_neogb_set_construct_trace(rh.lib().refh_construct_trace_ptr())
     rh.set_device_callback(L.f4la_b200_neogb_set_device)
-    la = C.cast(L.f4la_b200_linear_algebra, C.c_void_p).value
-    ela = C.cast(L.f4la_b200_exact_linear_algebra, C.c_void_p).value
-    rh.set_backend(la, ela, None)
+    L.f4la_b200_neogb_set_free_basis_elements.argtypes = [C.c_void_p]
+    rh.lib().refh_free_basis_elements_ptr.restype = C.c_void_p
+    L.f4la_b200_neogb_set_free_basis_elements(rh.lib().refh_free_basis_elements_ptr())
+    # all five matrix-level pointers of data.h:529-595
+    fns = [C.cast(getattr(L, n), C.c_void_p).value for n in (
+        "f4la_b200_linear_algebra", "f4la_b200_exact_linear_algebra", "f4la_b200_interreduce_matrix_rows",
+        "f4la_b200_application_linear_algebra", "f4la_b200_trace_linear_algebra")]
+    rh.set_backend(*fns)
     rh.reset()
     rh.set_mode(mode, 0, verbose)
     return L
 
 
 def uninstall_backend():
-    rh.set_backend(None, None, None)
+    rh.set_backend(None, None, None, None, None)
     rh.reset()
     rh.set_mode(rh.MODE_REFERENCE)
 
