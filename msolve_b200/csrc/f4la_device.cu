@@ -58,7 +58,7 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf sched, items, flowflags;
+    DevBuf sched, items, flowflags, refcnt;
     int           ge_mode = 0;          /* F4LA_B200_GE: (default) batched with the batch's pivot columns in shared memory;
                                            "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
                                            elimination pass per pivot (the fallbacks for very tall blocks, kept selectable for A-B) */
@@ -71,6 +71,8 @@ struct f4la_ctx {
     uint32_t      ge_batch = 8, ge_miss_limit = 4;   /* F4LA_B200_GE_BATCH (<= 32), F4LA_B200_GE_MISSES: pivots per batch, empty visits that end one */
     int           zerocopy = 1;         /* F4LA_B200_ZEROCOPY=0: result rows through a device buffer + copy */
     int           debug = 0;            /* F4LA_B200_DEBUG=1: statistics on stderr */
+    int           debug_sync = 0;       /* F4LA_B200_SYNC=1: synchronise after every kernel launch and name a failing one */
+    bool          debug_sync_reported = false;
     int           compress_fault = 0;   /* F4LA_B200_COMPRESS_FAULT=1 (tests): treat every verification as failed */
     size_t        batch_smem_optin = 0;
     DevBuf in_row_ptr, in_cols, in_row_cf, in_cf_ptr, in_cf;   /* staging of f4la_b200_reduce() inputs */
@@ -120,6 +122,22 @@ int fail(f4la_ctx *ctx, int code, const char *fmt, ...)
         int rc_ = (call);                                                              \
         if (rc_ != F4LA_OK) return rc_;                                                \
     } while (0)
+
+/* counts the kernels launched; with F4LA_B200_SYNC=1 every launch is followed by a synchronisation, so that a
+ * faulting kernel is reported with the source line of its launch (compute-sanitizer is not always available) */
+void note_launch(f4la_ctx *ctx, uint32_t n, int line)
+{
+    ctx->launches += n;
+    if (ctx->debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess && !ctx->debug_sync_reported) {
+            ctx->debug_sync_reported = true;
+            fprintf(stderr, "[f4la_b200] F4LA_B200_SYNC: kernel launched at f4la_device.cu:%d failed: %s\n", line,
+                    cudaGetErrorString(e));
+        }
+    }
+}
 
 int ensure(f4la_ctx *ctx, DevBuf &b, size_t bytes)
 {
@@ -196,7 +214,7 @@ void launch_flow(f4la_ctx *ctx, int T, const FlowArgs &a, bool wide)
         default: FLOW(4); break;
     }
 #undef FLOW
-    ctx->launches++;
+    note_launch(ctx, 1, __LINE__);
 }
 
 void empty_result(f4la_flat_result *out, uint32_t cf_bytes)
@@ -257,7 +275,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         uint32_t upd_grid = (ncr + 31) / 32;
         if (upd_grid > (uint32_t)ctx->sm_count) upd_grid = (uint32_t)ctx->sm_count;
         k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         for (uint32_t batches = 0;;) {
             const int group = 4;
             for (int k = 0; k < group; ++k) {
@@ -269,7 +287,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
                     Dm, ld, nrl, nrows4, ncr, nb_fit, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
                     as<uint8_t>(ctx->ispiv), as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol),
                     as<uint32_t>(ctx->pivrow), as<uint32_t>(ctx->pivinv), p, pinv, two64);
-                ctx->launches += 2;
+                note_launch(ctx, 2, __LINE__);
             }
             batches += group;
             CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
@@ -288,7 +306,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             ctx->batch_smem_optin = smem_cap;
         }
         k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         for (uint32_t batches = 0;;) {
             const int group = 4;
             for (int k = 0; k < group; ++k) {
@@ -300,7 +318,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
                     Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used), as<uint8_t>(ctx->ispiv),
                     as<GEState>(ctx->gestate), as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                     as<uint32_t>(ctx->pivinv), p, pinv);
-                ctx->launches += 2;
+                note_launch(ctx, 2, __LINE__);
             }
             batches += group;
             CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
@@ -312,7 +330,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         }
     } else {
     k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
-    ctx->launches++;
+    note_launch(ctx, 1, __LINE__);
     for (uint32_t done_steps = 0;;) {
         const int batch = 16;
         for (int k = 0; k < batch; ++k) {
@@ -322,7 +340,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
                                          as<uint32_t>(ctx->pivinv), p);
             k_ge_eliminate<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag), as<uint8_t>(ctx->used),
                                                as<GEState>(ctx->gestate), p, pinv);
-            ctx->launches += 2;
+            note_launch(ctx, 2, __LINE__);
         }
         done_steps += batch;
         CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
@@ -388,7 +406,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         }
         uint32_t *D2 = as<uint32_t>(ctx->D2);
         k_ge_compress<<<ncr, 256, (size_t)nrows4 * 4, s>>>(Dm, ld, nrl, nrows4, kc, d_ptr, d_row, d_rho, D2, p, pinv, two64);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         uint32_t rank = 0;
         OK(gauss_jordan(ctx, D2, kc, kc, ncr, p, pinv, &rank));
         if (rank + slack > kc) { ctx->compress_escalated++; continue; }   /* too close to the number of combinations */
@@ -398,7 +416,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
             k_ge_extract<<<grid, 256, 0, s>>>(D2, kc, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
                                               as<uint32_t>(ctx->dense_out), p, pinv);
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         }
         uint32_t *d_bad = as<uint32_t>(ctx->flags32) + 8;
         CU(cudaMemsetAsync(d_bad, 0, 4, s));
@@ -406,7 +424,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         dim3 vgrid(nrows_pad / kVerTile, (ncr + kVerTile - 1) / kVerTile);
         k_ge_verify<<<vgrid, 256, 0, s>>>(Dm, ld, nrows_pad, ncr, rank, as<uint32_t>(ctx->pivcol),
                                           as<uint32_t>(ctx->dense_out), p, pinv, two64, d_bad);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         uint32_t *h_bad = (uint32_t *)ctx->h_small.p + 128;
         CU(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
@@ -481,6 +499,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint32_t *d_err = as<uint32_t>(ctx->flags32);           /* [0] err, [1] changed, [2] max level */
     CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));
     CU(cudaMemsetAsync(d_err, 0, 64, s));
+    OK(ensure(ctx, ctx->refcnt, (size_t)kRefSlots * 32));
+    CU(cudaMemsetAsync(ctx->refcnt.p, 0, (size_t)kRefSlots * 32, s));
     const uint32_t *colmap = nullptr;
     if (by_lead) {
         OK(ensure(ctx, ctx->is_piv, ((size_t)nc + 2) * 4));
@@ -492,17 +512,17 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc);
         k_build_colmap<<<(nc + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->is_piv), as<uint32_t>(ctx->pividx), nc, npr,
                                                        as<uint32_t>(ctx->colmap), as<uint32_t>(ctx->invmap));
-        ctx->launches += 3;
+        note_launch(ctx, 3, __LINE__);
         colmap = as<uint32_t>(ctx->colmap);
     }
     if (npr) {
         k_pull_count<<<blocks_for_warps(npr), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf,
                                                            d.cf_bytes, npr, ncl, nc, colmap,
                                                            as<uint32_t>(ctx->col_cnt), d_err);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
     }
     k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->col_cnt), as<uint32_t>(ctx->col_ptr), nc);
-    ctx->launches++;
+    note_launch(ctx, 1, __LINE__);
     CU(cudaMemcpyAsync(h_small, as<uint32_t>(ctx->col_ptr) + nc, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h_small + 1, d_err, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
@@ -517,7 +537,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         k_pull_fill<<<blocks_for_warps(npr), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
                                                           npr, nc, p, colmap, as<uint32_t>(ctx->col_ptr),
                                                           as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent));
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
     }
 
     /* ---- 2. levels of the pivot columns ---- */
@@ -533,7 +553,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             if (g > gmax) g = gmax;
             k_level_flow<<<g, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), as<uint2>(ctx->ent), ncl,
                                            as<uint32_t>(ctx->level), d_err + 1, d_err);
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         }
         /* class histogram: slot 2l = long columns of level l, 2l+1 = short ones */
         OK(ensure(ctx, ctx->slots, ((size_t)kLenClasses * ncl + 8) * 4));
@@ -542,19 +562,19 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)kLenClasses * ncl + 8) * 4, s));
         k_level_count<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->level), as<uint32_t>(ctx->col_ptr), ncl,
                                                         as<uint32_t>(ctx->slots), d_err + 2);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         CU(cudaMemcpyAsync(h_small, d_err + 2, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
         nlev = h_small[0] + 1;
         const uint32_t nslots = kLenClasses * nlev;
         k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->slots), as<uint32_t>(ctx->slot_ptr), nslots);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         CU(cudaMemsetAsync(ctx->slots.p, 0, ((size_t)nslots + 1) * 4, s));  /* reuse as cursor */
         k_level_fill<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->level), as<uint32_t>(ctx->col_ptr), ncl,
                                                        as<uint32_t>(ctx->slot_ptr), as<uint32_t>(ctx->slots),
                                                        as<uint32_t>(ctx->order));
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         slot_ptr_h.resize(nslots + 1);
         OK(ensure_host(ctx, ctx->h_small, ((size_t)nslots + 16) * 4));
         h_small = (uint32_t *)ctx->h_small.p;
@@ -632,7 +652,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemcpyAsync(ctx->items.p, ctx->h_dense.p, (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
         k_flow_sched<<<(na + ncr + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->order), first, ncl, ncr,
                                                            as<uint32_t>(ctx->sched));
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         /* the staging buffer is reused for the result later: the copy must be done first */
         CU(cudaStreamSynchronize(s));
     }
@@ -646,7 +666,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         if (ncl) {
             k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), ncl, nc, g,
                                                                as<uint32_t>(ctx->flowflags));
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         }
         if (ctx->copy_pending) {                  /* the lower rows of a split host->device copy */
             CU(cudaStreamWaitEvent(s, ctx->ev_copy, 0));
@@ -664,7 +684,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             k_scatter_lower<<<blocks_for_warps((uint64_t)rows_here * kScatterSplit), 256, 0, s>>>(
                 m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes, nru, nrl, nc, p, c0, g, Rc, colmap,
                 as<uint32_t>(ctx->flowflags), as<uint32_t>(ctx->V), d_err);
-        ctx->launches++;
+        note_launch(ctx, 1, __LINE__);
         FlowArgs f;
         memset(&f, 0, sizeof(f));
         f.col_ptr = as<uint32_t>(ctx->col_ptr); f.ent = as<uint2>(ctx->ent);
@@ -678,8 +698,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.two64 = (uint32_t)(((~0ull) % p + 1) % p);
         f.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6);
         /* reference-equivalent unit count: pivots keyed by row index, true lower rows only */
-        f.piv_row_ptr = (!by_lead && !combos) ? m->row_ptr : nullptr;
-        f.ref_units = reinterpret_cast<unsigned long long *>(d_err + 12);
+        f.piv_row_ptr = (!by_lead && !combos && !getenv("F4LA_B200_NOUNITS")) ? m->row_ptr : nullptr;
+        f.ref_units = as<unsigned long long>(ctx->refcnt);
         CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
@@ -688,7 +708,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             dim3 grid(rba_words, g * (Rc / 128));
             k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
                                             as<uint32_t>(ctx->rba));
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         }
     }
     CU(cudaEventRecord(ctx->ev[2], s));
@@ -718,10 +738,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint64_t ref_units = 0, ref_apps = 0;
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
+        uint64_t *h_ref = (uint64_t *)((uint32_t *)ctx->h_small.p + 256);
         CU(cudaMemcpyAsync(h_err, d_err, 64, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_ref, ctx->refcnt.p, (size_t)kRefSlots * 32, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        memcpy(&ref_units, h_err + 12, 8);
-        memcpy(&ref_apps, h_err + 14, 8);
+        for (uint32_t k = 0; k < kRefSlots; ++k) { ref_units += h_ref[4 * k]; ref_apps += h_ref[4 * k + 1]; }
         if (*h_err)
             return fail(ctx, F4LA_ERR_CUDA, "device pipeline reported error bits 0x%x (4: column out of range in a lower "
                         "row, 16: dataflow watchdog expired)", *h_err);
@@ -749,13 +770,13 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             /* by_lead: the rows of A^-1 B are the NEGATED solve results */
             dim3 grid((ncr + 31) / 32, (nrl + 31) / 32), block(32, 8);
             k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, by_lead ? p : 0u, dense_dst);
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         } else if (rank) {
             dim3 grid(rank, (ncr + 255) / 256);
             k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
                                               dense_dst, p, pinv);
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
         }
         if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[0], s));
         uint32_t *h_dense = (uint32_t *)ctx->h_dense.p;
@@ -772,7 +793,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         if (by_lead) {
             OK(ensure(ctx, ctx->leads, (size_t)nrl * 4 + 16));
             k_lower_leads<<<(nrl + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, as<uint32_t>(ctx->leads));
-            ctx->launches++;
+            note_launch(ctx, 1, __LINE__);
             CU(cudaMemcpyAsync(h_invmap, ctx->invmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
         }
@@ -1016,6 +1037,8 @@ f4la_ctx *f4la_b200_create(int device)
     if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
     ctx->debug = dbg && atoi(dbg) != 0;
+    const char *dsy = getenv("F4LA_B200_SYNC");
+    ctx->debug_sync = dsy && atoi(dsy) != 0;
     const char *wd = getenv("F4LA_B200_WATCHDOG_MS");
     ctx->watchdog_ms = wd && atof(wd) > 0 ? atof(wd) : 20000.0;
     const char *tm = getenv("F4LA_B200_TMAX");
@@ -1033,7 +1056,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
     for (auto b : bufs) free_dev(*b);

@@ -492,7 +492,7 @@ struct FlowArgs {
     uint64_t        pinv;
     uint64_t        watchdog_ns; /* a wait for a source column longer than this sets kErrWatchdog */
     const uint64_t *piv_row_ptr; /* row_ptr of the pivot rows (pivot j = row j): row length = cost of one application; or NULL */
-    unsigned long long *ref_units; /* [0] += reference-equivalent coefficient applications, [1] += pivot applications; or NULL */
+    unsigned long long *ref_units; /* [kRefSlots][4]: [.][0] += reference-equivalent coefficient applications, [.][1] += pivot applications */
 };
 
 /* Ready words are polled with a relaxed, L1-bypassing load.  An acquire load would
@@ -535,6 +535,16 @@ __device__ __forceinline__ uint4 ld_cg_u4(const uint4 *ptr)
     return v;
 }
 
+/* Coefficient applications of the REFERENCE algorithm: a known pivot j is applied to every lower row with a
+ * non-zero multiplier V[j][r], at the cost of its row length (the reference counts len per application,
+ * la_ff_32.c:1214-1216).  Fire-and-forget reductions into kRefSlots x {units, applications} spread over
+ * separate 32-byte sectors (one address would serialise ~10^6 of them); the host adds the slots up.
+ * NOTE: the kernel must keep its single `return` inside the work loop -- with a flush after the loop (a second,
+ * predicated EXIT) ptxas 12.9 produced code that faulted at run time ("illegal instruction"). */
+constexpr uint32_t kRefSlots = 64;
+struct FlowArgs;
+__device__ __forceinline__ void count_ref_units(const FlowArgs &A, uint32_t j, uint32_t nnz);
+
 /* Entries [b0,b1) of one column in batches of 32; waits for every source. */
 template <int T, bool WIDE>
 __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_t *__restrict__ Vc,
@@ -560,7 +570,12 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                 __nanosleep(64);
                 f = ld_relaxed_flag(&flagc[en.x]);
                 ready = f >= kFlagAlwaysZ || (f >> 1) == A.epoch;
+#ifdef F4LA_OLD_WATCHDOG
+                if (++spins > kSpinLimit) { atomicOr(A.err, kErrWatchdog); ready = true; }
+                if (false) {
+#else
                 if ((++spins & 1023u) == 0) {        /* watchdog on wall time: never hang the GPU */
+#endif
                     const uint64_t now = global_timer_ns();
                     if (t_wait0 == 0) t_wait0 = now;
                     else if (now - t_wait0 > A.watchdog_ns) {
@@ -572,7 +587,9 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
         }
         /* relaxed polls + ONE fence per batch make the acquire pattern of the PTX memory model: the
          * producer's stores of V[src] (fence + st.release of the ready word) happen before the loads below */
+#ifndef F4LA_NO_FENCE
         __threadfence();
+#endif
         __syncwarp();
         /* Sources whose vector is entirely zero in this chunk contribute nothing:
          * the lower rows come clustered, 15-60 % of the (pivot, chunk) vectors are
@@ -616,6 +633,13 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
     }
 }
 
+__device__ __forceinline__ void count_ref_units(const FlowArgs &A, uint32_t j, uint32_t nnz)
+{
+    unsigned long long *slot = A.ref_units + (size_t)(j % kRefSlots) * 4;
+    atomicAdd(slot, (unsigned long long)nnz * (A.piv_row_ptr[j + 1] - A.piv_row_ptr[j]));
+    atomicAdd(slot + 1, (unsigned long long)nnz);
+}
+
 template <int T, bool WIDE>
 __global__ void __launch_bounds__(kSolveThreads, (T <= 2) ? F4LA_FLOW_OCC : 2)
 k_pull_flow(const FlowArgs A)
@@ -624,17 +648,12 @@ k_pull_flow(const FlowArgs A)
     __shared__ uint32_t s_id;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t total = A.n_items * A.G;
-    /* coefficient applications of the REFERENCE algorithm done by this thread's columns: a known pivot j
-     * is applied to every lower row with a non-zero multiplier V[j][r], at the cost of its row length
-     * (the reference counts len per application, la_ff_32.c:1214-1216) */
-    uint64_t ref_units = 0, ref_apps = 0;
-
     for (;;) {
         if (threadIdx.x == 0) s_id = atomicAdd(A.counter, 1u);
         __syncthreads();
         const uint32_t id = s_id;
         __syncthreads();
-        if (id >= total) break;
+        if (id >= total) return;
         const uint32_t chunk = id % A.G;
         const uint32_t it = A.items[id / A.G];
         const uint32_t pos = it >> 5, cnt = (it >> 1) & 15u;
@@ -671,7 +690,10 @@ k_pull_flow(const FlowArgs A)
                     nnz += (r.x != 0) + (r.y != 0) + (r.z != 0) + (r.w != 0);
                 }
                 if (!to_out) {
-                    if (A.piv_row_ptr) { ref_units += (uint64_t)nnz * (A.piv_row_ptr[j + 1] - A.piv_row_ptr[j]); ref_apps += nnz; }
+                    if (A.piv_row_ptr) {
+                        nnz = __reduce_add_sync(0xffffffffu, nnz);
+                        if (lane == 0 && nnz) count_ref_units(A, j, nnz);
+                    }
                     const bool any = __any_sync(0xffffffffu, nonzero != 0);
                     __threadfence();
                     __syncwarp();
@@ -712,20 +734,13 @@ k_pull_flow(const FlowArgs A)
             nonzero += v != 0;
         }
         if (!to_out) {
-            if (A.piv_row_ptr) { ref_units += (uint64_t)nonzero * (A.piv_row_ptr[j + 1] - A.piv_row_ptr[j]); ref_apps += nonzero; }
+            if (A.piv_row_ptr) {
+                const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)nonzero);
+                if (lane == 0 && cnt) count_ref_units(A, j, cnt);
+            }
             __threadfence();
             nonzero = __syncthreads_or(nonzero);
             if (threadIdx.x == 0) st_release(&flagc[j], (A.epoch << 1) | (nonzero ? 1u : 0u));
-        }
-    }
-    if (A.ref_units) {
-        for (int o = 16; o; o >>= 1) {
-            ref_units += __shfl_xor_sync(0xffffffffu, ref_units, o);
-            ref_apps += __shfl_xor_sync(0xffffffffu, ref_apps, o);
-        }
-        if (lane == 0 && ref_apps) {
-            atomicAdd(A.ref_units, (unsigned long long)ref_units);
-            atomicAdd(A.ref_units + 1, (unsigned long long)ref_apps);
         }
     }
 }
