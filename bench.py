@@ -1,27 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- F4 linear algebra over GF(p) on B200: mod-p Gop/s and LA seconds.
 
-Workload (BASELINE.json configs[1]): katsura-12 (13 variables, formula
+Workload (default, BASELINE.json configs[1]): katsura-12 (13 variables, formula
 convention) modulo the 31-bit prime 1073741827, degree-reverse-lex, `-l 2`:
-every linear-algebra matrix the F4 run builds (14 rounds).  One bench "step" =
-one pass of the hot path over all those matrices.
+every linear-algebra matrix the F4 run builds.  One bench "step" = one pass of
+the hot path over all those matrices.  `--workload cyclic-8 --prime 65521|251`,
+`--workload eco-14`, `--workload randquad-12` give the lines of configs 3 and 4.
 
   value : whole-job throughput with the matrices already resident in HBM
           (f4la_b200_reduce_resident), Gop/s = 2 * units / seconds where
           `units` is the REFERENCE algorithm's count of coefficient
           applications for the same matrices (its own counters at -t 1,
-          tests/golden/workload_katsura-12_t1.json; msolve.c:2666-2673).
-  e2e   : the same passes through f4la_b200_reduce() from pinned HOST buffers,
-          host->device copy of every matrix and device->host copy of every
-          result inside the timed region.
+          tests/golden/workload_*_t1.json; msolve.c:2666-2673).
+  e2e   : the same matrices through the PLUGIN POINTER the reference calls,
+          f4la_b200_linear_algebra(mat_t *, bs_t *, bs_t *, md_t *): gathering
+          the malloc()ed rows into staging, host->device copies, kernels,
+          device->host copy and materialisation of the result rows as neogb
+          rows are all inside the timed calls.  `e2e.flat_abi` keeps the number
+          of the flat C ABI (f4la_b200_reduce from pinned host arrays).
 
 The matrices are produced by running the unmodified reference F4 driver
-(oracle/_ref/libneogb_ref.so = reference neogb compiled as is) with its
-`linear_algebra` pointer set to the GPU backend -- the drop-in scenario -- and
+(oracle/_ref/libneogb_ref*.so = reference neogb compiled as is) with all five
+linear-algebra pointers set to the GPU backend -- the drop-in scenario -- and
 capturing what it hands to the backend.  Only this library's calls are timed.
 
   --impl reference : the reference's own CPU linear algebra (all host threads)
-                     on a bounded sample of the same matrices.
+                     on the IDENTICAL matrices, recorded from the reference's
+                     own F4 run.
+
+With --gpus N > 1 (torchrun, one rank per GPU) the headline becomes the metric
+north_star names for several GPUs: QQ primes/s of the multi-modular tracer
+application phase, a FIXED batch of primes sharded over the ranks, all host
+cores in use at every N, residues gathered with NCCL; the per-GPU replicas of
+the single-prime workload are reported under `replicas`.
 """
 from __future__ import annotations
 
@@ -37,22 +48,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# the reference's OpenMP row loops (and the adapter's gather of the rows): one thread per core, no migration.
+# Not under torchrun: every rank would bind its threads to the same first cores.
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
 import numpy as np  # noqa: E402
 
 P31 = 1073741827
-CPU_SAMPLE_UNITS = 4.5e10     # bounded CPU sample: rounds while cumulative reference units stay below
+CPU_SAMPLE_UNITS = 4.5e10     # cpu_baseline leg of the GPU arm: bounded sample of the step (about 10-30 s of CPU work)
+BYTES_PER_UNIT = {4: 8, 2: 6, 1: 5}      # 4 B column index + coefficient
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def load_workload_stats(system: str):
+def load_workload_stats(system: str, prime: int):
+    if prime != P31:
+        return None
     path = os.path.join(ROOT, "tests", "golden", f"workload_{system}_t1.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f)
     return None
+
+
+def golden_digest(system: str, prime: int):
+    import golden_io
+    return golden_io.gb_digests().get(f"{system}@{prime}")
 
 
 def measured_peaks():
@@ -71,7 +96,7 @@ class ClockSampler:
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index: int):
         self.index = index
@@ -100,44 +125,44 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, util, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
                 continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
+                if len(r) > 7:
+                    util.append(float(r[7]))
             except ValueError:
                 continue
             for k, nm in enumerate(names):
                 if r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "gpu_util_pct_mean": float(np.mean(util)) if util else None}
 
 
 def generate_workload(system_name: str, p: int, threads: int):
-    """Reference F4 driver + GPU backend; returns the captured LA inputs."""
+    """Reference F4 driver + GPU backend (all five LA pointers); returns the captured LA inputs,
+    the cold (first run of the process) and warm (second run) drop-in timings."""
     import gpu_helpers
     from msolve_b200 import systems
     from oracle import refharness as rh
     L = gpu_helpers.install_backend(mode=rh.MODE_RECORD_BACKEND)
+    assert rh.hooked_pointers() == 0b11111
     t0 = time.time()
     gb = rh.run_f4(systems.by_name(system_name, p), p, threads=threads, laopt=2)
-    f4_s = time.time() - t0
-    tot = gpu_helpers.neogb_totals(L)
+    cold = {"f4_seconds": time.time() - t0, "la_seconds": gb.la_seconds, "totals": gpu_helpers.neogb_totals(L)}
     recs = [r for r in rh.records() if r.kind == 0]
-    # second run in the same process, nothing recorded: the drop-in path in steady state
-    # (staging buffers already sized); this is the reference's own "F4 LA time" metric (st->la_rtime)
     rh.reset(); rh.set_mode(rh.MODE_BACKEND)
     t0 = time.time()
     gb2 = rh.run_f4(systems.by_name(system_name, p), p, threads=threads, laopt=2)
-    tot["warm_f4_seconds"] = time.time() - t0
-    tot["warm_la_seconds"] = gb2.la_seconds
-    tot["warm"] = gpu_helpers.neogb_totals(L)
+    warm = {"f4_seconds": time.time() - t0, "la_seconds": gb2.la_seconds, "totals": gpu_helpers.neogb_totals(L)}
     assert gb2.digest() == gb.digest()
     gpu_helpers.uninstall_backend()
-    return gb, recs, f4_s, tot
+    return gb, recs, cold, warm
 
 
 def reference_units(recs, stats):
@@ -151,6 +176,36 @@ def reference_units(recs, stats):
     return None, None
 
 
+def count_units(recs, stats, be):
+    units_per, src = reference_units(recs, stats)
+    if units_per is not None:
+        return units_per, src
+    total_nnz = sum(r.matrix.nnz for r in recs)
+    if total_nnz < 2.5e7:
+        from oracle import oracle
+        log("[bench] no committed reference unit counts for this workload: counting with the oracle restatement (CPU)")
+        return [float(oracle.reduce(r.matrix)[1]) for r in recs], "oracle restatement counters (identical to the reference's at -t 1)"
+    log("[bench] no committed reference unit counts for this workload: using the device's counters "
+        "(exact for the known pivots, the reference adds the applications of the new pivots)")
+    out = []
+    for r in recs:
+        rm = be.upload(r.matrix)
+        _, st = be.reduce_resident(rm, want_result=False)
+        rm.release()
+        out.append(float(st["units"]))
+    return out, "device counters: reference units of the reduction by the known pivots (lower bound of the reference's total)"
+
+
+def workload_label(args, n):
+    return f"{args.workload} mod {args.prime}, DRL, all {n} F4 linear-algebra matrices of the run (-l 2)"
+
+
+def metric_name(args):
+    if args.workload == "katsura-12" and args.prime == P31:
+        return "mod-p Gop/s, F4 linear algebra, katsura-12 mod 31-bit p"
+    return f"mod-p Gop/s, F4 linear algebra, {args.workload} mod {args.prime}"
+
+
 def run_gpu(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -162,33 +217,10 @@ def run_gpu(args, rank, world):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local),
-                                timeout=datetime.timedelta(seconds=180))
+                                timeout=datetime.timedelta(seconds=600))
     os.environ["F4LA_B200_DEVICE"] = str(local)
-
+    cpu = rh.host_cpu()
     host_threads = max(1, (os.cpu_count() or 8) // world)
-    log(f"[bench] rank {rank}: generating {args.workload} mod {args.prime} matrices (reference F4 driver + GPU backend)")
-    gb, recs, f4_s, tot = generate_workload(args.workload, args.prime, host_threads)
-    stats = load_workload_stats(args.workload) if args.prime == P31 else None
-    if stats:
-        assert gb.digest() == stats["digest"], "reduced Groebner basis differs from the reference's"
-        log(f"[bench] reduced GB bit-exact vs reference ({stats['nelts']} elements, {stats['nterms']} terms)")
-    units_per, units_src = reference_units(recs, stats)
-    if units_per is None:
-        from oracle import oracle
-        log("[bench] no committed reference unit counts for this workload: counting with the oracle (CPU)")
-        units_per = [float(oracle.reduce(r.matrix)[1]) for r in recs]
-        units_src = "oracle restatement counters"
-    units = float(sum(units_per))
-    log(f"[bench] {len(recs)} matrices, {units:.4g} reference units; F4 with GPU LA took {f4_s:.1f} s "
-        f"(LA {tot['ms_total'] / 1e3:.2f} s: flatten {tot['ms_flatten'] / 1e3:.2f} h2d {tot['ms_h2d'] / 1e3:.2f} "
-        f"prep {tot['ms_prep'] / 1e3:.2f} reduce {tot['ms_reduce'] / 1e3:.2f} echelon {tot['ms_echelon'] / 1e3:.2f} "
-        f"d2h {tot['ms_d2h'] / 1e3:.2f} materialize {tot['ms_materialize'] / 1e3:.2f})")
-
-    be = Backend(local)
-    mats = [r.matrix for r in recs]
-    pinned = [be.pin(m) for m in mats]
-    resident = [be.upload(m) for m in mats]
-    h2d_bytes = sum(int(m.row_ptr.nbytes + m.cols.nbytes + m.row_cf.nbytes + m.cf_ptr.nbytes + m.cf.nbytes) for m in mats)
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,24 +228,57 @@ def run_gpu(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    log(f"[bench] rank {rank}: generating {args.workload} mod {args.prime} matrices (reference F4 driver + GPU backend, "
+        f"{host_threads} host threads)")
+    gb, recs, cold, warm = generate_workload(args.workload, args.prime, host_threads)
+    want = golden_digest(args.workload, args.prime)
+    if want:
+        assert gb.digest() == want["digest"], "reduced Groebner basis differs from the reference's"
+        log(f"[bench] reduced GB bit-exact vs the unmodified reference ({want['nelts']} elements, {want['nterms']} terms)")
+    be = Backend(local)
+    stats = load_workload_stats(args.workload, args.prime)
+    units_per, units_src = count_units(recs, stats, be)
+    units = float(sum(units_per))
+    ct, wt = cold["totals"], warm["totals"]
+    log(f"[bench] {len(recs)} matrices, {units:.4g} reference units; F4 with GPU LA: first run {cold['f4_seconds']:.1f} s "
+        f"(LA {cold['la_seconds']:.3f} s), second run {warm['f4_seconds']:.1f} s (LA {warm['la_seconds']:.3f} s: "
+        f"flatten {wt['ms_flatten'] / 1e3:.3f} h2d {wt['ms_h2d'] / 1e3:.3f} prep {wt['ms_prep'] / 1e3:.3f} "
+        f"reduce {wt['ms_reduce'] / 1e3:.3f} echelon {wt['ms_echelon'] / 1e3:.3f} d2h {wt['ms_d2h'] / 1e3:.3f} "
+        f"materialize {wt['ms_materialize'] / 1e3:.3f})")
+
+    mats = [r.matrix for r in recs]
+    cf_bytes = mats[0].cf_bytes
+    pinned = [be.pin(m) for m in mats]
+    resident = [be.upload(m) for m in mats]
+    in_bytes = sum(int(m.row_ptr.nbytes + m.cols.nbytes + m.row_cf.nbytes + m.cf_ptr.nbytes + m.cf.nbytes) for m in mats)
+
+    KEYS_V = ("ms_prep", "ms_reduce", "ms_echelon", "ms_d2h", "kernel_launches", "bytes_d2h", "ms_hot_kernel",
+              "hot_kernel_launches", "units", "dense_macs")
+
     def pass_resident():
-        agg = {"ms_prep": 0.0, "ms_reduce": 0.0, "ms_echelon": 0.0, "ms_d2h": 0.0, "kernel_launches": 0, "bytes_d2h": 0,
-               "ms_hot_kernel": 0.0, "hot_kernel_launches": 0, "units": 0, "dense_macs": 0}
+        agg = dict.fromkeys(KEYS_V, 0.0)
         for rm in resident:
             _, st = be.reduce_resident(rm, want_result=False)
             for k in agg:
                 agg[k] += st[k]
         return agg
 
-    def pass_host():
+    def pass_flat():
         agg = {"ms_h2d": 0.0, "kernel_launches": 0, "bytes_d2h": 0, "bytes_h2d": 0}
-        digests = []
+        outs = []
         for pm in pinned:
             out, st = be.reduce(pm.matrix)
             for k in agg:
                 agg[k] += st[k]
-            digests.append(out)
-        return agg, digests
+            outs.append(out)
+        return agg, outs
 
     if args.per_matrix:
         for r, rm, u in zip(recs, resident, units_per):
@@ -223,10 +288,11 @@ def run_gpu(args, rank, world):
             log(f"[bench]   {m.nru:7d}+{m.nrl:5d} x {m.ncl:7d}+{m.ncr:5d} nnz {m.nnz:9d} units {u:10.3g} rank {st['rank']:4d} "
                 f"launches {st['kernel_launches']:5d} | prep {st['ms_prep']:8.2f} reduce {st['ms_reduce']:8.2f} "
                 f"echelon {st['ms_echelon']:8.2f} d2h {st['ms_d2h']:6.2f} total {st['ms_total']:8.2f} ms | "
-                f"{u * 8 / max(st['ms_reduce'], 1e-9) / 1e6:7.1f} GB/s-equiv dense-macs {st['dense_macs']:.3g} ref-units(known pivots) {st['units']:.4g}")
+                f"dense-macs {st['dense_macs']:.3g} ref-units(known pivots) {st['units']:.4g}")
 
-    # parity of what is being timed: the results of the host path against the reference's rows
-    _, outs = pass_host()
+    # what is timed returns the rows the drop-in run produced (whose final basis equals the reference's);
+    # per-matrix parity against the reference's own rows is tests/test_gpu_configs.py
+    _, outs = pass_flat()
     for o, r in zip(outs, recs):
         assert o.same_rows(r.result)
 
@@ -243,19 +309,43 @@ def run_gpu(args, rank, world):
         el = time.perf_counter() - t0
         barrier()
         clocks = sampler.stop() if rank == 0 else None
-        if world > 1:
-            t = torch.tensor([el], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
+        el = max_over_ranks(el)
         log(f"[bench] rank {rank} {label}: {el / args.steps * 1e3:.1f} ms/step")
         return el, aggs, clocks
 
     el_v, aggs_v, clocks = timed(pass_resident, "device-resident")
-    el_e, aggs_e, _ = timed(lambda: pass_host()[0], "host buffers (e2e)")
+    el_f, aggs_f, _ = timed(lambda: pass_flat()[0], "flat C ABI from pinned host buffers")
+
+    # ---- e2e: the plugin pointer on mat_t (what msolve calls) ----
+    import ctypes as C
+    import gpu_helpers
+    Lib = gpu_helpers.install_backend()
+    la_fn = C.cast(Lib.f4la_b200_linear_algebra, C.c_void_p).value
+
+    def pass_plugin(check=False):
+        sec = 0.0
+        for r in recs:
+            out, _, _ = rh.call_entry(r.matrix, 0, la_fn, threads=host_threads)   # builds mat_t/bs_t/md_t, calls, reads back
+            sec += rh.last_side()["call_seconds"]                               # wall time of the pointer call alone
+            if check:
+                assert out.same_rows(r.result)
+        return sec
+
+    pass_plugin(check=True)
+    for _ in range(max(0, args.warmup - 1)):
+        pass_plugin()
+    gpu_helpers.neogb_totals(Lib)
+    barrier()
+    plugin_secs = [pass_plugin() for _ in range(args.steps)]
+    barrier()
+    pt = gpu_helpers.neogb_totals(Lib)
+    gpu_helpers.uninstall_backend()
+    sec_e = max_over_ranks(float(np.mean(plugin_secs)))
+    log(f"[bench] rank {rank} plugin pointer on mat_t (e2e): {sec_e * 1e3:.1f} ms/step")
 
     # the reference's -l 44 semantics on the same matrices: random row combinations (F4LA_FLAG_PROBABILISTIC)
     prob = None
-    if not args.no_prob:
+    if not args.no_prob and args.prime > 32768:
         from msolve_b200.flat import FLAG_PROBABILISTIC
         for rm in resident:
             rm.release()
@@ -274,17 +364,18 @@ def run_gpu(args, rank, world):
         for m in mats:
             m.flags = 0
 
-    # the matrices are not needed any more
+    mac_peak = be.measure_mac_peak(200.0)
     for rm in resident:
         rm.release()
     for pm in pinned:
         pm.free()
     be.close()
+
     qq = None
     if not args.no_qq:
         try:
-            qq = run_qq(args, rank, world, local, dist, torch)
-        except Exception as e:          # the headline number must survive a failure of the extra block
+            qq = run_qq(args, rank, world, local, dist, torch, cpu)
+        except Exception as e:          # the single-prime numbers must survive a failure of the QQ block
             qq = {"error": repr(e)}
             log(f"[bench] rank {rank}: QQ block failed: {e!r}")
 
@@ -294,86 +385,98 @@ def run_gpu(args, rank, world):
         return
 
     steps = args.steps
-    sec_v = el_v / steps
-    sec_e = el_e / steps
-    gops_v = 2.0 * units * world / sec_v / 1e9
-    gops_e = 2.0 * units * world / sec_e / 1e9
-    ms_reduce = sum(a["ms_reduce"] for a in aggs_v) / steps
+    sec_v, sec_f = el_v / steps, el_f / steps
+    gops = lambda s: 2.0 * units * world / s / 1e9                                         # noqa: E731
     ms_hot = sum(a["ms_hot_kernel"] for a in aggs_v) / steps
     n_hot = sum(a["hot_kernel_launches"] for a in aggs_v) / steps
     dense_macs = sum(a["dense_macs"] for a in aggs_v) / steps
+    known_units = sum(a["units"] for a in aggs_v) / steps
     peak, peak_src = measured_peaks()
-    bytes_per_unit = 8
-    # algorithmic bytes of all launches of the hot kernel in a step / their summed duration
-    # (= the launch-weighted average of bytes-per-launch / launch-duration)
-    achieved = units * bytes_per_unit / (ms_hot / 1e3) / 1e9
-    launches = sum(a["kernel_launches"] for a in aggs_v) + sum(a["kernel_launches"] for a in aggs_e)
+    bpu = BYTES_PER_UNIT[cf_bytes]
+    achieved = units * bpu / (ms_hot / 1e3) / 1e9 if ms_hot > 0 else 0.0
+    launches = (sum(a["kernel_launches"] for a in aggs_v) + sum(a["kernel_launches"] for a in aggs_f)
+                + pt["kernel_launches"])
 
-    # CPU baseline on a bounded sample of the same matrices (reference code, all host threads)
-    cpu = cpu_baseline(recs, units_per, os.cpu_count() or 1, 1)
+    cpu_base = None
+    if world == 1 and not args.no_cpu:
+        cpu_base = cpu_baseline(recs, units_per, os.cpu_count() or 1, 3, cpu)
 
-    line = {
-        "metric": "mod-p Gop/s, F4 linear algebra, katsura-12 mod 31-bit p" if args.workload == "katsura-12"
-                  else f"mod-p Gop/s, F4 linear algebra, {args.workload}",
-        "value": gops_v, "unit": "Gop/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": sec_v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 residues, u64 accumulators (exact)", "data": "synthetic (formula-generated system)",
-        "config": {"workload": f"{args.workload} mod {args.prime}, DRL, all {len(recs)} F4 linear-algebra matrices of the run (-l 2)",
-                   "units_per_step": units, "units_source": units_src,
-                   "largest_matrix": max(((r.matrix.nru + r.matrix.nrl, r.matrix.ncl + r.matrix.ncr) for r in recs)),
-                   "cache": "inputs larger than L2 (%.2f GB per step), no flush" % (h2d_bytes / 1e9),
-                   "multi_gpu": "replicas only (one prime field F4 does not shard); each rank runs the full workload"},
+    roofline = {
+        # what binds the kernel (ncu, profiles/): L2 -> SM vector traffic and the issue rate of the multiplier
+        # pipe, not HBM; `achieved / peak / frac` keep the contract's definition on the survey's yardstick
+        # (reference units x algorithmic bytes / kernel time vs the measured HBM copy peak) and can exceed 1
+        # because the restructured kernel keeps the vectors in L2 and moves far fewer DRAM bytes
+        "bound": "l2+imad", "kernel": "k_pull_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "frac_survey_yardstick": achieved / peak,
+        "traffic": 2.36e10 if args.workload == "katsura-12" else None,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (largest matrix), "
+                          "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv; algorithmic bytes of that launch 3.2e11",
+        "binding": {"pipe": "IMAD.WIDE issue (fmaheavy pipe)", "peak_mac_per_s": mac_peak,
+                    "peak_source": "f4la_b200_measure_mac_peak(): 96-bit multiply-accumulate with register operands, "
+                                   "measured in this run on this GPU",
+                    "dense_macs_per_step": dense_macs, "achieved_mac_per_s": dense_macs / (ms_hot / 1e3) if ms_hot else None,
+                    "frac_nominal": dense_macs / (ms_hot / 1e3) / mac_peak if ms_hot and mac_peak else None,
+                    "note": "dense_macs counts every (pull-list entry, lower row) pair, the all-zero source vectors the "
+                            "kernel skips included: the executed fraction is lower",
+                    "l2": {"ncu_bytes_per_launch": 2.30e11, "ncu_TB_per_s": 14.3,
+                           "source": "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv (lts__t_sectors_srcunit_tex_op_read)"}},
+        "peak_source": peak_src, "bytes_per_unit": bpu, "launches_per_step": n_hot, "kernel_ms_per_step": ms_hot,
+        "algorithmic_bytes_per_launch": units * bpu / max(n_hot, 1), "ms_per_launch": ms_hot / max(n_hot, 1),
+        "reference_units_known_pivots_counted_on_device": known_units,
+    }
+    single = {
+        "metric": metric_name(args), "value": gops(sec_v), "unit": "Gop/s", "ms_per_step": sec_v * 1e3,
         "la_seconds": sec_v,
         "phases_ms": {k: sum(a[k] for a in aggs_v) / steps for k in ("ms_prep", "ms_reduce", "ms_echelon", "ms_d2h")},
-        "e2e": {"value": gops_e, "unit": "Gop/s", "la_seconds": sec_e,
-                "h2d_bytes_per_step": int(sum(a["bytes_h2d"] for a in aggs_e) / steps),
-                "d2h_bytes_per_step": int(sum(a["bytes_d2h"] for a in aggs_e) / steps)},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_pull_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch: first group (15 of 20
-                     # row chunks) of the largest matrix, profiles/r01_ncu_full_k_pull_flow_v5_raw.csv; the
-                     # algorithmic bytes of that launch are 5.34e10 units x 8 B x 15/20 = 3.2e11
-                     "traffic": 2.36e10,
-                     # what actually bounds the kernel: the multiplier pipe.  One 31 x 31 -> 96-bit multiply-add
-                     # is one IMAD.WIDE.U32 (+ half an add-with-carry): 8.1e12/s measured on this GPU
-                     # (tools/ubench/imad_wide.cu, profiles/README.md).  "dense_macs" counts every (pull-list
-                     # entry, lower row) pair, including the all-zero source vectors the kernel skips.
-                     "pipe": {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "peak_mac_per_s": 8.1e12,
-                              "dense_macs_per_step": dense_macs,
-                              "achieved_mac_per_s": dense_macs / (ms_hot / 1e3),
-                              "frac": dense_macs / (ms_hot / 1e3) / 8.1e12},
-                     # L2 -> SM traffic of the same capture (every multiply-add needs its own 4-byte vector element):
-                     # 7.18e9 sectors x 32 B in 16.1 ms = 14 TB/s, about the chip's L2 ceiling -- but cutting that
-                     # traffic (column groups sharing vector loads) did not help: the kernel is bound by
-                     # instruction issue on the multiplier-pipe path
-                     "l2": {"ncu_bytes_per_launch": 2.30e11, "ncu_TB_per_s": 14.3,
-                            "source": "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv (lts__t_sectors_srcunit_tex_op_read)"},
-                     "peak_source": peak_src, "bytes_per_unit": bytes_per_unit,
-                     "launches_per_step": n_hot, "kernel_ms_per_step": ms_hot,
-                     "algorithmic_bytes_per_launch": units * bytes_per_unit / max(n_hot, 1),
-                     "ms_per_launch": ms_hot / max(n_hot, 1),
-                     "note": "the kernel is restructured (transposed solve, vectors L2-resident): it moves far fewer "
-                             "DRAM bytes than the reference algorithm's 8 B per coefficient application; the fraction "
-                             "uses the survey's yardstick (reference units x 8 B / kernel time / measured HBM copy peak) "
-                             "and can exceed 1"},
-        "cpu_baseline": cpu,
-        "f4_total_seconds_with_gpu_la": f4_s,
-        "f4_drop_in": {"what": "whole reference F4 run with all LA pointers on the GPU backend, second run in the process",
-                       "f4_seconds": tot["warm_f4_seconds"], "la_seconds": tot["warm_la_seconds"],
-                       "la_breakdown_ms": {k: tot["warm"][k] for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce",
-                                                                       "ms_echelon", "ms_d2h", "ms_materialize")},
-                       "host_threads": host_threads},
-        "probabilistic": prob,
-        "qq": qq,
     }
+    e2e = {"value": gops(sec_e), "unit": "Gop/s", "la_seconds": sec_e,
+           "what": "f4la_b200_linear_algebra(mat_t*, bs_t*, bs_t*, md_t*) on reference-built matrices: row gather, "
+                   "H2D, kernels, D2H and materialisation of neogb rows inside the timed calls (sum of the wall clock "
+                   "of the pointer calls of a step; building mat_t between calls is the F4 driver's job)",
+           "h2d_bytes_per_step": int(pt["bytes_h2d"] / steps), "d2h_bytes_per_step": int(pt["bytes_d2h"] / steps),
+           "breakdown_ms_per_step": {k: pt[k] / steps for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce",
+                                                                 "ms_echelon", "ms_d2h", "ms_materialize")},
+           "host_threads": host_threads,
+           "flat_abi": {"value": gops(sec_f), "unit": "Gop/s", "la_seconds": sec_f,
+                        "what": "f4la_b200_reduce() from pinned flat arrays",
+                        "h2d_bytes_per_step": int(sum(a["bytes_h2d"] for a in aggs_f) / steps),
+                        "d2h_bytes_per_step": int(sum(a["bytes_d2h"] for a in aggs_f) / steps)},
+           "cold_first_f4_run": {"what": "first F4 run of the process (what a one-shot msolve process pays): CUDA context, "
+                                         "module load, first staging / device allocations included",
+                                 "f4_seconds": cold["f4_seconds"], "la_seconds": cold["la_seconds"],
+                                 "la_breakdown_ms": {k: ct[k] for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce",
+                                                                        "ms_echelon", "ms_d2h", "ms_materialize")}},
+           "warm_f4_run": {"f4_seconds": warm["f4_seconds"], "la_seconds": warm["la_seconds"]}}
+    config = {"workload": workload_label(args, len(recs)), "units_per_step": units, "units_source": units_src,
+              "largest_matrix": max(((r.matrix.nru + r.matrix.nrl, r.matrix.ncl + r.matrix.ncr) for r in recs)),
+              "cache": "inputs larger than L2 (%.2f GB per step), no flush" % (in_bytes / 1e9)
+                       if in_bytes > 2.6e8 else "L2 flushed by the working set of the step: %.2f GB of inputs plus the "
+                       "vector blocks written by every call" % (in_bytes / 1e9),
+              "host_cpu": cpu}
+    line = {"n_gpus": world, "steps": steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+            "dtype": "u32 residues, 96-bit accumulators (exact)" if cf_bytes == 4 else "u32 residues, u64 accumulators (exact)",
+            "data": "synthetic (formula-generated system)", "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_base, "probabilistic": prob}
+    if world == 1 or qq is None or "error" in qq:
+        config["multi_gpu"] = "replicas only for one prime field (an F4 run does not shard); QQ primes shard, see `qq`"
+        line.update(single)
+        line.update({"scaling": "weak", "config": config, "e2e": e2e, "qq": qq})
+    else:
+        # several GPUs: the axis north_star names is the QQ multi-modular loop
+        config["workload"] = qq["workload"]
+        config["multi_gpu"] = "primes of the QQ tracer application phase sharded over the ranks (one GPU each), residues " \
+                              "all-gathered with NCCL; `replicas` = the single-prime workload run independently on every GPU"
+        line.update({"metric": qq["metric"], "value": qq["value"], "unit": "primes/s", "ms_per_step": qq["seconds"] * 1e3,
+                     "scaling": "strong", "config": config,
+                     "e2e": {"value": qq["value"], "unit": "primes/s", "what": qq["what"],
+                             "h2d_bytes_per_step": qq["h2d_bytes"], "d2h_bytes_per_step": qq["d2h_bytes"]},
+                     "qq": qq, "replicas": dict(single, e2e=e2e, scaling="weak")})
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-SAMPLE_FIRST = 9    # the bounded sample is drawn from the first rounds of the run
+SAMPLE_FIRST = 9    # the bounded sample of the cpu_baseline leg is drawn from the first rounds of the run
 
 
 def cpu_sample(recs, units_per):
@@ -386,30 +489,31 @@ def cpu_sample(recs, units_per):
     return idx, cum
 
 
-def run_qq(args, rank, world, local, dist, torch):
-    """QQ multi-modular tracer loop (BASELINE config 5): learn once, then replay the
-    trace for independent primes.  Primes are sharded over the ranks (GPU = rank),
-    every rank drives its GPU with a fixed number of host threads; the only
-    collective is the gather of the per-prime results (here: 64-bit digests of the
-    modular bases; msolve gathers residues for CRT, msolve.c:2694-2712)."""
+def run_qq(args, rank, world, local, dist, torch, cpu):
+    """QQ multi-modular tracer loop (BASELINE config 5; msolve.c:1628-1632 learn, :1815-1824 apply): learn once,
+    then replay the trace for a FIXED batch of independent primes.  Primes are sharded over the ranks (GPU = rank);
+    every rank drives its GPU with its share of ALL host cores (cpu_count / world threads), so the host resources
+    are the same at every N.  The collective is the all-gather of the residues (coefficients of every modular
+    basis), the payload msolve lifts by CRT on the host (msolve.c:2694-2712)."""
     import gpu_helpers
-    from msolve_b200 import systems
+    from msolve_b200 import sharding, systems
     from oracle import refharness as rh
     system = systems.by_name(args.qq_system)
-    threads = max(1, (os.cpu_count() or 8) // 8)          # fixed per GPU, whatever N is
-    per_rank = args.qq_primes_per_thread * threads
-    all_primes = rh.primes_above(1 << 30, 1 + per_rank * world)
-    from msolve_b200 import sharding
-    p0, mine = all_primes[0], sharding.shard(all_primes[1:], rank, world)[:per_rank]
-    # every rank always reaches the collectives below, whatever happens locally
-    local_err, res, learn, tot = None, [], {"seconds": 0.0, "nelts": 0}, {"ms_total": 0.0}
+    ncpu = os.cpu_count() or 8
+    threads = max(1, ncpu // world)
+    batch = args.qq_primes
+    all_primes = rh.primes_above(1 << 30, 1 + batch + world * threads)
+    p0 = all_primes[0]
+    warm_primes = sharding.shard(all_primes[1 + batch:], rank, world)
+    mine = sharding.shard(all_primes[1:1 + batch], rank, world)
+    local_err, res, resid, learn, tot = None, [], None, {"seconds": 0.0, "nelts": 0, "nterms": 0}, {"ms_total": 0.0}
     L = gpu_helpers.install_backend()
     try:
         rh.qq_setup(system, threads=threads)
         learn = rh.qq_learn(p0)
         assert learn["rc"] == 0
         # ngpus=0: every host thread of this rank uses the rank's own GPU ($F4LA_B200_DEVICE)
-        rh.qq_apply(mine[:threads], threads=threads, ngpus=0)    # warm-up
+        rh.qq_apply(warm_primes[:threads], threads=threads, ngpus=0)    # warm-up: contexts, staging, allocations
         gpu_helpers.neogb_totals(L)
     except Exception as e:
         local_err = repr(e)
@@ -417,19 +521,23 @@ def run_qq(args, rank, world, local, dist, torch):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     t0 = time.perf_counter()
     if local_err is None:
         try:
-            res, wall = rh.qq_apply(mine, threads=threads, ngpus=0)
+            res, wall, resid = rh.qq_apply(mine, threads=threads, ngpus=0, residue_words=learn["nterms"])
             assert all(r["err"] == 0 and r["nelts"] == learn["nelts"] for r in res)
         except Exception as e:
             local_err, res = repr(e), []
+    if resid is None or local_err is not None:
+        resid = np.zeros((0, max(1, learn["nterms"])), dtype=np.uint32)
     torch.cuda.set_device(local)
-    # NCCL all-gather of the per-prime results (msolve: residues for CRT on the host)
-    parts = sharding.gather_uint64([r["digest"] for r in res], dist if world > 1 else None,
-                                  device=torch.device("cuda", local))
+    gathered = sharding.gather_residues(resid, dist if world > 1 else None, device=torch.device("cuda", local))
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
+    util = sampler.stop() if rank == 0 else None
     try:
         tot = gpu_helpers.neogb_totals(L)
     finally:
@@ -438,29 +546,42 @@ def run_qq(args, rank, world, local, dist, torch):
         t = torch.tensor([el], device=torch.device("cuda", local), dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         el = float(t.item())
-    done = sum(len(x) for x in parts)
-    if local_err is not None or done != per_rank * world:
-        return {"error": local_err or f"only {done} of {per_rank * world} primes completed"}
-    out = {"metric": "QQ primes/s (F4 tracer application phase)", "system": f"{args.qq_system} over QQ",
-           "value": per_rank * world / el, "unit": "primes/s", "n_gpus": world, "primes": per_rank * world,
-           "host_threads_per_gpu": threads, "seconds": el, "scaling": "weak",
-           "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"],
-           "la_share_of_host_thread_time": tot["ms_total"] / 1e3 / max(1e-9, sum(r["seconds"] for r in res)),
+    if local_err is not None or gathered.shape[0] != batch:
+        return {"error": local_err or f"only {gathered.shape[0]} of {batch} primes completed"}
+    # the gathered residues of this rank's primes are the ones it computed
+    for j, r in enumerate(res):
+        assert rh.residue_digest(gathered[rank + j * world]) == rh.residue_digest(resid[j])
+    host_sec = max(1e-9, sum(r["seconds"] for r in res))
+    out = {"metric": "QQ primes/s (F4 tracer application phase)",
+           "workload": f"{args.qq_system} over QQ, tracer application phase, fixed batch of {batch} primes above 2^30",
+           "what": "per prime: the reference's F4 replay on the host (matrix construction from the trace) with every "
+                   "linear-algebra call on the GPU through the plugin pointer; residues of all primes all-gathered",
+           "value": batch / el, "unit": "primes/s", "n_gpus": world, "primes": batch,
+           "host_threads_per_gpu": threads, "host_threads_total": threads * world, "seconds": el, "scaling": "strong",
+           "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": learn["nterms"],
+           "gathered_bytes": int(gathered.nbytes),
+           "h2d_bytes": int(tot.get("bytes_h2d", 0)), "d2h_bytes": int(tot.get("bytes_d2h", 0)),
+           "la_share_of_host_thread_time": tot["ms_total"] / 1e3 / host_sec,
            "la_ms_per_prime": tot["ms_total"] / max(1, len(res)),
-           "collective": "nccl all_gather of per-prime results" if world > 1 else "none (1 GPU)"}
+           "gpu0_util_pct_mean": util.get("gpu_util_pct_mean") if util else None,
+           "collective": "nccl all_gather of the residues (uint32 [primes, words])" if world > 1 else "none (1 GPU)",
+           "note": "the loop is bound by the host part of every prime (symbolic matrix construction, single threaded per "
+                   "prime in the reference, msolve.c:1815-1824); linear algebra is a few per cent of a prime's time once "
+                   "it runs on the GPU"}
     if rank == 0 and not args.no_qq_cpu:
         rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
-        rh.qq_setup(system, threads=os.cpu_count() or 1)
+        rh.qq_setup(system, threads=ncpu)
         rh.qq_learn(p0)
-        ncpu = os.cpu_count() or 1
-        sample = all_primes[1:1 + 2 * ncpu]
+        sample = all_primes[1:1 + min(batch, 4 * ncpu)]
+        rh.qq_apply(sample[:ncpu], threads=ncpu)
         _, wall_cpu = rh.qq_apply(sample, threads=ncpu)
         out["cpu_baseline"] = {"value": len(sample) / wall_cpu, "unit": "primes/s", "cores": ncpu, "kind": "reference",
-                               "sample": f"{len(sample)} primes, reference core_gba apply, one prime per thread"}
+                               "host_cpu": cpu,
+                               "sample": f"{len(sample)} primes of the same batch, reference core_gba apply, one prime per thread"}
     return out
 
 
-def cpu_baseline(recs, units_per, threads, repeats):
+def cpu_baseline(recs, units_per, threads, repeats, cpu):
     from oracle import refharness as rh
     idx, cum = cpu_sample(recs, units_per)
     best = None
@@ -472,54 +593,79 @@ def cpu_baseline(recs, units_per, threads, repeats):
             sec += s
         best = sec if best is None else min(best, sec)
     return {"value": 2.0 * cum / best / 1e9, "unit": "Gop/s", "cores": threads, "kind": "reference",
-            "la_seconds": best,
-            "sample": f"{len(idx)} of {len(recs)} matrices of the same run ({cum:.3g} of the step's units), "
-                      f"reference exact_sparse_linear_algebra_ff_32 via dispatch_linear_algebra, -l 2"}
+            "la_seconds": best, "repeats": repeats, "host_cpu": cpu,
+            "simd": "AVX-512" if rh.selected_lib_path().endswith("avx512.so") else "AVX2",
+            "sample": f"{len(idx)} of {len(recs)} matrices of the same run ({cum:.3g} of the step's units), best of {repeats}, "
+                      f"reference exact_sparse_linear_algebra_ff_* via dispatch_linear_algebra, -l 2, "
+                      f"OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')} OMP_PLACES={os.environ.get('OMP_PLACES')}"}
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU LA on a bounded sample, all host threads."""
+    """Reference arm: the reference's own CPU linear algebra on the IDENTICAL workload -- every LA matrix of its own
+    F4 run -- with all host threads.  A step is one pass over all matrices; when K passes do not fit the time budget
+    fewer are timed (the line says how many), the workload is never cut."""
     if rank != 0:
         return
     from msolve_b200 import systems
     from oracle import refharness as rh
     threads = os.cpu_count() or 1
-    log(f"[bench] reference arm: recording the first {SAMPLE_FIRST} {args.workload} matrices with the reference itself "
-        f"({threads} threads; the reference F4 has to run to completion)")
-    stats = load_workload_stats(args.workload) if args.prime == P31 else None
-    rh.reset(); rh.set_mode(rh.MODE_RECORD, SAMPLE_FIRST)
-    t0 = time.time()
+    cpu = rh.host_cpu()
+    log(f"[bench] reference arm: recording the {args.workload} mod {args.prime} matrices with the reference itself "
+        f"({threads} threads, {cpu['model']}, {'AVX-512' if rh.selected_lib_path().endswith('avx512.so') else 'AVX2'} build)")
+    t_begin = time.time()
+    stats = load_workload_stats(args.workload, args.prime)
+    rh.reset(); rh.set_mode(rh.MODE_RECORD)
     gb = rh.run_f4(systems.by_name(args.workload, args.prime), args.prime, threads=threads, laopt=2)
     recs = [r for r in rh.records() if r.kind == 0]
     rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
-    if stats:
-        assert gb.digest() == stats["digest"]
-    log(f"[bench] reference F4 run took {time.time() - t0:.1f} s, {len(recs)} matrices kept")
-    units_per = [r.units for r in recs]
-    if stats:
-        ref_rounds = [r for r in stats["rounds"] if r["kind"] == 0][:len(recs)]
-        units_per = [float(r["units"]) for r in ref_rounds]       # -t 1 counters are exact, threaded ones race
-    idx, cum = cpu_sample(recs, units_per)
-    for _ in range(args.warmup):
-        for i in idx[:2]:
-            rh.reference_la(recs[i].matrix, laopt=2, threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for i in idx:
-            rh.reference_la(recs[i].matrix, laopt=2, threads=threads)
-    el = (time.perf_counter() - t0) / args.steps
-    gops = 2.0 * cum / el / 1e9
+    want = golden_digest(args.workload, args.prime)
+    if want:
+        assert gb.digest() == want["digest"]
+    f4_s = time.time() - t_begin
+    log(f"[bench] reference F4 run took {f4_s:.1f} s (LA {gb.la_seconds:.1f} s inside F4), {len(recs)} matrices")
+    units_per, units_src = reference_units(recs, stats)
+    if units_per is None:
+        if args.prime >= 65536:
+            units_per = [r.units for r in recs]        # the reference's counters of the recording run (racy with threads)
+            units_src = f"reference counters of the recording run at -t {threads} (the counters race between threads)"
+        else:
+            from oracle import oracle
+            units_per = [float(oracle.reduce(r.matrix)[1]) for r in recs]
+            units_src = "oracle restatement counters (identical to the reference's at -t 1)"
+    units = float(sum(units_per))
+
+    def one_pass():
+        sec = 0.0
+        for r in recs:
+            _, s, _, _ = rh.reference_la(r.matrix, laopt=2, threads=threads)
+            sec += s
+        return sec
+
+    t0 = time.time()
+    first = one_pass()                                  # full warm-up pass over the whole workload
+    per_pass_wall = time.time() - t0
+    budget = args.ref_budget_s - (time.time() - t_begin)
+    warm_extra = max(0, min(args.warmup - 1, int(budget / max(per_pass_wall, 1e-6)) - 1))
+    for _ in range(warm_extra):
+        one_pass()
+    budget = args.ref_budget_s - (time.time() - t_begin)
+    steps = max(1, min(args.steps, int(budget / max(per_pass_wall, 1e-6))))
+    secs = [one_pass() for _ in range(steps)]
+    el = float(np.mean(secs))
+    gops = 2.0 * units / el / 1e9
     line = {
-        "impl": "reference",
-        "metric": "mod-p Gop/s, F4 linear algebra, katsura-12 mod 31-bit p" if args.workload == "katsura-12"
-                  else f"mod-p Gop/s, F4 linear algebra, {args.workload}",
-        "value": gops, "unit": "Gop/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": el * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": metric_name(args), "value": gops, "unit": "Gop/s", "n_gpus": world,
+        "steps": steps, "steps_requested": args.steps, "warmup": 1 + warm_extra, "ms_per_step": el * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64 accumulators (exact)", "data": "synthetic (formula-generated system)",
-        "config": {"workload": f"{args.workload} mod {args.prime}, DRL, F4 linear-algebra matrices (-l 2); "
-                               f"bounded sample: {len(idx)} matrices, {cum:.3g} units per step"},
-        "cpu_baseline": {"value": gops, "unit": "Gop/s", "cores": threads, "kind": "reference",
-                         "sample": f"{len(idx)} matrices ({cum:.3g} units) per step"},
+        "config": {"workload": workload_label(args, len(recs)), "units_per_step": units, "units_source": units_src,
+                   "host_cpu": cpu, "step_seconds_min_max": [float(min(secs)), float(max(secs))],
+                   "first_pass_seconds": first, "la_seconds_inside_its_own_f4_run": gb.la_seconds,
+                   "time_budget_s": args.ref_budget_s},
+        "cpu_baseline": {"value": gops, "unit": "Gop/s", "cores": threads, "kind": "reference", "host_cpu": cpu,
+                         "simd": "AVX-512" if rh.selected_lib_path().endswith("avx512.so") else "AVX2",
+                         "sample": f"all {len(recs)} matrices ({units:.4g} units) per step, {steps} steps, "
+                                   f"OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')} OMP_PLACES={os.environ.get('OMP_PLACES')}"},
         "e2e": {"value": gops, "unit": "Gop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -552,14 +698,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="katsura-12")
-    ap.add_argument("--prime", type=int, default=P31)
+    ap.add_argument("--workload", default="katsura-12", help="katsura-N, cyclic-N, eco-N, randquad-N")
+    ap.add_argument("--prime", type=int, default=P31, help="1073741827 (31-bit), 65521 (16-bit), 251 (8-bit)")
     ap.add_argument("--per-matrix", action="store_true", help="log per-matrix phase times (stderr)")
     ap.add_argument("--no-qq", action="store_true", help="skip the QQ multi-modular block")
     ap.add_argument("--no-prob", action="store_true", help="skip the probabilistic-mode block")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
     ap.add_argument("--qq-system", default="katsura-10")
-    ap.add_argument("--qq-primes-per-thread", type=int, default=4)
+    ap.add_argument("--qq-primes", type=int, default=128, help="size of the fixed prime batch of the QQ block")
+    ap.add_argument("--ref-budget-s", type=float, default=1200.0,
+                    help="--impl reference: wall-clock budget; fewer steps are timed when K passes do not fit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -186,6 +186,11 @@ void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m);
 
 void f4la_b200_free_result(f4la_flat_result *res);
 
+/* Measurement aid (bench.py): sustained rate, in multiply-adds per second, of the 32 x 32 -> 96-bit
+ * multiply-accumulate of the hot kernel with register operands, run for about `milliseconds` on the
+ * context's device -- the issue ceiling of the multiplier pipe the kernel is bound by. */
+double f4la_b200_measure_mac_peak(f4la_ctx *ctx, double milliseconds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
     "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
     "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
-    "f4la_b200_free_result",
+    "f4la_b200_free_result", "f4la_b200_measure_mac_peak",
     # include/f4la_b200_neogb.h
     "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",
     "f4la_b200_exact_linear_algebra", "f4la_b200_application_linear_algebra", "f4la_b200_trace_linear_algebra",
@@ -84,6 +84,8 @@ def load_library() -> C.CDLL:
     L.f4la_b200_reduce_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CFlatResult), C.POINTER(CStats)]
     L.f4la_b200_release.argtypes = [C.c_void_p, C.c_void_p]
     L.f4la_b200_free_result.argtypes = [C.POINTER(CFlatResult)]
+    L.f4la_b200_measure_mac_peak.restype = C.c_double
+    L.f4la_b200_measure_mac_peak.argtypes = [C.c_void_p, C.c_double]
     L.f4la_b200_neogb_configure.restype = C.c_int
     L.f4la_b200_neogb_configure.argtypes = [C.c_void_p]
     L.f4la_b200_neogb_set_device.argtypes = [C.c_int]
@@ -114,6 +116,10 @@ class Backend:
         if not self.ctx:
             raise F4LAError(f"f4la_b200_create({device}) failed: no usable sm_100 GPU (no CPU fallback)")
         self.device = device
+
+    def measure_mac_peak(self, milliseconds: float = 200.0) -> float:
+        """Multiply-adds per second of the hot kernel's 96-bit accumulate with register operands."""
+        return float(self.lib.f4la_b200_measure_mac_peak(self.ctx, milliseconds))
 
     def set_seed(self, seed: int) -> None:
         self.lib.f4la_b200_set_seed(self.ctx, seed)

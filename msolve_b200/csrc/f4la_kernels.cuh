@@ -438,6 +438,26 @@ __device__ __forceinline__ uint32_t fold_acc(const Acc &a, uint32_t extra, uint3
     return mod_u64(x, p, pinv);
 }
 
+/* Peak of the multiply-add the hot kernel is made of (mac<true>: one IMAD.WIDE.U32 with carry-out + one
+ * add-with-carry), operands in registers: the ceiling bench.py's roofline.binding quotes, measured on the GPU the
+ * bench runs on instead of a constant. */
+__global__ void __launch_bounds__(256) k_mac_peak(uint32_t *out, uint32_t seed, int iters)
+{
+    uint32_t v[8], c = seed | 1u;
+    Acc a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = seed * (i + 3) + threadIdx.x; a[i] = Acc{0ull, 0u}; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mac<true>(a[i], v[i], c);
+        c = c * 1664525u + 1013904223u;
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= (uint32_t)a[i].lo ^ (uint32_t)(a[i].lo >> 32) ^ a[i].a2;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 /* ------------------------------------------------------------------ */
 /* the hot kernel, dataflow-scheduled (one launch per chunk group)      */
 /* ------------------------------------------------------------------ */

@@ -56,3 +56,34 @@ def gather_uint64(local: Sequence[int], dist=None, device="cpu") -> List[List[in
         b = bufs[r].cpu().numpy()
         out.append([int(b[k, 0]) | (int(b[k, 1]) << 32) for k in range(int(counts[r].item()))])
     return out
+
+
+def gather_residues(local: "np.ndarray", dist=None, device="cpu") -> "np.ndarray":
+    """All-gather the modular results of a batch: ``local`` is uint32 [k, words], one row per prime of this
+    rank (the coefficients of the modular Groebner basis / parametrisation, what msolve hands to CRT,
+    msolve.c:2694-2712).  Returns uint32 [sum k, words] in BATCH order (prime i of the batch came from rank
+    i % world, see :func:`shard`) on every rank.  One collective for the counts, one for the payload."""
+    local = np.ascontiguousarray(local, dtype=np.uint32)
+    if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local.copy()
+    import torch
+    world = dist.get_world_size()
+    k, words = local.shape
+    meta = torch.tensor([k, words], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    ks = [int(m[0].item()) for m in metas]
+    assert all(int(m[1].item()) == words or int(m[0].item()) == 0 for m in metas), "ranks disagree on the residue length"
+    kmax = max(max(ks), 1)
+    pad = np.zeros((kmax, max(words, 1)), dtype=np.int32)          # NCCL / gloo: no uint32, same bits as int32
+    pad[:k, :words] = local.view(np.int32)
+    t = torch.from_numpy(pad).to(device)
+    bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(bufs, t)
+    total = sum(ks)
+    out = np.zeros((total, words), dtype=np.uint32)
+    for r in range(world):
+        b = bufs[r].cpu().numpy().view(np.uint32)
+        for j in range(ks[r]):
+            out[r + j * world] = b[j, :words]
+    return out

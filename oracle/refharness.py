@@ -23,6 +23,39 @@ if _ROOT not in sys.path:
 from msolve_b200.flat import CFlatMatrix, CFlatResult, FlatMatrix, FlatResult, _np_from_ptr  # noqa: E402
 
 LIB_PATH = os.path.join(_HERE, "_ref", "libneogb_ref.so")
+LIB_PATH_AVX512 = os.path.join(_HERE, "_ref", "libneogb_ref_avx512.so")
+
+
+def host_cpu() -> dict:
+    """Model name, logical / physical core counts and SIMD level of the host (for the bench lines)."""
+    model, flags, cores = "unknown", set(), set()
+    phys = core = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                k, _, v = line.partition(":")
+                k, v = k.strip(), v.strip()
+                if k == "model name":
+                    model = v
+                elif k == "flags" and not flags:
+                    flags = set(v.split())
+                elif k == "physical id":
+                    phys = v
+                elif k == "core id":
+                    core = v
+                elif k == "" and phys is not None:
+                    cores.add((phys, core)); phys = core = None
+    except OSError:
+        pass
+    return {"model": model, "logical_cpus": os.cpu_count() or 1, "physical_cores": len(cores) or None,
+            "avx512": bool({"avx512f", "avx512bw"} <= flags), "avx2": "avx2" in flags}
+
+
+def selected_lib_path() -> str:
+    """The AVX-512 build of the reference when this host can run it (REFH_SIMD=avx2 forces the AVX2 one)."""
+    if os.environ.get("REFH_SIMD", "") != "avx2" and os.path.exists(LIB_PATH_AVX512) and host_cpu()["avx512"]:
+        return LIB_PATH_AVX512
+    return LIB_PATH
 
 MODE_REFERENCE, MODE_BACKEND, MODE_SHADOW, MODE_RECORD, MODE_RECORD_BACKEND = 0, 1, 2, 3, 4
 
@@ -89,7 +122,7 @@ def lib() -> C.CDLL:
     if _lib is None:
         if not available():
             raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(selected_lib_path(), mode=C.RTLD_GLOBAL)
         L.refh_set_mode.argtypes = [C.c_int, C.c_int, C.c_int]
         L.refh_set_backend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refh_num_records.restype = C.c_int
@@ -224,18 +257,32 @@ def qq_learn(p0: int) -> dict:
     return d
 
 
-def qq_apply(primes, threads: int = 1, ngpus: int = 0):
-    """-> (list of per-prime dicts, wall seconds)"""
+def qq_apply(primes, threads: int = 1, ngpus: int = 0, residue_words: int = 0):
+    """-> (list of per-prime dicts, wall seconds[, residues uint32 [nprimes, residue_words]])
+    residue_words > 0 also returns the coefficients of every modular basis (the residues msolve
+    lifts by CRT); pass the learn phase's nterms."""
     L = lib()
-    L.refh_qq_apply.restype = C.c_int
-    L.refh_qq_apply.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(QQResult), C.POINTER(C.c_double)]
+    L.refh_qq_apply_residues.restype = C.c_int
+    L.refh_qq_apply_residues.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(QQResult),
+                                         C.POINTER(C.c_double), C.c_void_p, C.c_int64]
     arr = np.asarray(primes, dtype=np.uint32)
-    res = (QQResult * len(arr))()
+    res = (QQResult * max(1, len(arr)))()
     wall = C.c_double()
-    rc = L.refh_qq_apply(arr.ctypes.data, len(arr), threads, ngpus, res, C.byref(wall))
+    resid = np.zeros((len(arr), residue_words), dtype=np.uint32) if residue_words else None
+    rc = L.refh_qq_apply_residues(arr.ctypes.data, len(arr), threads, ngpus, res, C.byref(wall),
+                                  resid.ctypes.data if resid is not None and resid.size else None, residue_words)
     if rc != 0:
         raise RuntimeError(f"refh_qq_apply failed: {rc} (learn first)")
-    return [r.as_dict() for r in res], wall.value
+    out = [res[i].as_dict() for i in range(len(arr))]
+    return (out, wall.value, resid) if residue_words else (out, wall.value)
+
+
+def residue_digest(row: np.ndarray, lens_digest: int = 0) -> int:
+    """FNV-1a over the residues of one prime (to compare gathered residues across ranks)."""
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(row, dtype=np.uint32).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
 
 
 def set_device_callback(fn) -> None:
@@ -300,10 +347,10 @@ def call_trace_entry(m: FlatMatrix, fn=None, threads: int = 1):
 
 def last_side() -> dict:
     """Side channels (md_t / mat_t fields) left by the last call_entry()."""
-    buf = (C.c_double * 10)()
+    buf = (C.c_double * 11)()
     lib().refh_last_side(buf)
     names = ["st_np", "mat_np", "mat_nr", "mat_sz", "num_zerored", "la_rtime", "la_ctime",
-             "application_nr_mult", "application_nr_add", "application_nr_red"]
+             "application_nr_mult", "application_nr_add", "application_nr_red", "call_seconds"]
     return dict(zip(names, [float(x) for x in buf]))
 
 

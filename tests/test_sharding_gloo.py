@@ -34,13 +34,20 @@ rank, world = dist.get_rank(), dist.get_world_size()
 primes = rh.primes_above(1 << 30, 7)
 rh.set_mode(rh.MODE_REFERENCE)
 rh.qq_setup(systems.by_name("katsura-6"), threads=1)
-assert rh.qq_learn(primes[0])["rc"] == 0
+learn = rh.qq_learn(primes[0])
+assert learn["rc"] == 0
 mine = sharding.shard(primes[1:], rank, world)
-res, _ = rh.qq_apply(mine, threads=1)
-assert all(r["err"] == 0 for r in res)
+res, _, resid = rh.qq_apply(mine, threads=1, residue_words=learn["nterms"])
+assert all(r["err"] == 0 and r["nterms"] == learn["nterms"] for r in res)
 parts = sharding.gather_uint64([r["digest"] for r in res], dist)
+# the payload msolve lifts by CRT: every prime's residues, in batch order, on every rank
+allres = sharding.gather_residues(resid, dist)
+assert allres.shape == (len(primes) - 1, learn["nterms"])
+for i, p in enumerate(primes[1:]):
+    assert int(allres[i].max()) < p
 if rank == 0:
     print("RESULT " + json.dumps(sharding.unshard(parts)))
+    print("RESID " + json.dumps([rh.residue_digest(row) for row in allres]))
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -53,8 +60,10 @@ def test_qq_prime_sharding_world2_gloo(tmp_path):
     rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
     rh.qq_setup(systems.by_name("katsura-6"), threads=1)
     assert rh.qq_learn(primes[0])["rc"] == 0
-    single, _ = rh.qq_apply(primes[1:], threads=1)
+    learn = rh.qq_learn(primes[0])
+    single, _, resid = rh.qq_apply(primes[1:], threads=1, residue_words=learn["nterms"])
     want = [r["digest"] for r in single]
+    want_resid = [rh.residue_digest(row) for row in resid]
 
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
@@ -68,3 +77,5 @@ def test_qq_prime_sharding_world2_gloo(tmp_path):
     import json
     got = json.loads(line[len("RESULT "):])
     assert got == want
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESID ")][-1]
+    assert json.loads(line[len("RESID "):]) == want_resid
