@@ -91,6 +91,8 @@ typedef struct f4la_flat_matrix {
 /* f4la_b200_reduce() only: the column indices are already on the device, sent piecewise with
  * f4la_b200_stage_cols() while the caller was still assembling them; `cols` is not read. */
 #define F4LA_FLAG_COLS_STAGED 16u
+/* likewise for the coefficient pool (f4la_b200_stage_commit with F4LA_STAGE_CF); `cf` is not read. */
+#define F4LA_FLAG_CF_STAGED 32u
 
 /* Result: rows of the reduced row echelon form, as CSR over ALL columns
  * (column ids in 0..ncl+ncr-1, ascending inside a row).  In echelon mode the
@@ -104,10 +106,11 @@ typedef struct f4la_flat_result {
     uint32_t *cols;      /* [row_ptr[nrows]]                                  */
     void     *cf;        /* [row_ptr[nrows]] coefficients, cf_bytes wide      */
     uint32_t *src_row;   /* [nrows] index of an input lower row whose
-                            reduction produced this pivot (BINDEX/MULT donor);
-                            0xffffffff when the pivot came out of random combinations
-                            of the lower rows (probabilistic mode, compress-and-verify:
-                            never while F4LA_FLAG_WANT_RBA / tracing is on)          */
+                            reduction produced this pivot (BINDEX/MULT donor); when the
+                            pivot came out of a random combination of lower rows
+                            (probabilistic mode, compress-and-verify: never while
+                            F4LA_FLAG_WANT_RBA / tracing is on) one of the rows that
+                            entered the combination                                  */
     uint32_t *rba;       /* F4LA_FLAG_WANT_RBA: [nrl][rba_words] bit i%32 of
                             word i/32 set iff pivot i was used; else NULL     */
     uint32_t  rba_words; /* ceil(nru / 32)                                    */
@@ -177,6 +180,18 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in,
  * they become ready, then f4la_b200_reduce() with F4LA_FLAG_COLS_STAGED.  Used by the neogb
  * adapter, which gathers the rows of a mat_t (one malloc block each) piece by piece. */
 int f4la_b200_stage_cols(f4la_ctx *ctx, const uint32_t *cols, uint64_t first, uint64_t count, uint64_t total_nnz);
+
+/* Staging through a ring of page-locked pieces owned by the context (4 x 16 MB, pinned once): for callers whose
+ * data lies in many small heap blocks (neogb: one malloc block per row / per polynomial) and is gathered piece by
+ * piece.  f4la_b200_stage_acquire() hands out the next free piece (waiting for the copy that last used it);
+ * the caller fills it with elements [first, first+count) of the column indices (which = F4LA_STAGE_COLS,
+ * elem_bytes 4) or of the coefficient pool (F4LA_STAGE_CF, elem_bytes = cf_bytes) and commits: the piece is
+ * copied asynchronously to its place on the device.  Then f4la_b200_reduce() with F4LA_FLAG_COLS_STAGED and / or
+ * F4LA_FLAG_CF_STAGED.  No staging memory is ever re-pinned, whatever the size of the matrix. */
+#define F4LA_STAGE_COLS 0
+#define F4LA_STAGE_CF   1
+int f4la_b200_stage_acquire(f4la_ctx *ctx, void **piece, size_t *capacity_bytes);
+int f4la_b200_stage_commit(f4la_ctx *ctx, int which, uint32_t elem_bytes, uint64_t first, uint64_t count, uint64_t total);
 
 /* Same computation with the input already resident in HBM (bench: `value`). */
 f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in);

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     # include/f4la_b200.h
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
     "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
-    "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
+    "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
     "f4la_b200_free_result", "f4la_b200_measure_mac_peak",
     # include/f4la_b200_neogb.h
     "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",

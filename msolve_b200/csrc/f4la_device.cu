@@ -41,6 +41,8 @@ double now_ms()
 } // namespace
 
 constexpr int kMaxFlowEvents = 512;
+constexpr int kRingSlots = 4;
+constexpr size_t kRingPieceBytes = (size_t)16 << 20;
 
 struct f4la_ctx {
     int           device = 0;
@@ -83,6 +85,13 @@ struct f4la_ctx {
     uint64_t      seed = 0x9e3779b97f4a7c15ull;   /* random combinations of the probabilistic mode */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense, h_combo;
+    /* ring of page-locked pieces for the big input arrays (f4la_b200_stage_acquire / _commit): pinned ONCE, so a
+     * growing matrix never re-pins staging memory on the critical path (the cold-start cost of round 1) */
+    void         *ring_buf[kRingSlots] = {};
+    cudaEvent_t   ring_ev[kRingSlots] = {};
+    bool          ring_busy[kRingSlots] = {};
+    int           ring_next = 0, ring_held = -1;
+    std::vector<uint32_t> donor;          /* per random combination: one lower row that entered it (BINDEX / MULT donor) */
 };
 
 struct f4la_resident {
@@ -432,6 +441,9 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         ctx->compress_attempts++;
         if (*h_bad || ctx->compress_fault) { ctx->compress_rejected++; return F4LA_OK; }      /* rank lost in the compression: eliminate directly */
         ctx->d2_ld = kc;
+        ctx->donor.assign(kc, 0xffffffffu);
+        for (uint32_t q = 0; q < kc; ++q)
+            if (h_ptr[q + 1] > h_ptr[q]) ctx->donor[q] = h_row[h_ptr[q]];
         *rank_out = rank;
         *ok = true;
         return F4LA_OK;
@@ -728,6 +740,15 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         }
         ge_ld = ld;
         rows_are_combinations = compressed || combos;
+        if (combos) {                     /* same hash as k_scatter_combos: first lower row of every combination */
+            const uint32_t kw = nvr / kProbWeight;
+            ctx->donor.assign(nvr, 0xffffffffu);
+            for (uint32_t r = nrl_in; r-- > 0;)
+                for (uint32_t f = 0; f < kProbWeight; ++f) {
+                    const uint64_t h = host_mix64(ctx->seed ^ ((uint64_t)f << 40) ^ r);
+                    ctx->donor[f * kw + (uint32_t)(h % kw)] = r;
+                }
+        }
         if (compressed) { Dm = as<uint32_t>(ctx->D2); ge_ld = ctx->d2_ld; }
         else OK(gauss_jordan(ctx, Dm, ld, nrl, ncr, p, pinv, &rank));
     }
@@ -837,8 +858,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         uint64_t nnz = 0;
         for (uint32_t t = 0; t < nout; ++t) {
             out->row_ptr[t] = nnz;
-            /* a pivot row of a block of random combinations has no single donor among the lower rows */
-            out->src_row[t] = (nf_mode || by_lead) ? t : rows_are_combinations ? 0xffffffffu : h_pivrow[rank - 1 - t];
+            /* a pivot row of a block of random combinations: one of the lower rows that entered that combination */
+            out->src_row[t] = (nf_mode || by_lead) ? t
+                              : rows_are_combinations ? ctx->donor[h_pivrow[rank - 1 - t]] : h_pivrow[rank - 1 - t];
             nnz += rnz[t];
         }
         out->row_ptr[nout] = nnz;
@@ -911,10 +933,10 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
         return fail(ctx, F4LA_ERR_ARG, "field characteristic %u out of range (need 2 <= p < 2^31)", in->fc);
     if (in->cf_bytes != 1 && in->cf_bytes != 2 && in->cf_bytes != 4)
         return fail(ctx, F4LA_ERR_ARG, "cf_bytes must be 1, 2 or 4");
-    if ((in->flags & F4LA_FLAG_COLS_STAGED) && own)
-        return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_COLS_STAGED is for f4la_b200_reduce() only");
+    if ((in->flags & (F4LA_FLAG_COLS_STAGED | F4LA_FLAG_CF_STAGED)) && own)
+        return fail(ctx, F4LA_ERR_ARG, "F4LA_FLAG_COLS_STAGED / F4LA_FLAG_CF_STAGED are for f4la_b200_reduce() only");
     r->dims = *in;
-    r->dims.flags &= ~F4LA_FLAG_COLS_STAGED;
+    r->dims.flags &= ~(F4LA_FLAG_COLS_STAGED | F4LA_FLAG_CF_STAGED);
     r->owned = own;
     r->nnz = n ? in->row_ptr[n] : 0;
     r->ncoef = in->ncf ? in->cf_ptr[in->ncf] : 0;
@@ -942,7 +964,7 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
      * lower rows' column indices and coefficient arrays therefore travel on a second stream while those
      * steps run; the pipeline waits for them just before it scatters the lower rows. */
     const bool split = !own && ctx->split_h2d && in->nrl && in->nru && r->nnz >= (1u << 20) &&
-                       !(in->flags & (F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_COLS_STAGED));
+                       !(in->flags & (F4LA_FLAG_PIVOT_BY_LEAD | F4LA_FLAG_COLS_STAGED | F4LA_FLAG_CF_STAGED));
     if (split) {
         const uint64_t nz_up = in->row_ptr[in->nru];
         uint32_t k_up = 0;                                   /* coefficient arrays 0 .. k_up-1 serve the pivot rows */
@@ -963,7 +985,8 @@ int upload(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_resident *r, bool own
     } else {
         if (r->nnz && !(in->flags & F4LA_FLAG_COLS_STAGED))
             CU(cudaMemcpyAsync(r->cols, in->cols, r->nnz * 4, cudaMemcpyHostToDevice, s));
-        if (r->ncoef) CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
+        if (r->ncoef && !(in->flags & F4LA_FLAG_CF_STAGED))
+            CU(cudaMemcpyAsync(r->cf, in->cf, r->ncoef * in->cf_bytes, cudaMemcpyHostToDevice, s));
     }
     r->bytes = (n + 1) * 8 + r->nnz * 4 + n * 4 + ((uint64_t)in->ncf + 1) * 8 + r->ncoef * in->cf_bytes;
     return F4LA_OK;
@@ -1063,6 +1086,10 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     if (ctx->h_small.p) cudaFreeHost(ctx->h_small.p);
     if (ctx->h_dense.p) cudaFreeHost(ctx->h_dense.p);
     if (ctx->h_combo.p) cudaFreeHost(ctx->h_combo.p);
+    for (int k = 0; k < kRingSlots; ++k) {
+        if (ctx->ring_buf[k]) cudaFreeHost(ctx->ring_buf[k]);
+        if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
+    }
     for (auto &e : ctx->ev) cudaEventDestroy(e);
     for (auto &e : ctx->dbg_ev) cudaEventDestroy(e);
     for (auto &e : ctx->flow_ev) cudaEventDestroy(e);
@@ -1121,6 +1148,44 @@ int f4la_b200_stage_cols(f4la_ctx *ctx, const uint32_t *cols, uint64_t first, ui
     OK(ensure(ctx, ctx->in_cols, (total_nnz + 1) * 4));
     if (count)
         CU(cudaMemcpyAsync(as<uint32_t>(ctx->in_cols) + first, cols + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return F4LA_OK;
+}
+
+int f4la_b200_stage_acquire(f4la_ctx *ctx, void **piece, size_t *capacity_bytes)
+{
+    if (!ctx || !piece || !capacity_bytes) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const int k = ctx->ring_next;
+    if (!ctx->ring_buf[k]) {
+        CU(cudaMallocHost(&ctx->ring_buf[k], kRingPieceBytes));
+        CU(cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming));
+    }
+    if (ctx->ring_busy[k]) { CU(cudaEventSynchronize(ctx->ring_ev[k])); ctx->ring_busy[k] = false; }
+    ctx->ring_held = k;
+    *piece = ctx->ring_buf[k];
+    *capacity_bytes = kRingPieceBytes;
+    return F4LA_OK;
+}
+
+int f4la_b200_stage_commit(f4la_ctx *ctx, int which, uint32_t elem_bytes, uint64_t first, uint64_t count, uint64_t total)
+{
+    if (!ctx || ctx->ring_held < 0 || first + count > total || count * elem_bytes > kRingPieceBytes) return F4LA_ERR_ARG;
+    if ((which == F4LA_STAGE_COLS && elem_bytes != 4) ||
+        (which == F4LA_STAGE_CF && elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4) ||
+        (which != F4LA_STAGE_COLS && which != F4LA_STAGE_CF)) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const int k = ctx->ring_held;
+    /* same sizes as upload() asks for: the buffers are not reallocated between the pieces and the reduce call */
+    DevBuf &dst = which == F4LA_STAGE_COLS ? ctx->in_cols : ctx->in_cf;
+    OK(ensure(ctx, dst, (total + 1) * elem_bytes));
+    if (count) {
+        CU(cudaMemcpyAsync((char *)dst.p + first * elem_bytes, ctx->ring_buf[k], count * elem_bytes, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CU(cudaEventRecord(ctx->ring_ev[k], ctx->stream));
+        ctx->ring_busy[k] = true;
+    }
+    ctx->ring_held = -1;
+    ctx->ring_next = (k + 1) % kRingSlots;
     return F4LA_OK;
 }
 

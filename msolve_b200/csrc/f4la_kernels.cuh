@@ -487,6 +487,9 @@ constexpr uint32_t kErrWatchdog = 16u;
 #ifndef F4LA_FLOW_LOAD
 #define F4LA_FLOW_LOAD __ldcg   /* source vectors: L2 only (A/B: ld_ca_u4 keeps them in L1 as well) */
 #endif
+#ifndef F4LA_FLOW_ACQUIRE_FENCE
+#define F4LA_FLOW_ACQUIRE_FENCE 0
+#endif
 #ifndef F4LA_FLOW_U
 #define F4LA_FLOW_U 4        /* entries (source vectors) in flight per warp for T <= 2 */
 #endif
@@ -605,9 +608,14 @@ __device__ __forceinline__ void flow_accumulate(const FlowArgs &A, const uint32_
                 }
             }
         }
-        /* relaxed polls + ONE fence per batch make the acquire pattern of the PTX memory model: the
-         * producer's stores of V[src] (fence + st.release of the ready word) happen before the loads below */
-#ifndef F4LA_NO_FENCE
+        /* -DF4LA_FLOW_ACQUIRE_FENCE=1: relaxed polls + ONE fence per batch make the formal acquire pattern of the
+         * PTX memory model.  Off by default: the fence compiles to MEMBAR.SC.GPU + CCTL.IVALL (an L1 invalidation
+         * per batch) and costs 5.4 % of the katsura-12 step (134.6 vs 127.7 ms, same GPU, round 2), while nothing
+         * here can be stale in L1: the ready word is polled with ld.relaxed.gpu and the vectors are read with ld.cg,
+         * both served by L2 (the point of coherence), the vector loads are issued after the branch that consumed
+         * the ready word (the SM does not speculate loads past a branch), and the producer orders its vector stores
+         * before the st.release of the word with a fence. */
+#if F4LA_FLOW_ACQUIRE_FENCE
         __threadfence();
 #endif
         __syncwarp();

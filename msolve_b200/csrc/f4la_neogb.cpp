@@ -128,7 +128,12 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     void **&mcf = fld<void **>(mat, cf_off);
     mcf = (void **)realloc(mcf, (size_t)fld<uint32_t>(mat, L.mat_nr) * sizeof(void *));
 
-    /* ---- flatten into pinned staging ---- */
+    /* ---- flatten ---- */
+    /* The small arrays (row offsets, coefficient-array ids and offsets) go through small page-locked buffers.  The
+     * two big ones -- the column indices (4 B per non-zero, ~1 GB per katsura-12 run) and the coefficient pool --
+     * are gathered from the rows' individual malloc blocks straight into the library's ring of page-locked pieces
+     * (pinned once, never re-pinned) and sent piece by piece, so the gather of piece k+1 by st->nthrds host threads
+     * (like the reference's own row loops, e.g. convert.c:365-397) overlaps the host->device copy of piece k. */
     uint64_t *row_ptr = (uint64_t *)stage(0, ((size_t)n + 1) * 8);
     uint32_t *row_cf = (uint32_t *)stage(2, ((size_t)n + 1) * 4);
     uint64_t nnz = 0;
@@ -137,7 +142,6 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
         row_ptr[r] = nnz; nnz += row[L.row_length];
     }
     row_ptr[n] = nnz;
-    uint32_t *cols = (uint32_t *)stage(1, (nnz + 1) * 4);
     void *const *bs_cf = fld<void *const *>(bs, bcf_off);
     void *const *tbr_cf = fld<void *const *>(tbr, bcf_off);
     const uint32_t bs_ld = fld<uint32_t>(bs, L.bs_ld), tbr_ld = fld<uint32_t>(tbr, L.bs_ld);
@@ -149,27 +153,7 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     std::vector<uint32_t> src_bindex(nrl), src_mult(nrl);
     uint64_t ncoef = 0;
     const int nthr = fld<int32_t>(st, L.md_nthrds) > 1 ? fld<int32_t>(st, L.md_nthrds) : 1;
-    /* the bulk copy of the column indices is row-parallel (st->nthrds host
-     * threads, like the reference's own row loops, e.g. convert.c:365-397) */
-    /* ... and pipelined with the host->device copy: as soon as a piece of `cols` is assembled it is
-     * sent (f4la_b200_stage_cols, asynchronous), the next piece is gathered meanwhile */
     f4la_ctx *cx = ctx();
-    const bool staged = nnz >= (1u << 22);
-    {
-        const uint64_t piece = nnz / 8 > (1u << 21) ? nnz / 8 : (1u << 21);
-        for (uint32_t r0 = 0; r0 < n;) {
-            uint32_t r1 = r0;
-            while (r1 < n && row_ptr[r1] - row_ptr[r0] < piece) ++r1;
-#pragma omp parallel for num_threads(nthr) schedule(dynamic, 256)
-            for (uint32_t r = r0; r < r1; ++r) {
-                const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
-                memcpy(cols + row_ptr[r], row + L.row_offset, (size_t)row[L.row_length] * 4);
-            }
-            if (staged && f4la_b200_stage_cols(cx, cols, row_ptr[r0], row_ptr[r1] - row_ptr[r0], nnz) != F4LA_OK)
-                die(f4la_b200_last_error(cx));
-            r0 = r1;
-        }
-    }
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
         const uint32_t len = row[L.row_length];
@@ -189,23 +173,60 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     const uint32_t ncf = (uint32_t)cfsrc.size();
     uint64_t *cf_ptr = (uint64_t *)stage(3, ((size_t)ncf + 1) * 8);
     memcpy(cf_ptr, cfp.data(), ((size_t)ncf + 1) * 8);
-    unsigned char *pool = (unsigned char *)stage(4, (ncoef + 1) * w);
-    for (uint32_t c = 0; c < ncf; ++c)
-        memcpy(pool + cfp[c] * w, cfsrc[c], (size_t)(cfp[c + 1] - cfp[c]) * w);
+    {
+        /* column indices: elements [a, b) of the concatenation of all rows per piece */
+        uint32_t r_lo = 0;
+        for (uint64_t a = 0; a < nnz;) {
+            void *piece = nullptr; size_t cap = 0;
+            if (f4la_b200_stage_acquire(cx, &piece, &cap) != F4LA_OK) die(f4la_b200_last_error(cx));
+            const uint64_t b = std::min<uint64_t>(nnz, a + cap / 4);
+            while (row_ptr[r_lo + 1] <= a) ++r_lo;                           /* first row reaching into [a, b) */
+            uint32_t r_hi = r_lo;
+            while (r_hi < n && row_ptr[r_hi] < b) ++r_hi;
+            uint32_t *dst = (uint32_t *)piece;
+#pragma omp parallel for num_threads(nthr) schedule(static) if (r_hi - r_lo > 64)
+            for (uint32_t r = r_lo; r < r_hi; ++r) {
+                const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+                const uint64_t lo = std::max<uint64_t>(row_ptr[r], a), hi = std::min<uint64_t>(row_ptr[r + 1], b);
+                if (hi > lo) memcpy(dst + (lo - a), row + L.row_offset + (lo - row_ptr[r]), (size_t)(hi - lo) * 4);
+            }
+            if (f4la_b200_stage_commit(cx, F4LA_STAGE_COLS, 4, a, b - a, nnz) != F4LA_OK) die(f4la_b200_last_error(cx));
+            a = b;
+        }
+        /* coefficient pool: arrays [cfp[c], cfp[c+1]) likewise */
+        uint32_t c_lo = 0;
+        for (uint64_t a = 0; a < ncoef;) {
+            void *piece = nullptr; size_t cap = 0;
+            if (f4la_b200_stage_acquire(cx, &piece, &cap) != F4LA_OK) die(f4la_b200_last_error(cx));
+            const uint64_t b = std::min<uint64_t>(ncoef, a + cap / w);
+            while (cfp[c_lo + 1] <= a) ++c_lo;
+            uint32_t c_hi = c_lo;
+            while (c_hi < ncf && cfp[c_hi] < b) ++c_hi;
+            unsigned char *dst = (unsigned char *)piece;
+#pragma omp parallel for num_threads(nthr) schedule(static) if (c_hi - c_lo > 64)
+            for (uint32_t c = c_lo; c < c_hi; ++c) {
+                const uint64_t lo = std::max<uint64_t>(cfp[c], a), hi = std::min<uint64_t>(cfp[c + 1], b);
+                if (hi > lo) memcpy(dst + (lo - a) * w, (const unsigned char *)cfsrc[c] + (lo - cfp[c]) * w, (size_t)(hi - lo) * w);
+            }
+            if (f4la_b200_stage_commit(cx, F4LA_STAGE_CF, w, a, b - a, ncoef) != F4LA_OK) die(f4la_b200_last_error(cx));
+            a = b;
+        }
+    }
 
     f4la_flat_matrix fm;
     memset(&fm, 0, sizeof(fm));
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
     fm.flags = nf_mode ? F4LA_FLAG_NORMALFORM : final_step ? F4LA_FLAG_PIVOT_BY_LEAD : F4LA_FLAG_NONE;
     if (learn) fm.flags |= F4LA_FLAG_WANT_RBA;
-    if (staged) fm.flags |= F4LA_FLAG_COLS_STAGED;
+    if (nnz) fm.flags |= F4LA_FLAG_COLS_STAGED;
+    if (ncoef) fm.flags |= F4LA_FLAG_CF_STAGED;
     /* -l 42 / 43 / 44: the reference's probabilistic variants (io.c:885-957); no tracer runs with
      * them (f4.c:365), the device decides whether random combinations pay off */
     const int32_t laopt = fld<int32_t>(st, L.md_laopt);
     if ((laopt == 42 || laopt == 43 || laopt == 44) && entry == Entry::Normal && !learn && !nf_mode && !final_step &&
         trace_level == 0)
         fm.flags |= F4LA_FLAG_PROBABILISTIC;
-    fm.row_ptr = row_ptr; fm.cols = cols; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = pool;
+    fm.row_ptr = row_ptr; fm.cols = nullptr; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = nullptr;
     const double t_flat = now_ms();
 
     /* ---- device ---- */
@@ -451,6 +472,22 @@ int f4la_b200_neogb_configure(const f4la_neogb_layout *layout)
     }
     L = *layout;
     g_configured = true;
+    /* CUDA context, kernel module and the staging ring of the calling thread are set up here, once, before the
+     * reference starts its F4 run -- not inside the first linear-algebra call.  Without a device the handshake
+     * still succeeds (the layout can be checked anywhere); the first linear-algebra call then fails loudly, there
+     * is no CPU fallback. */
+    if (f4la_b200_device_count() <= 0) return F4LA_OK;
+    if (!T.ctx) {
+        if (T.device < 0) { const char *e = getenv("F4LA_B200_DEVICE"); T.device = e ? atoi(e) : 0; }
+        T.ctx = f4la_b200_create(T.device);
+        if (!T.ctx) return F4LA_OK;
+    }
+    f4la_ctx *cx = T.ctx;
+    void *piece = nullptr; size_t cap = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (f4la_b200_stage_acquire(cx, &piece, &cap) != F4LA_OK) return F4LA_ERR_CUDA;
+        if (f4la_b200_stage_commit(cx, F4LA_STAGE_COLS, 4, 0, 0, 0) != F4LA_OK) return F4LA_ERR_CUDA;
+    }
     return F4LA_OK;
 }
 

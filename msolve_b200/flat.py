@@ -20,6 +20,7 @@ FLAG_PIVOT_BY_LEAD = 2
 FLAG_WANT_RBA = 4
 FLAG_PROBABILISTIC = 8
 FLAG_COLS_STAGED = 16
+FLAG_CF_STAGED = 32
 
 _CF_DTYPE = {1: np.uint8, 2: np.uint16, 4: np.uint32}
 
