@@ -150,17 +150,23 @@ def generate_workload(system_name: str, p: int, threads: int):
     import gpu_helpers
     from msolve_b200 import systems
     from oracle import refharness as rh
-    L = gpu_helpers.install_backend(mode=rh.MODE_RECORD_BACKEND)
+    # run 1: first use of the backend in this process, nothing recorded -- what a one-shot msolve process pays
+    L = gpu_helpers.install_backend(mode=rh.MODE_BACKEND)
     assert rh.hooked_pointers() == 0b11111
     t0 = time.time()
     gb = rh.run_f4(systems.by_name(system_name, p), p, threads=threads, laopt=2)
     cold = {"f4_seconds": time.time() - t0, "la_seconds": gb.la_seconds, "totals": gpu_helpers.neogb_totals(L)}
-    recs = [r for r in rh.records() if r.kind == 0]
+    # run 2: steady state (second run of the process): the reference's own "F4 LA time" metric (st->la_rtime)
     rh.reset(); rh.set_mode(rh.MODE_BACKEND)
     t0 = time.time()
     gb2 = rh.run_f4(systems.by_name(system_name, p), p, threads=threads, laopt=2)
     warm = {"f4_seconds": time.time() - t0, "la_seconds": gb2.la_seconds, "totals": gpu_helpers.neogb_totals(L)}
-    assert gb2.digest() == gb.digest()
+    # run 3: the harness records what the driver hands to the backend (its copies perturb the timing: not reported)
+    rh.reset(); rh.set_mode(rh.MODE_RECORD_BACKEND)
+    gb3 = rh.run_f4(systems.by_name(system_name, p), p, threads=threads, laopt=2)
+    recs = [r for r in rh.records() if r.kind == 0]
+    gpu_helpers.neogb_totals(L)
+    assert gb2.digest() == gb.digest() and gb3.digest() == gb.digest()
     gpu_helpers.uninstall_backend()
     return gb, recs, cold, warm
 

@@ -134,6 +134,8 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
      * are gathered from the rows' individual malloc blocks straight into the library's ring of page-locked pieces
      * (pinned once, never re-pinned) and sent piece by piece, so the gather of piece k+1 by st->nthrds host threads
      * (like the reference's own row loops, e.g. convert.c:365-397) overlaps the host->device copy of piece k. */
+    static const bool dbg = getenv("F4LA_B200_DEBUG") && atoi(getenv("F4LA_B200_DEBUG")) != 0;
+    double dbg_t[6] = {0, 0, 0, 0, 0, 0}, dbg_t0 = now_ms();
     uint64_t *row_ptr = (uint64_t *)stage(0, ((size_t)n + 1) * 8);
     uint32_t *row_cf = (uint32_t *)stage(2, ((size_t)n + 1) * 4);
     uint64_t nnz = 0;
@@ -154,6 +156,7 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     uint64_t ncoef = 0;
     const int nthr = fld<int32_t>(st, L.md_nthrds) > 1 ? fld<int32_t>(st, L.md_nthrds) : 1;
     f4la_ctx *cx = ctx();
+    dbg_t[0] = now_ms() - dbg_t0;
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
         const uint32_t len = row[L.row_length];
@@ -173,12 +176,15 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     const uint32_t ncf = (uint32_t)cfsrc.size();
     uint64_t *cf_ptr = (uint64_t *)stage(3, ((size_t)ncf + 1) * 8);
     memcpy(cf_ptr, cfp.data(), ((size_t)ncf + 1) * 8);
+    dbg_t[1] = now_ms() - dbg_t0;
     {
         /* column indices: elements [a, b) of the concatenation of all rows per piece */
         uint32_t r_lo = 0;
         for (uint64_t a = 0; a < nnz;) {
             void *piece = nullptr; size_t cap = 0;
+            const double ta = now_ms();
             if (f4la_b200_stage_acquire(cx, &piece, &cap) != F4LA_OK) die(f4la_b200_last_error(cx));
+            dbg_t[2] += now_ms() - ta;
             const uint64_t b = std::min<uint64_t>(nnz, a + cap / 4);
             while (row_ptr[r_lo + 1] <= a) ++r_lo;                           /* first row reaching into [a, b) */
             uint32_t r_hi = r_lo;
@@ -190,9 +196,12 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
                 const uint64_t lo = std::max<uint64_t>(row_ptr[r], a), hi = std::min<uint64_t>(row_ptr[r + 1], b);
                 if (hi > lo) memcpy(dst + (lo - a), row + L.row_offset + (lo - row_ptr[r]), (size_t)(hi - lo) * 4);
             }
+            const double tc = now_ms();
             if (f4la_b200_stage_commit(cx, F4LA_STAGE_COLS, 4, a, b - a, nnz) != F4LA_OK) die(f4la_b200_last_error(cx));
+            dbg_t[3] += now_ms() - tc;
             a = b;
         }
+        dbg_t[4] = now_ms() - dbg_t0;
         /* coefficient pool: arrays [cfp[c], cfp[c+1]) likewise */
         uint32_t c_lo = 0;
         for (uint64_t a = 0; a < ncoef;) {
@@ -213,6 +222,10 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
         }
     }
 
+    if (dbg)
+        fprintf(stderr, "[f4la debug] flatten %u rows %llu nnz: small staging %.2f, dedupe %.2f, columns %.2f (acquire %.2f, "
+                "commit %.2f), coefficients %.2f ms\n", n, (unsigned long long)nnz, dbg_t[0], dbg_t[1] - dbg_t[0],
+                dbg_t[4] - dbg_t[1], dbg_t[2], dbg_t[3], now_ms() - dbg_t0 - dbg_t[4]);
     f4la_flat_matrix fm;
     memset(&fm, 0, sizeof(fm));
     fm.fc = fc; fm.cf_bytes = w; fm.nru = nru; fm.nrl = nrl; fm.ncl = ncl; fm.ncr = ncr; fm.ncf = ncf;
