@@ -201,6 +201,14 @@ void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m);
 
 void f4la_b200_free_result(f4la_flat_result *res);
 
+/* Exact dense product mod p on the tensor cores (tcgen05.mma.kind::i8 on 8-bit limbs, TMEM accumulators; see
+ * csrc/f4la_tc.cuh): C = A * B mod p with A (M x K) and C (M x N) column major with leading dimension M, B (K x N)
+ * row major, all host arrays of residues < p < 2^31, K <= 8192.  This is the kernel that certifies the echelon form
+ * of tall trailing blocks inside f4la_b200_reduce(); the entry point exists for tests and measurements.
+ * *kernel_ms (optional) receives the duration of the kernel alone. */
+int f4la_b200_modp_gemm(f4la_ctx *ctx, const uint32_t *A, const uint32_t *B, uint32_t M, uint32_t N, uint32_t K,
+                        uint32_t p, uint32_t *C, double *kernel_ms);
+
 /* Measurement aid (bench.py): sustained rate, in multiply-adds per second, of the 32 x 32 -> 96-bit
  * multiply-accumulate of the hot kernel with register operands, run for about `milliseconds` on the
  * context's device -- the issue ceiling of the multiplier pipe the kernel is bound by. */

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
     "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
     "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
-    "f4la_b200_free_result", "f4la_b200_measure_mac_peak",
+    "f4la_b200_free_result", "f4la_b200_measure_mac_peak", "f4la_b200_modp_gemm",
     # include/f4la_b200_neogb.h
     "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",
     "f4la_b200_exact_linear_algebra", "f4la_b200_application_linear_algebra", "f4la_b200_trace_linear_algebra",
@@ -84,6 +84,9 @@ def load_library() -> C.CDLL:
     L.f4la_b200_reduce_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CFlatResult), C.POINTER(CStats)]
     L.f4la_b200_release.argtypes = [C.c_void_p, C.c_void_p]
     L.f4la_b200_free_result.argtypes = [C.POINTER(CFlatResult)]
+    L.f4la_b200_modp_gemm.restype = C.c_int
+    L.f4la_b200_modp_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_void_p, C.POINTER(C.c_double)]
     L.f4la_b200_measure_mac_peak.restype = C.c_double
     L.f4la_b200_measure_mac_peak.argtypes = [C.c_void_p, C.c_double]
     L.f4la_b200_neogb_configure.restype = C.c_int
@@ -120,6 +123,19 @@ class Backend:
     def measure_mac_peak(self, milliseconds: float = 200.0) -> float:
         """Multiply-adds per second of the hot kernel's 96-bit accumulate with register operands."""
         return float(self.lib.f4la_b200_measure_mac_peak(self.ctx, milliseconds))
+
+    def modp_gemm(self, A: np.ndarray, B: np.ndarray, p: int):
+        """A (M x K) @ B (K x N) mod p on the tensor cores -> (C uint32 [M, N], kernel milliseconds)."""
+        M, K = A.shape
+        K2, N = B.shape
+        assert K == K2
+        a = np.asfortranarray(A, dtype=np.uint32)            # column major, leading dimension M
+        b = np.ascontiguousarray(B, dtype=np.uint32)
+        c = np.zeros((M, N), dtype=np.uint32, order="F")
+        ms = C.c_double()
+        self._check(self.lib.f4la_b200_modp_gemm(self.ctx, a.ctypes.data, b.ctypes.data, M, N, K, p, c.ctypes.data,
+                                                 C.byref(ms)))
+        return c, ms.value
 
     def set_seed(self, seed: int) -> None:
         self.lib.f4la_b200_set_seed(self.ctx, seed)

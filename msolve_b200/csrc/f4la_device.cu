@@ -12,6 +12,7 @@
 
 #include "f4la_b200.h"
 #include "f4la_kernels.cuh"
+#include "f4la_tc.cuh"
 
 using namespace f4la;
 
@@ -71,6 +72,9 @@ struct f4la_ctx {
     uint64_t      compress_attempts = 0, compress_rejected = 0, compress_escalated = 0;
     uint32_t      compress_rows = 768;  /* F4LA_B200_COMPRESS_ROWS: combinations of the first attempt (x4 per escalation) */
     uint32_t      ge_batch = 8, ge_miss_limit = 4;   /* F4LA_B200_GE_BATCH (<= 32), F4LA_B200_GE_MISSES: pivots per batch, empty visits that end one */
+    int           tc_verify = 1;        /* F4LA_B200_TC=0: verification product on the CUDA cores (k_ge_verify) instead of tcgen05 */
+    bool          tc_attr_set = false;
+    uint64_t      tc_launches = 0;
     int           zerocopy = 1;         /* F4LA_B200_ZEROCOPY=0: result rows through a device buffer + copy */
     int           debug = 0;            /* F4LA_B200_DEBUG=1: statistics on stderr */
     int           debug_sync = 0;       /* F4LA_B200_SYNC=1: synchronise after every kernel launch and name a failing one */
@@ -243,6 +247,24 @@ uint64_t host_mix64(uint64_t x)
     x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
     x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
     return x ^ (x >> 31);
+}
+
+/* C = A * B mod p (store) or D == A * B mod p (verify) on the tensor cores, see f4la_tc.cuh. */
+int launch_tc_gemm(f4la_ctx *ctx, TcGemmArgs g)
+{
+    if (g.K == 0 || g.K > kTcMaxK || g.M % kTcBM != 0 || g.M == 0 || g.N == 0)
+        return fail(ctx, F4LA_ERR_ARG, "tensor-core product: unsupported shape %u x %u x %u", g.M, g.N, g.K);
+    if (!ctx->tc_attr_set) {
+        CU(cudaFuncSetAttribute(k_tc_gemm_modp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        ctx->tc_attr_set = true;
+    }
+    g.w32 = (uint32_t)((1ull << 32) % g.p);
+    g.pinv = ~0ULL / g.p;
+    dim3 grid(g.M / kTcBM, (g.N + kTcBN - 1) / kTcBN);
+    k_tc_gemm_modp<<<grid, kTcThreads, kTcSmemBytes, ctx->stream>>>(g);
+    note_launch(ctx, 1, __LINE__);
+    ctx->tc_launches++;
+    return F4LA_OK;
 }
 
 /* Gauss-Jordan on a column-major block (ncr columns of ld words, nrl rows used): pivot columns, rows and
@@ -429,11 +451,23 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         }
         uint32_t *d_bad = as<uint32_t>(ctx->flags32) + 8;
         CU(cudaMemsetAsync(d_bad, 0, 4, s));
-        const uint32_t nrows_pad = (nrl + kVerTile - 1) / kVerTile * kVerTile;     /* <= ld, padding rows are zero */
-        dim3 vgrid(nrows_pad / kVerTile, (ncr + kVerTile - 1) / kVerTile);
-        k_ge_verify<<<vgrid, 256, 0, s>>>(Dm, ld, nrows_pad, ncr, rank, as<uint32_t>(ctx->pivcol),
-                                          as<uint32_t>(ctx->dense_out), p, pinv, two64, d_bad);
-        note_launch(ctx, 1, __LINE__);
+        if (ctx->tc_verify && rank >= 1 && rank <= kTcMaxK && ld % kTcBM == 0) {
+            /* D' == D'[:, pivot columns] * B on the tensor cores (u8-limb tcgen05.mma, f4la_tc.cuh); B row t
+             * belongs to pivot rank-1-t.  ld is a multiple of 128, the rows beyond nrl are zero. */
+            TcGemmArgs g;
+            memset(&g, 0, sizeof(g));
+            g.A = Dm; g.lda = ld; g.acol = as<uint32_t>(ctx->pivcol); g.acol_reverse = 1;
+            g.B = as<uint32_t>(ctx->dense_out); g.ldb = ncr;
+            g.M = (nrl + kTcBM - 1) / kTcBM * kTcBM; g.N = ncr; g.K = rank; g.p = p;
+            g.D = Dm; g.ldd = ld; g.mismatch = d_bad; g.err = as<uint32_t>(ctx->flags32);
+            OK(launch_tc_gemm(ctx, g));
+        } else {
+            const uint32_t nrows_pad = (nrl + kVerTile - 1) / kVerTile * kVerTile;     /* <= ld, padding rows are zero */
+            dim3 vgrid(nrows_pad / kVerTile, (ncr + kVerTile - 1) / kVerTile);
+            k_ge_verify<<<vgrid, 256, 0, s>>>(Dm, ld, nrows_pad, ncr, rank, as<uint32_t>(ctx->pivcol),
+                                              as<uint32_t>(ctx->dense_out), p, pinv, two64, d_bad);
+            note_launch(ctx, 1, __LINE__);
+        }
         uint32_t *h_bad = (uint32_t *)ctx->h_small.p + 128;
         CU(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
@@ -1056,6 +1090,8 @@ f4la_ctx *f4la_b200_create(int device)
     if (gb && atoi(gb) >= 2 && atoi(gb) <= (int)kGeBatchCached) ctx->ge_batch = (uint32_t)atoi(gb);
     const char *gm = getenv("F4LA_B200_GE_MISSES");
     if (gm && atoi(gm) >= 1) ctx->ge_miss_limit = (uint32_t)atoi(gm);
+    const char *tcv = getenv("F4LA_B200_TC");
+    if (tcv) ctx->tc_verify = atoi(tcv) != 0;
     const char *zc = getenv("F4LA_B200_ZEROCOPY");
     if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
@@ -1213,6 +1249,45 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result
         stats->bytes_h2d = r.bytes;
         stats->ms_total = now_ms() - t0;
     }
+    return rc;
+}
+
+int f4la_b200_modp_gemm(f4la_ctx *ctx, const uint32_t *A, const uint32_t *B, uint32_t M, uint32_t N, uint32_t K, uint32_t p,
+                        uint32_t *C, double *kernel_ms)
+{
+    if (!ctx || !A || !B || !C || p < 2 || p >= 0x80000000u) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t Mp = ((uint64_t)M + kTcBM - 1) / kTcBM * kTcBM;
+    uint32_t *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int rc = F4LA_OK;
+    auto body = [&]() -> int {
+        CU(cudaMalloc(&dA, Mp * (K ? K : 1) * 4));
+        CU(cudaMalloc(&dB, (size_t)(K ? K : 1) * N * 4));
+        CU(cudaMalloc(&dC, Mp * N * 4));
+        CU(cudaMemsetAsync(dA, 0, Mp * (K ? K : 1) * 4, s));
+        /* A arrives column major with leading dimension M: pad every column to Mp rows */
+        CU(cudaMemcpy2DAsync(dA, Mp * 4, A, (size_t)M * 4, (size_t)M * 4, K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dB, B, (size_t)K * N * 4, cudaMemcpyHostToDevice, s));
+        OK(ensure(ctx, ctx->flags32, 64));
+        CU(cudaMemsetAsync(ctx->flags32.p, 0, 64, s));
+        TcGemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.A = dA; g.lda = Mp; g.B = dB; g.ldb = N; g.M = (uint32_t)Mp; g.N = N; g.K = K; g.p = p;
+        g.C = dC; g.ldc = Mp; g.err = as<uint32_t>(ctx->flags32); g.mismatch = as<uint32_t>(ctx->flags32) + 8;
+        CU(cudaEventRecord(ctx->ev[0], s));
+        OK(launch_tc_gemm(ctx, g));
+        CU(cudaEventRecord(ctx->ev[1], s));
+        uint32_t h_err = 0;
+        CU(cudaMemcpyAsync(&h_err, ctx->flags32.p, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(C, (size_t)M * 4, dC, Mp * 4, (size_t)M * 4, N, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (h_err) return fail(ctx, F4LA_ERR_CUDA, "tensor-core product reported error bits 0x%x (64: pipeline wait expired)", h_err);
+        if (kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); *kernel_ms = ms; }
+        return F4LA_OK;
+    };
+    rc = body();
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
     return rc;
 }
 
