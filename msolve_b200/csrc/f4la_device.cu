@@ -61,7 +61,7 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf sched, items, flowflags, refcnt;
+    DevBuf sched, items, flowflags, refcnt, tcA, tcB, scB, scFlagA, scFlagB, scList, scCnt, scP;
     int           ge_mode = 0;          /* F4LA_B200_GE: (default) batched with the batch's pivot columns in shared memory;
                                            "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
                                            elimination pass per pivot (the fallbacks for very tall blocks, kept selectable for A-B) */
@@ -72,6 +72,9 @@ struct f4la_ctx {
     uint64_t      compress_attempts = 0, compress_rejected = 0, compress_escalated = 0;
     uint32_t      compress_rows = 768;  /* F4LA_B200_COMPRESS_ROWS: combinations of the first attempt (x4 per escalation) */
     uint32_t      ge_batch = 8, ge_miss_limit = 4;   /* F4LA_B200_GE_BATCH (<= 32), F4LA_B200_GE_MISSES: pivots per batch, empty visits that end one */
+    int           schur_tc = 1;         /* F4LA_B200_SCHUR_TC=0: non-pivot columns in the dataflow kernel instead of the tensor-core Schur product */
+    double        schur_min_macs = 2e9; /* F4LA_B200_SCHUR_MIN: smallest (non-pivot entries x lower rows) for the tensor path */
+    bool          schur_attr_set = false;
     int           tc_verify = 1;        /* F4LA_B200_TC=0: verification product on the CUDA cores (k_ge_verify) instead of tcgen05 */
     bool          tc_attr_set = false;
     uint64_t      tc_launches = 0;
@@ -260,7 +263,15 @@ int launch_tc_gemm(f4la_ctx *ctx, TcGemmArgs g)
     }
     g.w32 = (uint32_t)((1ull << 32) % g.p);
     g.pinv = ~0ULL / g.p;
-    dim3 grid(g.M / kTcBM, (g.N + kTcBN - 1) / kTcBN);
+    const uint32_t mblk = g.M / kTcBM, nblk = (g.N + kTcBN - 1) / kTcBN, nkb = (g.K + kTcBK - 1) / kTcBK;
+    /* both operands once, as limb planes in the shared-memory image of the pipeline stages */
+    OK(ensure(ctx, ctx->tcA, (size_t)mblk * nkb * kTcStageA));
+    OK(ensure(ctx, ctx->tcB, (size_t)nblk * nkb * kTcStageB));
+    g.Asplit = as<uint8_t>(ctx->tcA); g.Bsplit = as<uint8_t>(ctx->tcB);
+    k_tc_split_a<<<dim3(mblk, nkb), 128, 0, ctx->stream>>>(g);
+    k_tc_split_b<<<dim3(nblk, nkb), 128, 0, ctx->stream>>>(g);
+    note_launch(ctx, 2, __LINE__);
+    dim3 grid(mblk, nblk);
     k_tc_gemm_modp<<<grid, kTcThreads, kTcSmemBytes, ctx->stream>>>(g);
     note_launch(ctx, 1, __LINE__);
     ctx->tc_launches++;
@@ -571,9 +582,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     note_launch(ctx, 1, __LINE__);
     CU(cudaMemcpyAsync(h_small, as<uint32_t>(ctx->col_ptr) + nc, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h_small + 1, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_small + 2, as<uint32_t>(ctx->col_ptr) + ncl, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     const uint32_t nnz_pull = h_small[0];
+    const uint32_t nnz_schur = nnz_pull - h_small[2];        /* pull-list entries of the columns without pivot */
     if (h_small[1])
         return fail(ctx, F4LA_ERR_ARG, "malformed pivot rows (error bits 0x%x: 1 lead not first, 2 not upper "
                     "triangular, 4 column out of range, 8 lead coefficient != 1, 32 duplicate pivot column)", h_small[1]);
@@ -644,10 +657,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint32_t rank = 0, Rc = 0, nchunks = 0, G = 0, n_items = 0, maxrank = 0;
     uint64_t ld = 0;
     int T = 1, n_flow_ev = 0;
-    bool items_built = false;
+    bool items_built = false, schur = false, schur_b_built = false;
     uint32_t *Dm = nullptr;
     uint64_t ge_ld = 0;               /* leading dimension of the block the reduced rows are read from */
     uint32_t echelon_path = 0;
+    uint32_t schur_nseg = 1;
     bool rows_are_combinations = false;   /* the block that was eliminated holds random combinations, not lower rows */
     const uint32_t rba_words = (nru + 31) / 32;
 
@@ -672,6 +686,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
     CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));
 
+    /* The columns without pivot have no dependents: V[ncl + j] = X + M * Bneg is a dense-times-sparse product.
+     * When it is large it runs on the tensor cores over the non-zero 64 x 64 tiles of B (f4la_tc.cuh), and the
+     * dataflow kernel only solves the pivot columns. */
+    if (!items_built)
+        schur = ctx->schur_tc && ncl >= 1024 && ncr >= 64 && nrl >= 256 && (ncl + kTcBK - 1) / kTcBK < 65536 &&
+                (double)nnz_schur * nrl >= ctx->schur_min_macs;
     /* dataflow schedule: items in (level, length class) order, then the non-pivot columns */
     if (!items_built) {
         items_built = true;
@@ -689,7 +709,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                     items.push_back(((q - first) << 5) | (cnt << 1));
                 }
         }
-        for (uint32_t k = 0; k < ncr; ++k) items.push_back(((na + k) << 5) | (1u << 1) | 1u);
+        if (!schur)
+            for (uint32_t k = 0; k < ncr; ++k) items.push_back(((na + k) << 5) | (1u << 1) | 1u);
         n_items = (uint32_t)items.size();
         OK(ensure(ctx, ctx->sched, ((size_t)na + ncr + 1) * 4));
         OK(ensure(ctx, ctx->items, ((size_t)n_items + 1) * 4));
@@ -749,6 +770,55 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
+        if (schur) {
+            SchurArgs sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.V = as<uint32_t>(ctx->V); sa.nc = nc; sa.ncl = ncl; sa.ncr = ncr; sa.Rc = Rc; sa.G = g;
+            sa.col_ptr = as<uint32_t>(ctx->col_ptr); sa.ent = as<uint2>(ctx->ent);
+            sa.mblk = g * (Rc / kTcBM); sa.nblk = (ncr + kTcBN - 1) / kTcBN; sa.nkb = (ncl + kTcBK - 1) / kTcBK;
+            sa.ldp = (uint64_t)sa.mblk * kTcBM;
+            sa.out = as<uint32_t>(ctx->D); sa.out_ld = ld; sa.chunk0 = c0;
+            sa.p = p; sa.w32 = (uint32_t)((1ull << 32) % p); sa.pinv = pinv; sa.err = d_err;
+            OK(ensure(ctx, ctx->scB, (size_t)sa.nblk * sa.nkb * kTcStageB));
+            OK(ensure(ctx, ctx->scFlagB, (size_t)sa.nblk * sa.nkb + 16));
+            OK(ensure(ctx, ctx->scList, (size_t)sa.nblk * sa.nkb * 4 + 16));
+            OK(ensure(ctx, ctx->scCnt, (size_t)sa.nblk * 4 + 16));
+            OK(ensure(ctx, ctx->tcA, (size_t)sa.mblk * sa.nkb * kTcStageA));
+            OK(ensure(ctx, ctx->scFlagA, (size_t)sa.mblk * sa.nkb + 16));
+            sa.Asplit = as<uint8_t>(ctx->tcA); sa.Bsplit = as<uint8_t>(ctx->scB);
+            sa.flagA = as<uint8_t>(ctx->scFlagA); sa.flagB = as<uint8_t>(ctx->scFlagB);
+            sa.list = as<uint32_t>(ctx->scList); sa.list_cnt = as<uint32_t>(ctx->scCnt);
+            if (!schur_b_built) {
+                /* B does not depend on the lower rows: built once per matrix */
+                schur_b_built = true;
+                CU(cudaMemsetAsync(ctx->scB.p, 0, (size_t)sa.nblk * sa.nkb * kTcStageB, s));
+                CU(cudaMemsetAsync(ctx->scFlagB.p, 0, (size_t)sa.nblk * sa.nkb, s));
+                k_schur_b_build<<<blocks_for_warps(ncr), 256, 0, s>>>(sa);
+                k_schur_lists<<<sa.nblk, 256, 0, s>>>(sa);
+                note_launch(ctx, 2, __LINE__);
+                uint32_t *h_cnt = (uint32_t *)ctx->h_small.p + 512;
+                OK(ensure_host(ctx, ctx->h_small, ((size_t)sa.nblk + 1024) * 4));
+                h_cnt = (uint32_t *)ctx->h_small.p + 512;
+                CU(cudaMemcpyAsync(h_cnt, ctx->scCnt.p, (size_t)sa.nblk * 4, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                uint32_t mx = 0;
+                for (uint32_t k = 0; k < sa.nblk; ++k) mx = h_cnt[k] > mx ? h_cnt[k] : mx;
+                schur_nseg = (mx + kSchurSeg - 1) / kSchurSeg;
+                if (schur_nseg < 1) schur_nseg = 1;
+            }
+            sa.nseg = schur_nseg;
+            OK(ensure(ctx, ctx->scP, (size_t)sa.nseg * ncr * sa.ldp * 4));
+            sa.P = as<uint32_t>(ctx->scP);
+            if (!ctx->schur_attr_set) {
+                CU(cudaFuncSetAttribute(k_schur_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+                ctx->schur_attr_set = true;
+            }
+            k_schur_a_split<<<dim3(sa.mblk, sa.nkb), 128, 0, s>>>(sa);
+            k_schur_gemm<<<dim3(sa.mblk, sa.nblk, sa.nseg), kTcThreads, kTcSmemBytes, s>>>(sa);
+            k_schur_combine<<<dim3(ncr, (g * Rc + 255) / 256), 256, 0, s>>>(sa);
+            note_launch(ctx, 3, __LINE__);
+        }
+        /* "hot kernel" time = the reduction by the known pivots: dataflow solve + (when used) the tensor-core Schur product */
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) { CU(cudaEventRecord(ctx->flow_ev[n_flow_ev + 1], s)); n_flow_ev += 2; }
         if (want_rba && rba_words) {
             dim3 grid(rba_words, g * (Rc / 128));
@@ -1090,6 +1160,10 @@ f4la_ctx *f4la_b200_create(int device)
     if (gb && atoi(gb) >= 2 && atoi(gb) <= (int)kGeBatchCached) ctx->ge_batch = (uint32_t)atoi(gb);
     const char *gm = getenv("F4LA_B200_GE_MISSES");
     if (gm && atoi(gm) >= 1) ctx->ge_miss_limit = (uint32_t)atoi(gm);
+    const char *sct = getenv("F4LA_B200_SCHUR_TC");
+    if (sct) ctx->schur_tc = atoi(sct) != 0;
+    const char *scm = getenv("F4LA_B200_SCHUR_MIN");
+    if (scm && atof(scm) >= 0) ctx->schur_min_macs = atof(scm);
     const char *tcv = getenv("F4LA_B200_TC");
     if (tcv) ctx->tc_verify = atoi(tcv) != 0;
     const char *zc = getenv("F4LA_B200_ZEROCOPY");
@@ -1115,7 +1189,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
     for (auto b : bufs) free_dev(*b);
