@@ -61,8 +61,12 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
+    DevBuf gebar;
+    size_t        fused_smem_optin = 0;
+    int           coop_ok = 0;          /* device supports cooperative launches (k_ge_fused) */
     DevBuf sched, items, flowflags, refcnt, tcA, tcB, scB, scFlagA, scFlagB, scList, scCnt, scP;
-    int           ge_mode = 0;          /* F4LA_B200_GE: (default) batched with the batch's pivot columns in shared memory;
+    int           ge_mode = 0;          /* F4LA_B200_GE: (default) one persistent cooperative launch (k_ge_fused); "batched": two launches per
+                                           batch of 8 pivots with the batch's pivot columns in shared memory (the round-1 default);
                                            "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
                                            elimination pass per pivot (the fallbacks for very tall blocks, kept selectable for A-B) */
     size_t        cached_smem_optin = 0, compress_smem_optin = 0;
@@ -305,7 +309,46 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
     if ((size_t)nrows4 * 5 + 64 <= smem_cap)
         nb_fit = (uint32_t)((smem_cap - 64 - nrows4) / ((size_t)nrows4 * 4)) - 1;
     if (nb_fit > ctx->ge_batch) nb_fit = ctx->ge_batch;
-    if (nb_fit >= 2 && ctx->ge_mode == 0) {
+    /* one persistent cooperative launch: panels of up to 32 pivots factored in shared memory, rank-b updates
+     * behind grid barriers (k_ge_fused); needs a panel of >= 2 columns of nrows4 words in shared memory */
+    uint32_t pw = 0;
+    {
+        const size_t dyn_cap = (size_t)200 * 1024;
+        if ((size_t)nrows4 * 9 <= dyn_cap) pw = (uint32_t)((dyn_cap - nrows4) / ((size_t)nrows4 * 4));
+        if (pw > kPanelMax) pw = kPanelMax;
+    }
+    if (pw >= 2 && ctx->ge_mode == 0 && ctx->coop_ok) {
+        const size_t dyn = (size_t)pw * nrows4 * 4 + nrows4;
+        if (dyn > ctx->fused_smem_optin) {
+            CU(cudaFuncSetAttribute(k_ge_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * 1024)));
+            ctx->fused_smem_optin = (size_t)200 * 1024;
+        }
+        OK(ensure(ctx, ctx->gebar, 64));
+        CU(cudaMemsetAsync(ctx->gebar.p, 0, 64, s));
+        k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
+        note_launch(ctx, 1, __LINE__);
+        GeFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        a.D = Dm; a.ld = ld; a.nrows = nrl; a.nrows4 = nrows4; a.ncr = ncr; a.pw = pw;
+        a.colflag = as<uint8_t>(ctx->colflag); a.used = as<uint8_t>(ctx->used); a.ispiv = as<uint8_t>(ctx->ispiv);
+        a.st = as<GEState>(ctx->gestate);
+        a.pivcol = as<uint32_t>(ctx->pivcol); a.pivrow = as<uint32_t>(ctx->pivrow); a.pivinv = as<uint32_t>(ctx->pivinv);
+        a.p = p; a.two64 = (uint32_t)(((~0ull) % p + 1) % p); a.pinv = pinv;
+        a.bar = as<uint32_t>(ctx->gebar); a.err = as<uint32_t>(ctx->flags32);
+        a.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6); a.max_iter = ncr + 8;
+        unsigned grid = (ncr + 31) / 32;
+        if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;
+        if (grid < 1) grid = 1;
+        void *kargs[] = {&a};
+        CU(cudaLaunchCooperativeKernel((const void *)k_ge_fused, dim3(grid), dim3(kFusedThreads), kargs, dyn, s));
+        note_launch(ctx, 1, __LINE__);
+        CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        if (!h_state->done)
+            return fail(ctx, F4LA_ERR_CUDA, "fused Gauss-Jordan did not finish (rank %u, next column %u of %u)", h_state->rank,
+                        h_state->next_col, ncr);
+    } else if (nb_fit >= 2 && (ctx->ge_mode == 0 || ctx->ge_mode == 3)) {
         /* batched, pivot columns of the batch cached in shared memory by both passes */
         const size_t disc_smem = ((size_t)nb_fit + 1) * nrows4 * 4 + nrows4, upd_smem = (size_t)nb_fit * nrows4 * 4 + nrows4;
         if (disc_smem > ctx->cached_smem_optin) {
@@ -1141,6 +1184,7 @@ f4la_ctx *f4la_b200_create(int device)
     f4la_ctx *ctx = new f4la_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->coop_ok = prop.cooperativeLaunch;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
@@ -1149,7 +1193,7 @@ f4la_ctx *f4la_b200_create(int device)
     for (auto &e : ctx->dbg_ev) cudaEventCreate(&e);
     for (auto &e : ctx->flow_ev) cudaEventCreate(&e);
     const char *ge = getenv("F4LA_B200_GE");
-    ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : 0;
+    ctx->ge_mode = !ge ? 0 : !strcmp(ge, "columnwise") ? 2 : !strcmp(ge, "uncached") ? 1 : !strcmp(ge, "batched") ? 3 : 0;
     const char *cm = getenv("F4LA_B200_COMPRESS");
     if (cm) ctx->ge_compress = atoi(cm) != 0;
     const char *cr = getenv("F4LA_B200_COMPRESS_ROWS");
@@ -1189,7 +1233,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->gebar, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
     for (auto b : bufs) free_dev(*b);

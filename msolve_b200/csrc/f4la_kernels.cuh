@@ -1471,4 +1471,267 @@ __global__ void k_transpose_rows(const uint32_t *__restrict__ D, uint64_t ld, ui
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* trailing block, one persistent launch: panel factorisation + rank-b update behind grid barriers  */
+/* ------------------------------------------------------------------------------------------------ */
+/* The batched Gauss-Jordan above costs two launches per 8 pivots plus a host round trip every four batches
+ * (K12: ~270 batches x (40 us single-CTA discovery + 32 us update + gaps) = 29 of the 127 ms of a step).
+ * k_ge_fused runs the whole elimination in ONE cooperative launch (one CTA per SM, all co-resident):
+ *   factor  (CTA 0)   gathers the next <= 32 flagged columns into shared memory AT ONCE and eliminates inside
+ *                     the panel: a warp per column keeps "first non-zero row that is not a pivot row yet",
+ *                     the leftmost column with a candidate yields the next pivot, one pass of all warps
+ *                     applies it to the panel columns to its right and refreshes their candidates -- about a
+ *                     microsecond per pivot instead of one visited column at a time;
+ *   update  (all CTAs) the rank-b update of every column right of the panel's first pivot, the batch's pivot
+ *                     columns in shared memory, multipliers by the lane-distributed recurrence (as in
+ *                     k_ge_batch_update_cached), flags refreshed;
+ * separated by grid barriers (a monotone arrival counter; data written by other SMs is read with ld.cg, L1
+ * is not coherent).  The host reads the rank back once.  A watchdog on the barrier makes a stuck grid give up
+ * with an error bit instead of hanging the GPU. */
+
+constexpr uint32_t kPanelMax = 32;
+constexpr int kFusedThreads = 1024;
+constexpr uint32_t kErrGeBarrier = 128u;
+
+struct GeFusedArgs {
+    uint32_t *D; uint64_t ld; uint32_t nrows, nrows4, ncr, pw;     /* pw = panel width (<= kPanelMax, fits shared memory) */
+    uint8_t *colflag, *used, *ispiv; GEState *st;
+    uint32_t *pivcol, *pivrow, *pivinv;
+    uint32_t p, two64; uint64_t pinv;
+    uint32_t *bar;            /* [0] arrival counter, [1] abort flag; zeroed before the launch */
+    uint32_t *err; uint64_t watchdog_ns; uint32_t max_iter;
+};
+
+/* true = abort (watchdog expired somewhere) */
+__device__ __forceinline__ bool ge_grid_barrier(const GeFusedArgs &A, uint32_t &round)
+{
+    __shared__ uint32_t s_abort;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t target = (++round) * gridDim.x;
+        atomicAdd(A.bar, 1u);
+        uint32_t spins = 0, ab = 0;
+        uint64_t t0 = 0;
+        while (ld_relaxed_flag(A.bar) < target) {
+            if (ld_relaxed_flag(A.bar + 1)) { ab = 1; break; }
+            __nanosleep(32);
+            if ((++spins & 1023u) == 0) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > A.watchdog_ns) { atomicOr(A.err, kErrGeBarrier); atomicExch(A.bar + 1, 1u); ab = 1; break; }
+            }
+        }
+        __threadfence();
+        s_abort = ab;
+    } else {
+        ++round;
+    }
+    __syncthreads();
+    return s_abort != 0;
+}
+
+/* CTA 0: the next panel.  dynamic smem: [pw][nrows4] panel columns | [nrows4] used bytes */
+__device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t *s_used)
+{
+    __shared__ uint32_t s_cols[kPanelMax], s_cand[kPanelMax], s_pj[kPanelMax], s_prow[kPanelMax], s_pinv[kPanelMax];
+    __shared__ uint32_t s_wcnt[kFusedThreads / 32], s_m, s_next, s_sel, s_mult[kPanelMax];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nrows = A.nrows, nrows4 = A.nrows4, ncr = A.ncr, pw = A.pw, p = A.p;
+    GEState *st = A.st;
+    if (__ldcg(&st->done)) {
+        if (tid == 0) st->cur_col = __ldcg(&st->rank);          /* nothing pending: the update is a no-op */
+        return;
+    }
+    const uint32_t k0 = __ldcg(&st->rank);
+    const uint32_t c0 = __ldcg(&st->next_col);
+    for (uint32_t r = tid; r < nrows4; r += kFusedThreads) s_used[r] = r < nrows ? __ldcg(&A.used[r]) : (uint8_t)1;
+    if (tid == 0) { s_m = 0; s_next = ncr; }
+    __syncthreads();
+    /* gather the next <= pw flagged columns, in order */
+    for (uint32_t base = c0; base < ncr; base += kFusedThreads) {
+        const uint32_t k = base + tid;
+        const bool f = k < ncr && __ldcg(&A.colflag[k]) != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = s_m;
+        for (uint32_t w = 0; w < warp; ++w) off += s_wcnt[w];
+        const uint32_t idx = off + __popc(bal & ((1u << lane) - 1));
+        if (f && idx < pw) s_cols[idx] = k;
+        if (f && idx == pw - 1) s_next = k + 1;                   /* the panel is full after this column */
+        __syncthreads();
+        if (tid == 0) { uint32_t t = s_m; for (uint32_t w = 0; w < kFusedThreads / 32; ++w) t += s_wcnt[w]; s_m = t; }
+        __syncthreads();
+        if (s_m >= pw) break;
+    }
+    const uint32_t m = min(s_m, pw);
+    const uint32_t next_col = s_m >= pw ? s_next : ncr;
+    const bool exhausted = next_col >= ncr;
+    if (m == 0) {
+        if (tid == 0) { st->cur_col = k0; st->rank = k0; st->next_col = ncr; st->done = 1; }
+        return;
+    }
+    /* load the panel; candidates = first non-zero row that is not a pivot row yet */
+    for (uint32_t j = warp; j < m; j += kFusedThreads / 32) {
+        const uint32_t *g = A.D + (size_t)s_cols[j] * A.ld;
+        uint32_t cand = 0xffffffffu;
+        for (uint32_t r = lane; r < nrows4; r += 32) {
+            const uint32_t v = r < nrows ? __ldcg(&g[r]) : 0u;
+            s_panel[(size_t)j * nrows4 + r] = v;
+            if (v && !s_used[r]) cand = min(cand, r);
+        }
+        for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0) s_cand[j] = cand;
+    }
+    __syncthreads();
+    uint32_t np = 0, cur = 0;
+    for (;;) {
+        /* leftmost column at or after `cur` with a candidate */
+        if (tid < 32) {
+            uint32_t j = cur + lane;
+            const bool has = j < m && s_cand[j] != 0xffffffffu;
+            const uint32_t bal = __ballot_sync(0xffffffffu, has);
+            if (lane == 0) s_sel = bal ? cur + (uint32_t)__ffs(bal) - 1 : 0xffffffffu;
+        }
+        __syncthreads();
+        const uint32_t js = s_sel;
+        if (js == 0xffffffffu) break;
+        const uint32_t rs = s_cand[js];
+        const uint32_t *pc = s_panel + (size_t)js * nrows4;
+        if (tid == 0) {
+            const uint32_t inv = modinv(pc[rs], p);
+            s_pj[np] = js; s_prow[np] = rs; s_pinv[np] = inv;
+            s_used[rs] = 1;
+        }
+        __syncthreads();
+        const uint32_t inv = s_pinv[np];
+        /* apply the pivot to the panel columns right of it, refresh their candidates */
+        for (uint32_t j = js + 1 + warp; j < m; j += kFusedThreads / 32) {
+            uint32_t *col = s_panel + (size_t)j * nrows4;
+            const uint32_t e = col[rs];
+            const uint32_t neg = e ? p - mulmod(e, inv, p, A.pinv) : 0u;
+            uint32_t cand = 0xffffffffu;
+            for (uint32_t r = lane; r < nrows4; r += 32) {
+                uint32_t v = col[r];
+                if (neg && r != rs) {
+                    const uint32_t f = pc[r];
+                    if (f) { v = mod_u64((uint64_t)v + (uint64_t)neg * f, p, A.pinv); col[r] = v; }
+                }
+                if (v && !s_used[r]) cand = min(cand, r);
+            }
+            for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+            if (lane == 0) s_cand[j] = cand;
+        }
+        __syncthreads();
+        ++np;
+        cur = js + 1;
+    }
+    /* pivot columns are final (they carry the multipliers of their pivot): write them back */
+    for (uint32_t k = warp; k < np; k += kFusedThreads / 32) {
+        const uint32_t j = s_pj[k];
+        uint32_t *g = A.D + (size_t)s_cols[j] * A.ld;
+        const uint32_t *col = s_panel + (size_t)j * nrows4;
+        for (uint32_t r = lane; r < nrows; r += 32) g[r] = col[r];
+        if (lane == 0) {
+            A.pivcol[k0 + k] = s_cols[j]; A.pivrow[k0 + k] = s_prow[k]; A.pivinv[k0 + k] = s_pinv[k];
+            A.used[s_prow[k]] = 1; A.ispiv[s_cols[j]] = 1;
+        }
+    }
+    if (tid == 0) {
+        st->cur_col = k0; st->rank = k0 + np; st->next_col = next_col;
+        if (exhausted) st->done = 1;
+        st->visits += m; st->batches += np != 0;
+    }
+    (void)s_mult;
+}
+
+/* all CTAs: rank-b update with the pivots [k0, k1), the body of k_ge_batch_update_cached with L2 loads of
+ * everything other CTAs may have written.  dynamic smem: [nb][nrows4] pivot columns | [nrows4] used bytes */
+__device__ void ge_fused_update(const GeFusedArgs &A, uint32_t k0, uint32_t k1, uint32_t *s_piv, uint8_t *s_used)
+{
+    __shared__ uint32_t s_pc[kPanelMax], s_pr[kPanelMax], s_pi[kPanelMax];
+    __shared__ uint32_t s_x[kPanelMax][kPanelMax + 1];
+    __shared__ uint32_t s_neg[kFusedThreads / 32][kPanelMax];
+    const uint32_t nb = k1 - k0, nrows = A.nrows, nrows4 = A.nrows4, ncr = A.ncr, p = A.p;
+    const uint64_t pinv = A.pinv;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t first = __ldcg(&A.pivcol[k0]);
+    const uint32_t nwarps = gridDim.x * (kFusedThreads / 32);
+    const uint32_t gwarp = blockIdx.x * (kFusedThreads / 32) + (tid >> 5);
+    if (first + 1 + blockIdx.x * (kFusedThreads / 32) >= ncr) return;      /* no column for this CTA (uniform) */
+    if (tid < nb) { s_pc[tid] = __ldcg(&A.pivcol[k0 + tid]); s_pr[tid] = __ldcg(&A.pivrow[k0 + tid]); s_pi[tid] = __ldcg(&A.pivinv[k0 + tid]); }
+    __syncthreads();
+    for (uint32_t k = 0; k < nb; ++k) {
+        const uint32_t *src = A.D + (size_t)s_pc[k] * A.ld;
+        const uint32_t own = s_pr[k];
+        for (uint32_t r = tid; r < nrows4; r += kFusedThreads)
+            s_piv[(size_t)k * nrows4 + r] = (r < nrows && r != own) ? __ldcg(&src[r]) : 0u;
+    }
+    for (uint32_t r = tid; r < nrows4; r += kFusedThreads) s_used[r] = r < nrows ? __ldcg(&A.used[r]) : (uint8_t)1;
+    __syncthreads();
+    for (uint32_t q = tid; q < kPanelMax * kPanelMax; q += kFusedThreads) {
+        const uint32_t k = q / kPanelMax, j = q % kPanelMax;
+        s_x[k][j] = (k < nb && j < nb) ? s_piv[(size_t)k * nrows4 + s_pr[j]] : 0u;
+    }
+    __syncthreads();
+    for (uint32_t c = first + 1 + gwarp; c < ncr; c += nwarps) {
+        if (__ldcg(&A.ispiv[c])) continue;
+        uint32_t *g = A.D + (size_t)c * A.ld;
+        uint32_t e = lane < nb ? __ldcg(&g[s_pr[lane]]) : 0u, neg = 0;
+        bool touched = false;
+        for (uint32_t k = 0; k < nb; ++k) {
+            const uint32_t ek = __shfl_sync(0xffffffffu, e, k);
+            if (s_pc[k] >= c || ek == 0) continue;
+            const uint32_t ng = p - mulmod(ek, s_pi[k], p, pinv);
+            touched = true;
+            if (lane == k) neg = ng;
+            if (lane > k && lane < nb) e = mod_u64((uint64_t)e + (uint64_t)ng * s_x[k][lane], p, pinv);
+        }
+        uint32_t *my_neg = s_neg[tid >> 5];
+        my_neg[lane] = neg;
+        __syncwarp();
+        int any = 0;
+        for (uint32_t r4 = lane * 4; r4 < nrows4; r4 += 128) {
+            uint4 v = __ldcg(reinterpret_cast<const uint4 *>(g + r4));
+            if (touched) {
+                Acc a[4] = {{(uint64_t)v.x, 0u}, {(uint64_t)v.y, 0u}, {(uint64_t)v.z, 0u}, {(uint64_t)v.w, 0u}};
+                for (uint32_t k = 0; k < nb; ++k) {
+                    const uint32_t nk = my_neg[k];
+                    if (nk) {
+                        const uint4 f = *reinterpret_cast<const uint4 *>(s_piv + (size_t)k * nrows4 + r4);
+                        mac<true>(a[0], f.x, nk); mac<true>(a[1], f.y, nk);
+                        mac<true>(a[2], f.z, nk); mac<true>(a[3], f.w, nk);
+                    }
+                }
+                v.x = fold_acc<true>(a[0], 0u, p, pinv, A.two64); v.y = fold_acc<true>(a[1], 0u, p, pinv, A.two64);
+                v.z = fold_acc<true>(a[2], 0u, p, pinv, A.two64); v.w = fold_acc<true>(a[3], 0u, p, pinv, A.two64);
+                *reinterpret_cast<uint4 *>(g + r4) = v;
+            }
+            const uchar4 u = *reinterpret_cast<const uchar4 *>(s_used + r4);
+            any |= (v.x && !u.x) | (v.y && !u.y) | (v.z && !u.z) | (v.w && !u.w);
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) A.colflag[c] = (uint8_t)(any != 0);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_ge_fused(const GeFusedArgs A)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint8_t *s_used = reinterpret_cast<uint8_t *>(s_dyn + (size_t)A.pw * A.nrows4);
+    uint32_t round = 0;
+    for (uint32_t it = 0; it < A.max_iter; ++it) {
+        if (blockIdx.x == 0) ge_panel_factor(A, s_dyn, s_used);
+        if (ge_grid_barrier(A, round)) return;
+        const uint32_t k0 = __ldcg(&A.st->cur_col), k1 = __ldcg(&A.st->rank), done = __ldcg(&A.st->done);
+        if (k0 < k1) ge_fused_update(A, k0, k1, s_dyn, s_used);
+        else if (done) return;
+        if (ge_grid_barrier(A, round)) return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.err, kErrGeBarrier);       /* did not terminate */
+}
+
 } /* namespace f4la */

@@ -295,7 +295,7 @@ def test_gpu_backend_inside_reference_f4_large(name):
     assert gb.digest() == want["digest"]
 
 
-@pytest.mark.parametrize("mode", ["uncached", "columnwise"])
+@pytest.mark.parametrize("mode", ["batched", "uncached", "columnwise"])
 def test_gpu_elimination_fallbacks(monkeypatch, mode):
     """Tall trailing blocks fall back from the shared-memory-cached batches to batches that re-read
     the pivot columns from L2 ("uncached"), and to one find + one elimination pass per pivot
