@@ -340,11 +340,21 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;
         if (grid < 1) grid = 1;
         void *kargs[] = {&a};
+        if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[0], s));
         CU(cudaLaunchCooperativeKernel((const void *)k_ge_fused, dim3(grid), dim3(kFusedThreads), kargs, dyn, s));
+        if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[1], s));
         note_launch(ctx, 1, __LINE__);
         CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s));
+        if (ctx->debug) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->dbg_ev[0], ctx->dbg_ev[1]);
+            fprintf(stderr, "[f4la debug] k_ge_fused %u x %u: %.3f ms, grid %u, panel width %u; CTA 0 kilo-cycles: gather %llu load %llu "
+                    "select+inverse %llu eliminate %llu write-back %llu update %llu barriers %llu total %llu\n", nrl, ncr, ms, grid, pw,
+                    h_state->t[0] / 1000, h_state->t[1] / 1000, h_state->t[2] / 1000, h_state->t[3] / 1000, h_state->t[4] / 1000,
+                    h_state->t[5] / 1000, h_state->t[6] / 1000, h_state->t[7] / 1000);
+        }
         if (!h_state->done)
             return fail(ctx, F4LA_ERR_CUDA, "fused Gauss-Jordan did not finish (rank %u, next column %u of %u)", h_state->rank,
                         h_state->next_col, ncr);

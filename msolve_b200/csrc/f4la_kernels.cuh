@@ -809,6 +809,8 @@ struct GEState {
     uint32_t visits;     /* columns loaded by the discovery (statistics)     */
     uint32_t batches;    /* non-empty batches (statistics)                   */
     uint32_t pad;
+    unsigned long long t[8];   /* k_ge_fused, CTA 0, clock cycles: gather, load, select + inverse, eliminate, write-back,
+                                  update, barrier waits, total */
 };
 
 /* colflag[c] = 1 iff column c has a non-zero entry in a row that is not a
@@ -1535,7 +1537,7 @@ __device__ __forceinline__ bool ge_grid_barrier(const GeFusedArgs &A, uint32_t &
 __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t *s_used)
 {
     __shared__ uint32_t s_cols[kPanelMax], s_cand[kPanelMax], s_pj[kPanelMax], s_prow[kPanelMax], s_pinv[kPanelMax];
-    __shared__ uint32_t s_wcnt[kFusedThreads / 32], s_m, s_next, s_sel, s_mult[kPanelMax];
+    __shared__ uint32_t s_wcnt[kFusedThreads / 32], s_m, s_next, s_sel, s_mult[kPanelMax], s_multw[kPanelMax], s_scale[kPanelMax], s_isc[kPanelMax], s_pivw;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nrows = A.nrows, nrows4 = A.nrows4, ncr = A.ncr, pw = A.pw, p = A.p;
     GEState *st = A.st;
@@ -1545,6 +1547,7 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
     }
     const uint32_t k0 = __ldcg(&st->rank);
     const uint32_t c0 = __ldcg(&st->next_col);
+    long long tk0 = clock64(), tk1, tsel = 0, telim = 0;
     for (uint32_t r = tid; r < nrows4; r += kFusedThreads) s_used[r] = r < nrows ? __ldcg(&A.used[r]) : (uint8_t)1;
     if (tid == 0) { s_m = 0; s_next = ncr; }
     __syncthreads();
@@ -1572,6 +1575,9 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
         if (tid == 0) { st->cur_col = k0; st->rank = k0; st->next_col = ncr; st->done = 1; }
         return;
     }
+    tk1 = clock64();
+    if (tid == 0) st->t[0] += tk1 - tk0;
+    tk0 = tk1;
     /* load the panel; candidates = first non-zero row that is not a pivot row yet */
     for (uint32_t j = warp; j < m; j += kFusedThreads / 32) {
         const uint32_t *g = A.D + (size_t)s_cols[j] * A.ld;
@@ -1582,11 +1588,22 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
             if (v && !s_used[r]) cand = min(cand, r);
         }
         for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-        if (lane == 0) s_cand[j] = cand;
+        if (lane == 0) { s_cand[j] = cand; s_scale[j] = 1u; }
     }
     __syncthreads();
+    tk1 = clock64();
+    if (tid == 0) st->t[1] += tk1 - tk0;
     uint32_t np = 0, cur = 0;
+    /* Elimination inside the panel is FRACTION FREE: column j <- piv * column j - e_j * pivot column, i.e. the usual
+     * step times the constant piv.  Scaling a panel column by a non-zero constant is harmless: a column that never
+     * becomes a pivot column is discarded (the update pass recomputes it from memory), and a pivot column is only
+     * ever used relative to its own pivot entry (multiplier = entry x inverse of the pivot entry) -- except by the
+     * final extraction, which normalises ROWS with the inverse of the pivot entry; so the accumulated scale of every
+     * column is tracked and divided out when a pivot column is written back.  No modular inverse sits on the
+     * per-pivot critical path; the inverses are computed once per panel, in parallel. */
+    const uint32_t grp = tid >> 8, gt = tid & 255;          /* 4 groups of 256 threads: group g takes the columns js+1+g, +4, ... */
     for (;;) {
+        tk0 = clock64();
         /* leftmost column at or after `cur` with a candidate */
         if (tid < 32) {
             uint32_t j = cur + lane;
@@ -1599,40 +1616,54 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
         if (js == 0xffffffffu) break;
         const uint32_t rs = s_cand[js];
         const uint32_t *pc = s_panel + (size_t)js * nrows4;
-        if (tid == 0) {
-            const uint32_t inv = modinv(pc[rs], p);
-            s_pj[np] = js; s_prow[np] = rs; s_pinv[np] = inv;
-            s_used[rs] = 1;
+        const uint32_t piv = pc[rs];
+        __syncthreads();                                    /* everybody has read s_cand[js] / s_sel */
+        if (tid == 0) { s_pj[np] = js; s_prow[np] = rs; s_used[rs] = 1; s_pivw = shoup_pre(piv, p); }
+        if (tid > js && tid < m) {                          /* Shoup constants of the two fixed multipliers of a column */
+            const uint32_t e = s_panel[(size_t)tid * nrows4 + rs];
+            const uint32_t neg = e ? p - e : 0u;
+            s_mult[tid] = neg; s_multw[tid] = shoup_pre(neg, p);
+            s_cand[tid] = 0xffffffffu;
         }
         __syncthreads();
-        const uint32_t inv = s_pinv[np];
-        /* apply the pivot to the panel columns right of it, refresh their candidates */
-        for (uint32_t j = js + 1 + warp; j < m; j += kFusedThreads / 32) {
+        tk1 = clock64(); tsel += tk1 - tk0; tk0 = tk1;
+        /* column j <- piv * column j - e_j * pivot column (entry of the pivot row: piv * e_j); new candidates */
+        for (uint32_t j = js + 1 + grp; j < m; j += 4) {
             uint32_t *col = s_panel + (size_t)j * nrows4;
-            const uint32_t e = col[rs];
-            const uint32_t neg = e ? p - mulmod(e, inv, p, A.pinv) : 0u;
+            const uint32_t neg = s_mult[j], negw = s_multw[j], pivw = s_pivw;
             uint32_t cand = 0xffffffffu;
-            for (uint32_t r = lane; r < nrows4; r += 32) {
-                uint32_t v = col[r];
-                if (neg && r != rs) {
-                    const uint32_t f = pc[r];
-                    if (f) { v = mod_u64((uint64_t)v + (uint64_t)neg * f, p, A.pinv); col[r] = v; }
-                }
+#pragma unroll 3
+            for (uint32_t r = gt; r < nrows4; r += 256) {
+                const uint32_t f = r == rs ? 0u : pc[r];
+                uint32_t v = shoup_mul(col[r], piv, pivw, p) + shoup_mul(f, neg, negw, p);
+                v = v >= p ? v - p : v;
+                col[r] = v;
                 if (v && !s_used[r]) cand = min(cand, r);
             }
             for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-            if (lane == 0) s_cand[j] = cand;
+            if (lane == 0 && cand != 0xffffffffu) atomicMin(&s_cand[j], cand);
+            if (gt == 0) s_scale[j] = mulmod(s_scale[j], piv, p, A.pinv);
         }
         __syncthreads();
+        tk1 = clock64(); telim += tk1 - tk0;
         ++np;
         cur = js + 1;
     }
+    /* un-scaling factors and the inverses of the (true) pivot entries, all at once */
+    if (tid < np) {
+        const uint32_t isc = modinv(s_scale[s_pj[tid]], p);
+        s_isc[tid] = isc;
+        s_pinv[tid] = modinv(mulmod(s_panel[(size_t)s_pj[tid] * nrows4 + s_prow[tid]], isc, p, A.pinv), p);
+    }
+    __syncthreads();
+    tk0 = clock64();
     /* pivot columns are final (they carry the multipliers of their pivot): write them back */
     for (uint32_t k = warp; k < np; k += kFusedThreads / 32) {
         const uint32_t j = s_pj[k];
         uint32_t *g = A.D + (size_t)s_cols[j] * A.ld;
         const uint32_t *col = s_panel + (size_t)j * nrows4;
-        for (uint32_t r = lane; r < nrows; r += 32) g[r] = col[r];
+        const uint32_t isc = s_isc[k];
+        for (uint32_t r = lane; r < nrows; r += 32) g[r] = isc == 1u ? col[r] : mulmod(col[r], isc, p, A.pinv);
         if (lane == 0) {
             A.pivcol[k0 + k] = s_cols[j]; A.pivrow[k0 + k] = s_prow[k]; A.pivinv[k0 + k] = s_pinv[k];
             A.used[s_prow[k]] = 1; A.ispiv[s_cols[j]] = 1;
@@ -1642,6 +1673,7 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
         st->cur_col = k0; st->rank = k0 + np; st->next_col = next_col;
         if (exhausted) st->done = 1;
         st->visits += m; st->batches += np != 0;
+        st->t[2] += tsel; st->t[3] += telim; st->t[4] += clock64() - tk0;
     }
     (void)s_mult;
 }
@@ -1723,13 +1755,19 @@ k_ge_fused(const GeFusedArgs A)
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint8_t *s_used = reinterpret_cast<uint8_t *>(s_dyn + (size_t)A.pw * A.nrows4);
     uint32_t round = 0;
+    const bool t0 = blockIdx.x == 0 && threadIdx.x == 0;
+    const long long t_begin = clock64();
     for (uint32_t it = 0; it < A.max_iter; ++it) {
         if (blockIdx.x == 0) ge_panel_factor(A, s_dyn, s_used);
+        long long ta = clock64();
         if (ge_grid_barrier(A, round)) return;
+        long long tb = clock64();
         const uint32_t k0 = __ldcg(&A.st->cur_col), k1 = __ldcg(&A.st->rank), done = __ldcg(&A.st->done);
         if (k0 < k1) ge_fused_update(A, k0, k1, s_dyn, s_used);
-        else if (done) return;
+        else if (done) { if (t0) A.st->t[7] += clock64() - t_begin; return; }
+        long long tc = clock64();
         if (ge_grid_barrier(A, round)) return;
+        if (t0) { A.st->t[5] += tc - tb; A.st->t[6] += (tb - ta) + (clock64() - tc); }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.err, kErrGeBarrier);       /* did not terminate */
 }
