@@ -403,6 +403,22 @@ def run_gpu(args, rank, world):
     launches = (sum(a["kernel_launches"] for a in aggs_v) + sum(a["kernel_launches"] for a in aggs_f)
                 + pt["kernel_launches"])
 
+    # one-shot process: a fresh interpreter without torch runs the reference F4 with the backend once
+    # (tools/run_f4_gpu.py) -- what the msolve binary would pay, CUDA context and module load included
+    one_shot = None
+    if world == 1 and not args.no_cold:
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_f4_gpu.py"), args.workload, "--prime",
+                                  str(args.prime), "--threads", str(host_threads)], capture_output=True, text=True, timeout=900,
+                                 env=dict(os.environ, F4LA_B200_DEVICE=str(local)))
+            row = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            one_shot = {"what": "fresh process (no torch), one F4 run with all LA pointers on the GPU: tools/run_f4_gpu.py",
+                        "f4_seconds": row["f4_seconds_gpu_la"], "la_seconds": row["la_seconds_gpu"],
+                        "la_breakdown_ms": row["device_ms"], "bit_exact_vs_reference": row["bit_exact_vs_reference"]}
+            log(f"[bench] one-shot process: F4 {row['f4_seconds_gpu_la']} s, LA {row['la_seconds_gpu']} s")
+        except Exception as e:
+            one_shot = {"error": repr(e)}
+
     cpu_base = None
     if world == 1 and not args.no_cpu:
         cpu_base = cpu_baseline(recs, units_per, os.cpu_count() or 1, 3, cpu)
@@ -447,8 +463,9 @@ def run_gpu(args, rank, world):
                         "what": "f4la_b200_reduce() from pinned flat arrays",
                         "h2d_bytes_per_step": int(sum(a["bytes_h2d"] for a in aggs_f) / steps),
                         "d2h_bytes_per_step": int(sum(a["bytes_d2h"] for a in aggs_f) / steps)},
-           "cold_first_f4_run": {"what": "first F4 run of the process (what a one-shot msolve process pays): CUDA context, "
-                                         "module load, first staging / device allocations included",
+           "one_shot_process": one_shot,
+           "first_f4_run_of_this_process": {"what": "first F4 run inside the bench process (torch and NCCL loaded): first "
+                                                    "device / staging allocations and module load included",
                                  "f4_seconds": cold["f4_seconds"], "la_seconds": cold["la_seconds"],
                                  "la_breakdown_ms": {k: ct[k] for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce",
                                                                         "ms_echelon", "ms_d2h", "ms_materialize")}},
@@ -710,6 +727,7 @@ def main():
     ap.add_argument("--no-qq", action="store_true", help="skip the QQ multi-modular block")
     ap.add_argument("--no-prob", action="store_true", help="skip the probabilistic-mode block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cold", action="store_true", help="skip the one-shot (fresh process) run")
     ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
     ap.add_argument("--qq-system", default="katsura-10")
     ap.add_argument("--qq-primes", type=int, default=128, help="size of the fixed prime batch of the QQ block")

@@ -46,7 +46,7 @@ def main():
                "la_seconds_gpu": round(gb.la_seconds, 3), "la_calls": gb.la_calls,
                "device_ms": {k: round(tot[k], 1) for k in ("ms_flatten", "ms_h2d", "ms_prep", "ms_reduce", "ms_echelon",
                                                             "ms_d2h", "ms_materialize")},
-               "dense_macs": tot["units"], "host_threads": a.threads}
+               "reference_units_known_pivots": tot["units"], "host_threads": a.threads}
         if a.cpu:
             rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
             t0 = time.time()
