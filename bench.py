@@ -499,13 +499,11 @@ def run_gpu(args, rank, world):
         dist.destroy_process_group()
 
 
-SAMPLE_FIRST = 9    # the bounded sample of the cpu_baseline leg is drawn from the first rounds of the run
-
-
 def cpu_sample(recs, units_per):
-    """Bounded sample: the first rounds of the run while cumulative units stay under the cap."""
+    """Bounded sample: the first rounds of the run while cumulative units stay under the cap (a small workload
+    is taken whole)."""
     idx, cum = [], 0.0
-    for i in range(min(len(recs), SAMPLE_FIRST)):
+    for i in range(len(recs)):
         if cum + units_per[i] > CPU_SAMPLE_UNITS and idx:
             break
         idx.append(i); cum += units_per[i]
