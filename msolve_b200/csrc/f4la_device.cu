@@ -743,8 +743,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
      * When it is large it runs on the tensor cores over the non-zero 64 x 64 tiles of B (f4la_tc.cuh), and the
      * dataflow kernel only solves the pivot columns. */
     if (!items_built)
-        schur = ctx->schur_tc && ncl >= 1024 && ncr >= 64 && nrl >= 256 && (ncl + kTcBK - 1) / kTcBK < 65536 &&
-                (double)nnz_schur * nrl >= ctx->schur_min_macs;
+        schur = ctx->schur_tc && ncl >= 1 && ncr >= 1 && nnz_schur >= 1 && (ncl + kTcBK - 1) / kTcBK < 65536 &&
+                (double)nnz_schur * nrl >= ctx->schur_min_macs &&
+                (ctx->schur_min_macs == 0 || (ncl >= 1024 && ncr >= 64 && nrl >= 256));   /* F4LA_B200_SCHUR_MIN=0 (tests): always */
     /* dataflow schedule: items in (level, length class) order, then the non-pivot columns */
     if (!items_built) {
         items_built = true;

@@ -41,18 +41,19 @@ constexpr int kWarpsPerBlock  = kSolveThreads / 32;
 constexpr int kRowsPerT       = 128;   /* rows covered by one uint4 per lane */
 constexpr int kMaxT           = 4;     /* chunk = 128*T rows, T in 1..4      */
 constexpr uint32_t kScatterSplit = 8;  /* warps per lower row in k_scatter_lower */
-constexpr uint32_t kLongColumn = 128;  /* >= this many entries: one CTA/col  */
-constexpr int kLenClasses     = 7;     /* class 0 = long, 1..6 = short columns by decreasing length */
+#ifndef F4LA_LONG_COL_LOG2
+#define F4LA_LONG_COL_LOG2 7           /* columns with >= 2^7 = 128 pull-list entries are solved by a whole CTA */
+#endif
+constexpr uint32_t kLongColumn = 1u << F4LA_LONG_COL_LOG2;  /* >= this many entries: one CTA/col  */
+constexpr int kLenClasses     = F4LA_LONG_COL_LOG2;         /* class 0 = long, then the short columns by halving length:
+                                                               [L/2, L), [L/4, L/2), ..., [4, 8), [0, 4) */
 
 __host__ __device__ __forceinline__ uint32_t len_class(uint32_t len)
 {
     if (len >= kLongColumn) return 0;
-    if (len >= 64) return 1;
-    if (len >= 32) return 2;
-    if (len >= 16) return 3;
-    if (len >= 8) return 4;
-    if (len >= 4) return 5;
-    return 6;
+    uint32_t c = 1, lim = kLongColumn >> 1;
+    while (len < lim && lim > 4) { ++c; lim >>= 1; }
+    return len < 4 ? (uint32_t)kLenClasses - 1 : c;
 }
 
 /* x mod p for any 64-bit x, pinv = floor((2^64-1)/p).  The quotient estimate

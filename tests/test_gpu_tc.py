@@ -44,3 +44,49 @@ def test_tc_gemm_accumulator_bound(backend):
     from msolve_b200.backend import F4LAError
     with pytest.raises(F4LAError):
         backend.modp_gemm(np.ones((128, 8193), dtype=np.int64), np.ones((8193, 64), dtype=np.int64), p)
+
+
+def test_schur_tensor_path_forced_on_small_matrices(monkeypatch):
+    """The non-pivot columns as a tensor-core Schur product (k_schur_*: D' = X + M * Bneg over the non-zero tiles
+    of B) normally only runs on large matrices; F4LA_B200_SCHUR_MIN=0 forces it everywhere, and a small vector
+    budget ($F4LA_B200_L2_MB) splits the lower rows into several launch groups.  Every mode of the pipeline
+    (echelon, normal form, pivots keyed by lead, reducer bit arrays, 8/16/31-bit primes) must give the rows of the
+    reference fixtures and of the oracle."""
+    import golden_io
+    from msolve_b200.backend import Backend
+    from msolve_b200.flat import FLAG_NORMALFORM, FLAG_WANT_RBA
+    from oracle import oracle
+    from test_gpu_parity import random_matrix, big_sparse_matrix
+    monkeypatch.setenv("F4LA_B200_SCHUR_MIN", "0")
+    monkeypatch.setenv("F4LA_B200_L2_MB", "1")
+    be = Backend(0)
+    try:
+        n = 0
+        for path in golden_io.fixture_files():
+            for m, ref, meta in golden_io.load_cases(path):
+                out, st = be.reduce(m)
+                assert out.same_rows(ref), path
+                if meta["kind"] == 0 and m.nru:
+                    m.flags = FLAG_NORMALFORM
+                    out, _ = be.reduce(m)
+                    chk, _, _ = oracle.reduce(m)
+                    assert out.same_rows(chk)
+                    m.flags = FLAG_WANT_RBA
+                    out, _ = be.reduce(m)
+                    assert out.same_rows(ref) and out.rba is not None
+                    m.flags = 0
+                n += 1
+        assert n > 40
+        rng = np.random.default_rng(31)
+        for p, dt in ((1073741827, np.uint32), (2147483629, np.uint32), (65521, np.uint16), (251, np.uint8)):
+            for nru, nrl, ncr, dens in [(300, 150, 70, 0.05), (1000, 520, 130, 0.02), (64, 700, 40, 0.1)]:
+                m = random_matrix(rng, p, nru, nrl, ncr, dens, dt)
+                out, _ = be.reduce(m)
+                ref, _, _ = oracle.reduce(m)
+                assert out.same_rows(ref), (p, nru, nrl, ncr)
+        m = big_sparse_matrix(rng, 1073741827, 6000, 300, 400, 200)      # several k-block segments per column block
+        out, st = be.reduce(m)
+        ref, _, _ = oracle.reduce(m)
+        assert out.same_rows(ref)
+    finally:
+        be.close()
