@@ -198,6 +198,10 @@ f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in);
 int  f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m,
                                f4la_flat_result *out, f4la_stats *stats);
 void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m);
+/* A resident matrix with the same structure but other coefficients (and another prime): overwrites the coefficient
+ * pool from host memory (same layout and size as at upload time) and sets the field characteristic.  This is how
+ * the application phase of the multi-modular tracer reuses one structure for many primes (f4la_b200_neogb.h). */
+int  f4la_b200_resident_update(f4la_ctx *ctx, f4la_resident *m, uint32_t fc, const void *cf);
 
 void f4la_b200_free_result(f4la_flat_result *res);
 

@@ -85,6 +85,50 @@ typedef struct f4la_neogb_totals {
 } f4la_neogb_totals;
 void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Structure-cached replay of the tracer APPLICATION phase (the QQ multi-modular loop, src/msolve/msolve.c:1815-1824;
+ * neogb f4.c:416-478 with trace_level == APPLY_TRACER).
+ *
+ * In the application phase every prime builds matrices of IDENTICAL structure (the trace fixes which multiples of
+ * which basis elements form the rows, symbol.c:642-713); only the coefficients differ.  The reference nevertheless
+ * rebuilds the structure for every prime on the host (hash-table insertions, column maps), which is what bounds the
+ * loop once the linear algebra runs on a GPU.  A tape records, during ONE application run through the drop-in
+ * pointers, for every linear-algebra call: the flat structure of the matrix, the basis element behind every
+ * coefficient array, and the support of the result rows.  Replaying the tape for another prime needs no symbolic
+ * work at all: coefficient pools are assembled from the basis elements computed so far for that prime, every call
+ * runs on the structure already resident in HBM, new rows become the next basis elements exactly as
+ * convert_sparse_matrix_rows_to_basis_elements(-1, ...) numbers them (convert.c:660-705: element bl + k is result
+ * row np-1-k), and the rows of the final reduction step (f4.c:568-634) are the reduced basis.  Primes are
+ * independent: one replay per host thread / context, sharded over the GPUs.
+ *
+ * A replay stops with F4LA_ERR_BADPRIME when a call yields another number of rows than recorded (the reference's
+ * own bad-prime test, f4.c:433-441), and with F4LA_ERR_PATTERN when a result row has another support than on the
+ * recorded prime (a coefficient vanishing mod p): such primes go through the ordinary drop-in path.
+ * --------------------------------------------------------------------------------------------------------- */
+#define F4LA_ERR_PATTERN 5
+typedef struct f4la_tape f4la_tape;
+
+/* Between begin and end every call of the calling thread through the entry points above is recorded.
+ * end() returns NULL when nothing usable was recorded (no call, or a mode that cannot be replayed). */
+void       f4la_b200_neogb_tape_begin(void);
+f4la_tape *f4la_b200_neogb_tape_end(void);
+void       f4la_b200_tape_free(f4la_tape *tape);
+
+/* number of recorded calls; number of initial basis elements (indices 0 .. n-1, the input system); length of
+ * initial element i as the tape uses it (0: never referenced); words of the reduced basis a replay returns */
+uint32_t f4la_b200_tape_calls(const f4la_tape *tape);
+uint32_t f4la_b200_tape_initial_elements(const f4la_tape *tape);
+uint32_t f4la_b200_tape_initial_length(const f4la_tape *tape, uint32_t i);
+uint64_t f4la_b200_tape_residue_words(const f4la_tape *tape);
+
+/* Replays the tape for the prime p on the context ctx (struct f4la_ctx of f4la_b200.h).  init_cf / init_off: the
+ * coefficient arrays of the initial basis elements modulo p, normalised as normalize_initial_basis does (lead
+ * coefficient 1), element i at init_cf[init_off[i] .. init_off[i+1]).  residues receives the coefficients of the
+ * reduced basis, element after element (f4la_b200_tape_residue_words() words).  la_ms (optional) += device +
+ * host milliseconds spent.  Thread safe for distinct contexts. */
+int f4la_b200_tape_replay(const f4la_tape *tape, void *ctx, uint32_t p, const uint32_t *init_cf,
+                          const uint64_t *init_off, uint32_t *residues, double *la_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,12 +22,15 @@ EXPORTED_SYMBOLS = [
     # include/f4la_b200.h
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
     "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
-    "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release",
+    "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release", "f4la_b200_resident_update",
     "f4la_b200_free_result", "f4la_b200_measure_mac_peak", "f4la_b200_modp_gemm",
     # include/f4la_b200_neogb.h
     "f4la_b200_neogb_configure", "f4la_b200_neogb_set_device", "f4la_b200_neogb_set_construct_trace", "f4la_b200_linear_algebra",
     "f4la_b200_exact_linear_algebra", "f4la_b200_application_linear_algebra", "f4la_b200_trace_linear_algebra",
     "f4la_b200_interreduce_matrix_rows", "f4la_b200_neogb_set_free_basis_elements", "f4la_b200_neogb_get_totals",
+    "f4la_b200_neogb_tape_begin", "f4la_b200_neogb_tape_end", "f4la_b200_tape_free", "f4la_b200_tape_calls",
+    "f4la_b200_tape_initial_elements", "f4la_b200_tape_initial_length", "f4la_b200_tape_residue_words",
+    "f4la_b200_tape_replay",
 ]
 
 
@@ -231,3 +234,51 @@ class PinnedMatrix:
         for p in self._ptrs:
             self.lib.f4la_b200_pinned_free(p)
         self._ptrs = []
+
+
+class Tape:
+    """Structure-cached replay of the tracer application phase (include/f4la_b200_neogb.h): record one application
+    run through the drop-in pointers, then replay it for other primes with no symbolic work on the host."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+        lib.f4la_b200_tape_calls.restype = C.c_uint32
+        lib.f4la_b200_tape_calls.argtypes = [C.c_void_p]
+        lib.f4la_b200_tape_initial_elements.restype = C.c_uint32
+        lib.f4la_b200_tape_initial_elements.argtypes = [C.c_void_p]
+        lib.f4la_b200_tape_initial_length.restype = C.c_uint32
+        lib.f4la_b200_tape_initial_length.argtypes = [C.c_void_p, C.c_uint32]
+        lib.f4la_b200_tape_residue_words.restype = C.c_uint64
+        lib.f4la_b200_tape_residue_words.argtypes = [C.c_void_p]
+        lib.f4la_b200_tape_replay.restype = C.c_int
+        lib.f4la_b200_tape_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.POINTER(C.c_double)]
+        lib.f4la_b200_tape_free.argtypes = [C.c_void_p]
+        self.calls = int(lib.f4la_b200_tape_calls(handle))
+        self.initial_elements = int(lib.f4la_b200_tape_initial_elements(handle))
+        self.residue_words = int(lib.f4la_b200_tape_residue_words(handle))
+
+    @staticmethod
+    def begin(lib) -> None:
+        lib.f4la_b200_neogb_tape_begin()
+
+    @staticmethod
+    def end(lib) -> Optional["Tape"]:
+        lib.f4la_b200_neogb_tape_end.restype = C.c_void_p
+        h = lib.f4la_b200_neogb_tape_end()
+        return Tape(lib, h) if h else None
+
+    def replay(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray):
+        """-> (return code, residues uint32 [residue_words], milliseconds)"""
+        init_cf = np.ascontiguousarray(init_cf, dtype=np.uint32)
+        init_off = np.ascontiguousarray(init_off, dtype=np.uint64)
+        out = np.zeros(self.residue_words, dtype=np.uint32)
+        ms = C.c_double(0.0)
+        rc = self.lib.f4la_b200_tape_replay(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data,
+                                            out.ctypes.data, C.byref(ms))
+        return int(rc), out, ms.value
+
+    def free(self) -> None:
+        if self.handle:
+            self.lib.f4la_b200_tape_free(self.handle)
+            self.handle = None

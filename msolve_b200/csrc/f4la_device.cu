@@ -1288,6 +1288,17 @@ f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in)
     return r;
 }
 
+int f4la_b200_resident_update(f4la_ctx *ctx, f4la_resident *m, uint32_t fc, const void *cf)
+{
+    if (!ctx || !m || !cf) return F4LA_ERR_ARG;
+    if (fc < 2 || fc >= 0x80000000u) return fail(ctx, F4LA_ERR_ARG, "field characteristic %u out of range", fc);
+    cudaSetDevice(ctx->device);
+    m->dims.fc = fc;
+    if (m->ncoef)
+        CU(cudaMemcpyAsync(m->cf, cf, m->ncoef * m->dims.cf_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return F4LA_OK;
+}
+
 void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m)
 {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }

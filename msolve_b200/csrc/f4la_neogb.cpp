@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -34,6 +36,30 @@ void (*g_free_basis_elements)(void *) = nullptr;
 
 enum class Entry { Normal, Application, Trace };
 
+/* One recorded linear-algebra call of an application-phase run (see f4la_b200_neogb.h). */
+struct TapeCall {
+    uint32_t flags = 0, nru = 0, nrl = 0, ncl = 0, ncr = 0, cf_bytes = 4, bs_ld = 0;
+    bool final_step = false;
+    std::vector<uint64_t> row_ptr, cf_ptr;
+    std::vector<uint32_t> cols, row_cf, slot_bindex;      /* slot_bindex[s]: basis element behind coefficient array s */
+    std::vector<uint64_t> out_row_ptr;                    /* support of the result rows on the recorded prime */
+    std::vector<uint32_t> out_cols;
+};
+} // namespace
+
+struct f4la_tape {
+    std::vector<TapeCall> calls;
+    uint32_t ninit = 0;
+    std::vector<uint32_t> init_len;
+    uint64_t residue_words = 0;
+    bool valid = true;
+    /* per context: the structures resident in HBM (uploaded at the first replay on that context) */
+    std::mutex mu;
+    std::map<void *, std::vector<f4la_resident *>> resident;
+};
+
+namespace {
+
 struct ThreadState {
     f4la_ctx *ctx = nullptr;
     int device = -1;
@@ -41,9 +67,14 @@ struct ThreadState {
     void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[5] = {0, 0, 0, 0, 0};
     f4la_neogb_totals tot = {};
+    f4la_tape *tape = nullptr;          /* recording (f4la_b200_neogb_tape_begin) */
+    void *pool = nullptr;               /* pinned coefficient pool of the replays */
+    size_t pool_cap = 0;
     ~ThreadState()
     {
         for (auto &b : buf) if (b) f4la_b200_pinned_free(b);
+        if (pool) f4la_b200_pinned_free(pool);
+        delete tape;
         if (ctx) f4la_b200_destroy(ctx);
     }
 };
@@ -240,6 +271,25 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
         trace_level == 0)
         fm.flags |= F4LA_FLAG_PROBABILISTIC;
     fm.row_ptr = row_ptr; fm.cols = nullptr; fm.row_cf = row_cf; fm.cf_ptr = cf_ptr; fm.cf = nullptr;
+    if (T.tape) {
+        /* tape of an application-phase run: structure, basis element behind every coefficient array */
+        f4la_tape &tp = *T.tape;
+        if (tbr != bs || nf_mode || learn || entry != Entry::Normal) tp.valid = false;
+        tp.calls.emplace_back();
+        TapeCall &tc = tp.calls.back();
+        tc.flags = fm.flags & ~(F4LA_FLAG_COLS_STAGED | F4LA_FLAG_CF_STAGED);
+        tc.nru = nru; tc.nrl = nrl; tc.ncl = ncl; tc.ncr = ncr; tc.cf_bytes = w; tc.bs_ld = bs_ld; tc.final_step = final_step;
+        tc.row_ptr.assign(row_ptr, row_ptr + n + 1);
+        tc.row_cf.assign(row_cf, row_cf + n);
+        tc.cf_ptr.assign(cfp.begin(), cfp.end());
+        tc.cols.resize(nnz);
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
+            memcpy(tc.cols.data() + row_ptr[r], row + L.row_offset, (size_t)row[L.row_length] * 4);
+        }
+        tc.slot_bindex.assign(ncf, 0);
+        for (uint32_t ci = 0; ci < map_bs.size(); ++ci) if (map_bs[ci] >= 0) tc.slot_bindex[map_bs[ci]] = ci;
+    }
     const double t_flat = now_ms();
 
     /* ---- device ---- */
@@ -265,6 +315,11 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
         for (uint32_t i = 0; i < nru; ++i) rr[i] = nullptr;
     }
     if (rc != F4LA_OK) die(f4la_b200_last_error(cx));
+    if (T.tape) {
+        TapeCall &tc = T.tape->calls.back();
+        tc.out_row_ptr.assign(res.row_ptr, res.row_ptr + res.nrows + 1);
+        tc.out_cols.assign(res.cols, res.cols + res.row_ptr[res.nrows]);
+    }
     const double t_dev = now_ms();
 
     /* ---- learning: hand the reference's trace builder what it reads -------------
@@ -538,6 +593,133 @@ void f4la_b200_interreduce_matrix_rows(void *mat, void *bs, void *st, int free_b
 }
 
 void f4la_b200_neogb_set_free_basis_elements(void (*fn)(void *bs)) { g_free_basis_elements = fn; }
+
+void f4la_b200_neogb_tape_begin(void)
+{
+    delete T.tape;
+    T.tape = new f4la_tape();
+}
+
+f4la_tape *f4la_b200_neogb_tape_end(void)
+{
+    f4la_tape *tp = T.tape;
+    T.tape = nullptr;
+    if (!tp) return nullptr;
+    /* usable: every call recorded with pivots and rows from one basis, the last call is the final reduction step */
+    if (!tp->valid || tp->calls.empty() || !tp->calls.back().final_step) { delete tp; return nullptr; }
+    for (const TapeCall &tc : tp->calls)
+        if (tc.cf_bytes != 4) { delete tp; return nullptr; }      /* multi-modular primes are 31-bit (cf32_t) */
+    tp->ninit = tp->calls.front().bs_ld;
+    tp->init_len.assign(tp->ninit, 0);
+    uint32_t known = tp->ninit;                      /* basis elements defined so far */
+    for (size_t c = 0; c < tp->calls.size(); ++c) {
+        const TapeCall &tc = tp->calls[c];
+        for (size_t sl = 0; sl < tc.slot_bindex.size(); ++sl) {
+            const uint32_t bi = tc.slot_bindex[sl];
+            if (bi >= known) { delete tp; return nullptr; }      /* refers to an element no recorded call produced */
+            if (bi < tp->ninit) tp->init_len[bi] = (uint32_t)(tc.cf_ptr[sl + 1] - tc.cf_ptr[sl]);
+        }
+        const uint32_t np = (uint32_t)tc.out_row_ptr.size() - 1;
+        if (!tc.final_step) {
+            if (tc.bs_ld != known) { delete tp; return nullptr; }
+            known = tc.bs_ld + np;
+        } else if (c + 1 != tp->calls.size()) { delete tp; return nullptr; }
+    }
+    tp->residue_words = tp->calls.back().out_row_ptr.back();
+    return tp;
+}
+
+void f4la_b200_tape_free(f4la_tape *tape)
+{
+    if (!tape) return;
+    for (auto &kv : tape->resident)
+        for (f4la_resident *r : kv.second) f4la_b200_release((f4la_ctx *)kv.first, r);
+    delete tape;
+}
+
+uint32_t f4la_b200_tape_calls(const f4la_tape *tape) { return tape ? (uint32_t)tape->calls.size() : 0; }
+uint32_t f4la_b200_tape_initial_elements(const f4la_tape *tape) { return tape ? tape->ninit : 0; }
+uint32_t f4la_b200_tape_initial_length(const f4la_tape *tape, uint32_t i) { return tape && i < tape->ninit ? tape->init_len[i] : 0; }
+uint64_t f4la_b200_tape_residue_words(const f4la_tape *tape) { return tape ? tape->residue_words : 0; }
+
+int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const uint32_t *init_cf, const uint64_t *init_off,
+                          uint32_t *residues, double *la_ms)
+{
+    f4la_tape *tape = const_cast<f4la_tape *>(ctape);
+    f4la_ctx *cx = (f4la_ctx *)vctx;
+    if (!tape || !cx || !init_cf || !init_off || !residues) return F4LA_ERR_ARG;
+    const double t0 = now_ms();
+    /* the structures of all calls, resident in HBM once per context */
+    std::vector<f4la_resident *> *res_vec;
+    {
+        std::lock_guard<std::mutex> lk(tape->mu);
+        res_vec = &tape->resident[vctx];
+    }
+    if (res_vec->empty()) {
+        for (const TapeCall &tc : tape->calls) {
+            f4la_flat_matrix fm;
+            memset(&fm, 0, sizeof(fm));
+            fm.fc = p; fm.cf_bytes = tc.cf_bytes; fm.nru = tc.nru; fm.nrl = tc.nrl; fm.ncl = tc.ncl; fm.ncr = tc.ncr;
+            fm.ncf = (uint32_t)tc.slot_bindex.size(); fm.flags = tc.flags;
+            fm.row_ptr = tc.row_ptr.data(); fm.cols = tc.cols.data(); fm.row_cf = tc.row_cf.data(); fm.cf_ptr = tc.cf_ptr.data();
+            std::vector<uint32_t> zero(tc.cf_ptr.back() + 1, 1u);        /* placeholder pool, overwritten per prime */
+            fm.cf = zero.data();
+            f4la_resident *r = f4la_b200_upload(cx, &fm);
+            if (!r) return F4LA_ERR_CUDA;
+            res_vec->push_back(r);
+        }
+    }
+    /* basis elements of this prime, by basis index */
+    std::vector<std::vector<uint32_t>> cf(tape->ninit);
+    for (uint32_t i = 0; i < tape->ninit; ++i) {
+        const uint64_t len = init_off[i + 1] - init_off[i];
+        if (tape->init_len[i] && len != tape->init_len[i]) return F4LA_ERR_ARG;
+        cf[i].assign(init_cf + init_off[i], init_cf + init_off[i + 1]);
+    }
+    for (size_t c = 0; c < tape->calls.size(); ++c) {
+        const TapeCall &tc = tape->calls[c];
+        const uint64_t ncoef = tc.cf_ptr.back();
+        if ((ncoef + 1) * 4 > T.pool_cap) {
+            if (T.pool) f4la_b200_pinned_free(T.pool);
+            T.pool_cap = 2 * (ncoef + 1) * 4 + (1 << 16);
+            T.pool = f4la_b200_pinned_alloc(T.pool_cap);
+            if (!T.pool) { T.pool_cap = 0; return F4LA_ERR_CUDA; }
+        }
+        uint32_t *pool = (uint32_t *)T.pool;
+        for (size_t sl = 0; sl < tc.slot_bindex.size(); ++sl) {
+            const std::vector<uint32_t> &src = cf[tc.slot_bindex[sl]];
+            const uint64_t len = tc.cf_ptr[sl + 1] - tc.cf_ptr[sl];
+            if (src.size() != len) return F4LA_ERR_PATTERN;
+            memcpy(pool + tc.cf_ptr[sl], src.data(), len * 4);
+        }
+        f4la_resident *rm = (*res_vec)[c];
+        if (f4la_b200_resident_update(cx, rm, p, pool) != F4LA_OK) return F4LA_ERR_CUDA;
+        f4la_flat_result res;
+        if (f4la_b200_reduce_resident(cx, rm, &res, nullptr) != F4LA_OK) return F4LA_ERR_CUDA;
+        const uint32_t np = (uint32_t)tc.out_row_ptr.size() - 1;
+        int rc = F4LA_OK;
+        if (res.nrows != np) rc = F4LA_ERR_BADPRIME;                                   /* f4.c:433-441 */
+        else if (memcmp(res.row_ptr, tc.out_row_ptr.data(), ((size_t)np + 1) * 8) ||
+                 memcmp(res.cols, tc.out_cols.data(), tc.out_cols.size() * 4)) rc = F4LA_ERR_PATTERN;
+        if (rc == F4LA_OK) {
+            const uint32_t *rcf = (const uint32_t *)res.cf;
+            if (!tc.final_step) {
+                /* convert_sparse_matrix_rows_to_basis_elements(-1, ...): element bs_ld + k is result row np-1-k */
+                cf.resize((size_t)tc.bs_ld + np);
+                for (uint32_t k = 0; k < np; ++k) {
+                    const uint32_t i = np - 1 - k;
+                    cf[tc.bs_ld + k].assign(rcf + res.row_ptr[i], rcf + res.row_ptr[i + 1]);
+                }
+            } else {
+                memcpy(residues, rcf, (size_t)res.row_ptr[np] * 4);                   /* f4.c:612-622: element i = row i */
+            }
+        }
+        f4la_b200_free_result(&res);
+        if (rc != F4LA_OK) return rc;
+    }
+    if (la_ms) *la_ms += now_ms() - t0;
+    return F4LA_OK;
+}
 
 void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset)
 {

@@ -899,3 +899,40 @@ int refh_qq_apply_residues(const uint32_t *primes, int32_t nprimes, int32_t thre
     g_qq_st->nthrds = old_thr; g_qq_st->info_level = old_info;
     return 0;
 }
+
+/* The initial basis of an application run for the prime p, as initialize_f4 prepares it (f4.c:362-371):
+ * copy_basis_mod_p (basis.c:382-464: mpz_fdiv_ui of every coefficient) + normalize_initial_basis (basis.c:340-379:
+ * times the inverse of the lead coefficient), without the copies of the hash tables.  Element i (basis index i) at
+ * out_cf[out_off[i] .. out_off[i+1]).  Returns the number of elements, or -1 when cap is too small. */
+int refh_qq_initial_basis(uint32_t p, uint32_t *out_cf, uint64_t *out_off, int64_t cap)
+{
+    if (!g_qq_bs) return -1;
+    const bs_t *gbs = g_qq_bs;
+    const bl_t ld = gbs->ld;
+    /* coefficient arrays are addressed by their COEFFS index (the rows of the matrices carry it), which the
+     * initial sort of bs->hm does not change: lay the arrays out by that index */
+    len_t *len_of = calloc(ld ? ld : 1, sizeof(len_t));
+    for (bl_t i = 0; i < ld; ++i) {
+        const hm_t idx = gbs->hm[i][COEFFS];
+        if (idx >= ld) { free(len_of); return -1; }
+        len_of[idx] = gbs->hm[i][LENGTH];
+    }
+    uint64_t n = 0;
+    for (bl_t idx = 0; idx < ld; ++idx) { out_off[idx] = n; n += len_of[idx]; }
+    out_off[ld] = n;
+    if ((int64_t)n > cap) { free(len_of); return -1; }
+    for (bl_t idx = 0; idx < ld; ++idx) {
+        const len_t len = len_of[idx];
+        if (!len) continue;
+        uint32_t *row = out_cf + out_off[idx];
+        for (len_t j = 0; j < len; ++j) row[j] = (uint32_t)mpz_fdiv_ui(gbs->cf_qq[idx][j], (unsigned long)p);
+        const uint32_t inv = mod_p_inverse_32((int64_t)row[0], (int64_t)p);
+        for (len_t j = 0; j < len; ++j) {
+            int64_t t = ((int64_t)row[j] * inv) % p;
+            t += (t >> 63) & p;
+            row[j] = (uint32_t)t;
+        }
+    }
+    free(len_of);
+    return (int)ld;
+}

@@ -285,6 +285,20 @@ def residue_digest(row: np.ndarray, lens_digest: int = 0) -> int:
     return h
 
 
+def qq_initial_basis(p: int, cap: int = 1 << 20):
+    """Initial basis of an application run modulo p (normalised) -> (cf uint32, off uint64 [n+1]).
+    Coefficient arrays are ordered by position in the basis; the harness asserts position == COEFFS index."""
+    L = lib()
+    L.refh_qq_initial_basis.restype = C.c_int
+    L.refh_qq_initial_basis.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
+    cf = np.zeros(cap, dtype=np.uint32)
+    off = np.zeros(4096, dtype=np.uint64)
+    n = L.refh_qq_initial_basis(p, cf.ctypes.data, off.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("refh_qq_initial_basis failed (setup first / buffer too small)")
+    return cf[:int(off[n])].copy(), off[:n + 1].copy()
+
+
 def set_device_callback(fn) -> None:
     lib().refh_set_device_callback.argtypes = [C.c_void_p]
     lib().refh_set_device_callback(C.cast(fn, C.c_void_p).value if fn is not None else None)

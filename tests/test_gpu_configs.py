@@ -187,3 +187,43 @@ def test_gpu_side_channels_match_reference():
     finally:
         gpu_helpers.uninstall_backend()
     assert n >= 5
+
+
+@pytest.mark.parametrize("name", ["katsura-7", "cyclic-6", "eco-8", "katsura-9"])
+def test_gpu_qq_tape_replay_matches_reference(name):
+    """Structure-cached replay of the tracer application phase (f4la_b200_neogb.h): one application run through the
+    drop-in pointers is recorded, then further primes are replayed from the tape with no symbolic work.  The
+    residues (coefficients of the reduced modular basis) must equal the reference's own application run for
+    every prime."""
+    import gpu_helpers
+    from msolve_b200.backend import Backend, Tape
+    system = systems.by_name(name)
+    primes = rh.primes_above(1 << 30, 12)
+    rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
+    rh.qq_setup(system, threads=2)
+    learn = rh.qq_learn(primes[0])
+    assert learn["rc"] == 0
+    ref, _, ref_resid = rh.qq_apply(primes[1:], threads=2, residue_words=learn["nterms"])
+    assert all(r["err"] == 0 for r in ref)
+    L = gpu_helpers.install_backend()
+    be = Backend(0)
+    tape = None
+    try:
+        rh.qq_setup(system, threads=1)
+        assert rh.qq_learn(primes[0])["rc"] == 0
+        Tape.begin(L)
+        got, _, got_resid = rh.qq_apply(primes[1:2], threads=1, ngpus=0, residue_words=learn["nterms"])
+        tape = Tape.end(L)
+        assert tape is not None and tape.calls >= 3 and tape.residue_words == learn["nterms"]
+        assert np.array_equal(got_resid[0], ref_resid[0])
+        for k, p in enumerate(primes[1:]):
+            cf, off = rh.qq_initial_basis(p)
+            assert len(off) - 1 == tape.initial_elements
+            rc, resid, ms = tape.replay(be, p, cf, off)
+            assert rc == 0, (name, p, rc)
+            assert np.array_equal(resid, ref_resid[k]), (name, p)
+    finally:
+        if tape is not None:
+            tape.free()
+        be.close()
+        gpu_helpers.uninstall_backend()
