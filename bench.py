@@ -512,88 +512,152 @@ def cpu_sample(recs, units_per):
 
 def run_qq(args, rank, world, local, dist, torch, cpu):
     """QQ multi-modular tracer loop (BASELINE config 5; msolve.c:1628-1632 learn, :1815-1824 apply): learn once,
-    then replay the trace for a FIXED batch of independent primes.  Primes are sharded over the ranks (GPU = rank);
-    every rank drives its GPU with its share of ALL host cores (cpu_count / world threads), so the host resources
-    are the same at every N.  The collective is the all-gather of the residues (coefficients of every modular
-    basis), the payload msolve lifts by CRT on the host (msolve.c:2694-2712)."""
+    then the application phase for a FIXED batch of independent primes, sharded over the ranks (GPU = rank), every
+    rank using its share of ALL host cores (cpu_count / world threads).  Two ways through the same batch:
+
+      replay   : the structure-cached tape (f4la_b200_neogb.h): one application run is recorded through the drop-in
+                 pointers, every other prime is replayed with no symbolic host work -- coefficient pools in, reduced
+                 basis out, all linear algebra on structures resident in HBM.  This is the headline.
+      drop_in  : the reference's own per-prime F4 replay on the host with every linear-algebra call on the GPU
+                 through the plugin pointer (bound by the host's symbolic work).
+
+    The collective is the all-gather of the residues (coefficients of every modular basis), the payload msolve
+    lifts by CRT on the host (msolve.c:2694-2712)."""
     import gpu_helpers
+    from concurrent.futures import ThreadPoolExecutor
     from msolve_b200 import sharding, systems
+    from msolve_b200.backend import Backend, Tape
     from oracle import refharness as rh
     system = systems.by_name(args.qq_system)
     ncpu = os.cpu_count() or 8
     threads = max(1, ncpu // world)
     batch = args.qq_primes
-    all_primes = rh.primes_above(1 << 30, 1 + batch + world * threads)
-    p0 = all_primes[0]
-    warm_primes = sharding.shard(all_primes[1 + batch:], rank, world)
-    mine = sharding.shard(all_primes[1:1 + batch], rank, world)
-    local_err, res, resid, learn, tot = None, [], None, {"seconds": 0.0, "nelts": 0, "nterms": 0}, {"ms_total": 0.0}
+    all_primes = rh.primes_above(1 << 30, 2 + batch + world * threads)
+    p0, p_tape = all_primes[0], all_primes[1]
+    warm_primes = sharding.shard(all_primes[2 + batch:], rank, world)
+    mine = sharding.shard(all_primes[2:2 + batch], rank, world)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        torch.cuda.set_device(local)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     L = gpu_helpers.install_backend()
+    err = None
+    out = {}
     try:
         rh.qq_setup(system, threads=threads)
         learn = rh.qq_learn(p0)
         assert learn["rc"] == 0
-        # ngpus=0: every host thread of this rank uses the rank's own GPU ($F4LA_B200_DEVICE)
-        rh.qq_apply(warm_primes[:threads], threads=threads, ngpus=0)    # warm-up: contexts, staging, allocations
+        words = learn["nterms"]
+        # ---- the tape: one application run through the drop-in pointers ----
+        Tape.begin(L)
+        rec, _, rec_resid = rh.qq_apply([p_tape], threads=1, ngpus=0, residue_words=words)
+        tape = Tape.end(L)
+        assert tape is not None and rec[0]["err"] == 0 and tape.residue_words == words
+        nthr = min(threads, 16)
+        backends = [Backend(local) for _ in range(nthr)]
+
+        def replay_some(k, primes):
+            res = np.zeros((len(primes), words), dtype=np.uint32)
+            fallbacks, ms = 0, 0.0
+            for i, p in enumerate(primes):
+                cf, off = rh.qq_initial_basis(p, cap=1 << 16)
+                rc, resid, m = tape.replay(backends[k], p, cf, off)
+                ms += m
+                if rc != 0:              # bad prime / other support: the ordinary per-prime path
+                    fallbacks += 1
+                    r, _, rr = rh.qq_apply([p], threads=1, ngpus=0, residue_words=words)
+                    resid = rr[0]
+                res[i] = resid
+            return res, fallbacks, ms
+
+        def replay_batch(primes):
+            parts = [primes[k::nthr] for k in range(nthr)]
+            with ThreadPoolExecutor(max_workers=nthr) as ex:
+                outs = list(ex.map(lambda kv: replay_some(*kv), enumerate(parts)))
+            res = np.zeros((len(primes), words), dtype=np.uint32)
+            for k, (r, _, _) in enumerate(outs):
+                res[k::nthr] = r
+            return res, sum(o[1] for o in outs), sum(o[2] for o in outs)
+
+        # the tape reproduces the recorded prime, and the drop-in path's result for other primes
+        chk, _, _ = replay_batch([p_tape] + warm_primes[:nthr])
+        assert np.array_equal(chk[0], rec_resid[0]), "tape replay differs from the recorded application run"
+        _, _, want = rh.qq_apply(warm_primes[:2], threads=min(2, threads), ngpus=0, residue_words=words)
+        assert np.array_equal(chk[1:3], want), "tape replay differs from the drop-in application run"
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        resid, fallbacks, replay_ms = replay_batch(mine)
+        gathered = sharding.gather_residues(resid, dist if world > 1 else None, device=dev)
+        torch.cuda.synchronize()
+        el = max_over_ranks(time.perf_counter() - t0)
+        util = sampler.stop() if rank == 0 else None
+        assert gathered.shape == (batch, words)
+        for j in range(len(mine)):
+            assert rh.residue_digest(gathered[rank + j * world][:64]) == rh.residue_digest(resid[j][:64])
+        for b in backends:
+            b.close()
+        tape.free()
+
+        # ---- the per-prime drop-in path on the same batch ----
+        rh.qq_apply(warm_primes[:threads], threads=threads, ngpus=0)
         gpu_helpers.neogb_totals(L)
-    except Exception as e:
-        local_err = repr(e)
-    torch.cuda.set_device(local)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t0 = time.perf_counter()
-    if local_err is None:
-        try:
-            res, wall, resid = rh.qq_apply(mine, threads=threads, ngpus=0, residue_words=learn["nterms"])
-            assert all(r["err"] == 0 and r["nelts"] == learn["nelts"] for r in res)
-        except Exception as e:
-            local_err, res = repr(e), []
-    if resid is None or local_err is not None:
-        resid = np.zeros((0, max(1, learn["nterms"])), dtype=np.uint32)
-    torch.cuda.set_device(local)
-    gathered = sharding.gather_residues(resid, dist if world > 1 else None, device=torch.device("cuda", local))
-    torch.cuda.synchronize()
-    el = time.perf_counter() - t0
-    util = sampler.stop() if rank == 0 else None
-    try:
+        barrier()
+        t0 = time.perf_counter()
+        res2, _, resid2 = rh.qq_apply(mine, threads=threads, ngpus=0, residue_words=words)
+        gathered2 = sharding.gather_residues(resid2, dist if world > 1 else None, device=dev)
+        torch.cuda.synchronize()
+        el2 = max_over_ranks(time.perf_counter() - t0)
         tot = gpu_helpers.neogb_totals(L)
+        assert all(r["err"] == 0 for r in res2)
+        assert np.array_equal(gathered2, gathered), "replayed residues differ from the drop-in path's"
+        host_sec = max(1e-9, sum(r["seconds"] for r in res2))
+        out = {"metric": "QQ primes/s (F4 tracer application phase)",
+               "workload": f"{args.qq_system} over QQ, tracer application phase, fixed batch of {batch} primes above 2^30",
+               "what": "structure-cached replay: one application run recorded through the drop-in pointers, every prime of "
+                       "the batch replayed from the tape (coefficient pools in, reduced basis out, no symbolic host work), "
+                       "residues of all primes all-gathered; verified equal to the per-prime drop-in path",
+               "value": batch / el, "unit": "primes/s", "n_gpus": world, "primes": batch, "seconds": el,
+               "host_threads_per_gpu": nthr, "host_threads_total": nthr * world, "scaling": "strong",
+               "tape_calls": tape.calls, "replay_fallbacks": int(fallbacks),
+               "replay_ms_per_prime": replay_ms / max(1, len(mine)),
+               "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": words,
+               "gathered_bytes": int(gathered.nbytes), "h2d_bytes": int(len(mine) * words * 4), "d2h_bytes": int(resid.nbytes),
+               "gpu0_util_pct_mean": util.get("gpu_util_pct_mean") if util else None,
+               "collective": "nccl all_gather of the residues (uint32 [primes, words])" if world > 1 else "none (1 GPU)",
+               "drop_in": {"what": "the reference's per-prime F4 replay on the host, every LA call on the GPU through the plugin "
+                                   "pointer (bound by the host's symbolic work, msolve.c:1815-1824)",
+                           "value": batch / el2, "unit": "primes/s", "seconds": el2, "host_threads_per_gpu": threads,
+                           "la_share_of_host_thread_time": tot["ms_total"] / 1e3 / host_sec,
+                           "la_ms_per_prime": tot["ms_total"] / max(1, len(res2))}}
+    except Exception as e:
+        err = repr(e)
+        import traceback
+        traceback.print_exc()
     finally:
         gpu_helpers.uninstall_backend()
-    if world > 1:
-        t = torch.tensor([el], device=torch.device("cuda", local), dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el = float(t.item())
-    if local_err is not None or gathered.shape[0] != batch:
-        return {"error": local_err or f"only {gathered.shape[0]} of {batch} primes completed"}
-    # the gathered residues of this rank's primes are the ones it computed
-    for j, r in enumerate(res):
-        assert rh.residue_digest(gathered[rank + j * world]) == rh.residue_digest(resid[j])
-    host_sec = max(1e-9, sum(r["seconds"] for r in res))
-    out = {"metric": "QQ primes/s (F4 tracer application phase)",
-           "workload": f"{args.qq_system} over QQ, tracer application phase, fixed batch of {batch} primes above 2^30",
-           "what": "per prime: the reference's F4 replay on the host (matrix construction from the trace) with every "
-                   "linear-algebra call on the GPU through the plugin pointer; residues of all primes all-gathered",
-           "value": batch / el, "unit": "primes/s", "n_gpus": world, "primes": batch,
-           "host_threads_per_gpu": threads, "host_threads_total": threads * world, "seconds": el, "scaling": "strong",
-           "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": learn["nterms"],
-           "gathered_bytes": int(gathered.nbytes),
-           "h2d_bytes": int(tot.get("bytes_h2d", 0)), "d2h_bytes": int(tot.get("bytes_d2h", 0)),
-           "la_share_of_host_thread_time": tot["ms_total"] / 1e3 / host_sec,
-           "la_ms_per_prime": tot["ms_total"] / max(1, len(res)),
-           "gpu0_util_pct_mean": util.get("gpu_util_pct_mean") if util else None,
-           "collective": "nccl all_gather of the residues (uint32 [primes, words])" if world > 1 else "none (1 GPU)",
-           "note": "the loop is bound by the host part of every prime (symbolic matrix construction, single threaded per "
-                   "prime in the reference, msolve.c:1815-1824); linear algebra is a few per cent of a prime's time once "
-                   "it runs on the GPU"}
+    # every rank reaches this collective, whatever happened locally
+    flag = max_over_ranks(1.0 if err else 0.0)
+    if flag:
+        return {"error": err or "another rank failed"}
     if rank == 0 and not args.no_qq_cpu:
         rh.reset(); rh.set_mode(rh.MODE_REFERENCE)
         rh.qq_setup(system, threads=ncpu)
         rh.qq_learn(p0)
-        sample = all_primes[1:1 + min(batch, 4 * ncpu)]
+        sample = all_primes[2:2 + min(batch, 4 * ncpu)]
         rh.qq_apply(sample[:ncpu], threads=ncpu)
         _, wall_cpu = rh.qq_apply(sample, threads=ncpu)
         out["cpu_baseline"] = {"value": len(sample) / wall_cpu, "unit": "primes/s", "cores": ncpu, "kind": "reference",
@@ -728,7 +792,7 @@ def main():
     ap.add_argument("--no-cold", action="store_true", help="skip the one-shot (fresh process) run")
     ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
     ap.add_argument("--qq-system", default="katsura-10")
-    ap.add_argument("--qq-primes", type=int, default=128, help="size of the fixed prime batch of the QQ block")
+    ap.add_argument("--qq-primes", type=int, default=512, help="size of the fixed prime batch of the QQ block")
     ap.add_argument("--ref-budget-s", type=float, default=1200.0,
                     help="--impl reference: wall-clock budget; fewer steps are timed when K passes do not fit")
     args = ap.parse_args()
