@@ -567,28 +567,36 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
         nthr = min(threads, 16)
         backends = [Backend(local) for _ in range(nthr)]
 
+        init_lock = threading.Lock()
+
         def replay_some(k, primes):
             res = np.zeros((len(primes), words), dtype=np.uint32)
-            fallbacks, ms = 0, 0.0
+            failed, ms = [], 0.0
             for i, p in enumerate(primes):
-                cf, off = rh.qq_initial_basis(p, cap=1 << 16)
+                with init_lock:                      # the harness (reference code + GMP) is driven from one thread at a time
+                    cf, off = rh.qq_initial_basis(p, cap=1 << 16)
                 rc, resid, m = tape.replay(backends[k], p, cf, off)
                 ms += m
-                if rc != 0:              # bad prime / other support: the ordinary per-prime path
-                    fallbacks += 1
-                    r, _, rr = rh.qq_apply([p], threads=1, ngpus=0, residue_words=words)
-                    resid = rr[0]
-                res[i] = resid
-            return res, fallbacks, ms
+                if rc != 0:
+                    failed.append(i)
+                else:
+                    res[i] = resid
+            return res, failed, ms
 
         def replay_batch(primes):
             parts = [primes[k::nthr] for k in range(nthr)]
             with ThreadPoolExecutor(max_workers=nthr) as ex:
                 outs = list(ex.map(lambda kv: replay_some(*kv), enumerate(parts)))
             res = np.zeros((len(primes), words), dtype=np.uint32)
-            for k, (r, _, _) in enumerate(outs):
+            redo = []
+            for k, (r, failed, _) in enumerate(outs):
                 res[k::nthr] = r
-            return res, sum(o[1] for o in outs), sum(o[2] for o in outs)
+                redo += [k + i * nthr for i in failed]
+            if redo:                                 # bad prime / other support than recorded: the ordinary per-prime path
+                _, _, rr = rh.qq_apply([primes[i] for i in redo], threads=min(threads, len(redo)), ngpus=0, residue_words=words)
+                for i, row in zip(redo, rr):
+                    res[i] = row
+            return res, len(redo), sum(o[2] for o in outs)
 
         # the tape reproduces the recorded prime, and the drop-in path's result for other primes
         chk, _, _ = replay_batch([p_tape] + warm_primes[:nthr])

@@ -161,6 +161,11 @@ const char *f4la_b200_last_error(const f4la_ctx *ctx);
 /* Seed of the random combinations of F4LA_FLAG_PROBABILISTIC (default: a fixed constant, so a
  * run is reproducible; the reference seeds rand() with --random-seed). */
 void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed);
+/* How this context uses the host: `host_threads` bounds the OpenMP team of the result compaction (0 = OpenMP's default;
+ * 1 when the caller already runs one context per host thread, as msolve's multi-modular loop does, msolve.c:1815-1824);
+ * `blocking_sync` != 0 makes every wait for the device sleep on a blocking event instead of spinning in the driver, so
+ * that more host threads than cores can each drive a context. */
+void f4la_b200_set_host_mode(f4la_ctx *ctx, int host_threads, int blocking_sync);
 
 /* Page-locked host memory for the flat arrays handed to f4la_b200_reduce():
  * host->device copies from such buffers run at full PCIe rate and

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libf4la_b200.so")
 EXPORTED_SYMBOLS = [
     # include/f4la_b200.h
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
-    "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
+    "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_set_host_mode", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
     "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release", "f4la_b200_resident_update",
     "f4la_b200_free_result", "f4la_b200_measure_mac_peak", "f4la_b200_modp_gemm",
     # include/f4la_b200_neogb.h
@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
     L.f4la_b200_last_error.restype = C.c_char_p
     L.f4la_b200_last_error.argtypes = [C.c_void_p]
     L.f4la_b200_set_seed.argtypes = [C.c_void_p, C.c_uint64]
+    L.f4la_b200_set_host_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.f4la_b200_pinned_alloc.restype = C.c_void_p
     L.f4la_b200_pinned_alloc.argtypes = [C.c_size_t]
     L.f4la_b200_pinned_free.argtypes = [C.c_void_p]
@@ -139,6 +140,9 @@ class Backend:
         self._check(self.lib.f4la_b200_modp_gemm(self.ctx, a.ctypes.data, b.ctypes.data, M, N, K, p, c.ctypes.data,
                                                  C.byref(ms)))
         return c, ms.value
+
+    def set_host_mode(self, host_threads: int, blocking_sync: bool) -> None:
+        self.lib.f4la_b200_set_host_mode(self.ctx, host_threads, 1 if blocking_sync else 0)
 
     def set_seed(self, seed: int) -> None:
         self.lib.f4la_b200_set_seed(self.ctx, seed)

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <omp.h>
 
 #include "f4la_b200.h"
 #include "f4la_kernels.cuh"
@@ -93,6 +94,10 @@ struct f4la_ctx {
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
     double        watchdog_ms = 20000.0; /* F4LA_B200_WATCHDOG_MS: longest wait for a source column in the dataflow kernel */
+    uint32_t      grid_cap = 0;                   /* CTAs a persistent kernel of this context may occupy (0: the device) */
+    int           host_threads = 0;               /* threads of the host-side result compaction (0: OpenMP default) */
+    bool          blocking_sync = false;          /* waits sleep on a blocking event instead of spinning */
+    cudaEvent_t   ev_block = nullptr;
     uint64_t      seed = 0x9e3779b97f4a7c15ull;   /* random combinations of the probabilistic mode */
     int           tmax = 2;             /* F4LA_B200_TMAX: rows per chunk = 128 * T (T = 2 measured best on K12: 125 ms vs 142 / 140 ms for T = 3 / 4) */
     HostBuf h_small, h_dense, h_combo;
@@ -105,8 +110,21 @@ struct f4la_ctx {
     std::vector<uint32_t> donor;          /* per random combination: one lower row that entered it (BINDEX / MULT donor) */
 };
 
+/* What the layout kernels derive from the STRUCTURE of a matrix (pull lists, schedule, column maps): kept with a
+ * resident matrix whose coefficients are replaced (f4la_b200_resident_update), so that a run for another prime
+ * skips those kernels and their host round trips and only refreshes the values of the pull lists. */
+struct PrepCache {
+    bool      valid = false;
+    uint32_t  nnz_pull = 0, nnz_schur = 0, n_items = 0, schur_nseg = 0;
+    bool      schur = false;
+    uint32_t *col_ptr = nullptr, *ent_src = nullptr, *sched = nullptr, *items = nullptr, *colmap = nullptr, *invmap = nullptr;
+    uint2    *ent = nullptr;
+};
+
 struct f4la_resident {
     f4la_flat_matrix dims;        /* pointers below are DEVICE pointers */
+    bool      cache_enabled = false;
+    mutable PrepCache cache;
     uint64_t *row_ptr = nullptr;
     uint32_t *cols = nullptr;
     uint32_t *row_cf = nullptr;
@@ -181,6 +199,26 @@ int ensure_host(f4la_ctx *ctx, HostBuf &b, size_t bytes)
     return F4LA_OK;
 }
 
+/* Wait for the context's stream.  With several host threads per core (f4la_b200_set_host_mode) the wait sleeps on a
+ * blocking event instead of spinning in the driver, so that the core serves another thread's prime meanwhile. */
+int stream_sync(f4la_ctx *ctx)
+{
+    if (!ctx->blocking_sync) { CU(cudaStreamSynchronize(ctx->stream)); return F4LA_OK; }
+    if (!ctx->ev_block) CU(cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_block, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev_block));
+    return F4LA_OK;
+}
+
+/* (re)allocate one buffer of a resident matrix's layout cache */
+int cache_alloc(f4la_ctx *ctx, void **p, size_t bytes)
+{
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr;
+    CU(cudaMalloc(p, bytes + 16));
+    return F4LA_OK;
+}
+
 void free_dev(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
 template <typename T> T *as(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
@@ -223,6 +261,7 @@ void launch_flow(f4la_ctx *ctx, int T, const FlowArgs &a, bool wide)
     if (total == 0) return;
     uint64_t g = (uint64_t)ctx->sm_count * flow_blocks(ctx, T, wide);
     if (g > total) g = total;
+    if (ctx->grid_cap && g > ctx->grid_cap) g = ctx->grid_cap;   /* several contexts share the device */
     const unsigned grid = (unsigned)g;
 #define FLOW(TT)                                                                                   \
     if (wide) k_pull_flow<TT, true><<<grid, kSolveThreads, 0, ctx->stream>>>(a);                    \
@@ -346,7 +385,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         note_launch(ctx, 1, __LINE__);
         CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         if (ctx->debug) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->dbg_ev[0], ctx->dbg_ev[1]);
@@ -387,7 +426,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             batches += group;
             CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
             CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(s));
+            OK(stream_sync(ctx));
             if (h_state->done) break;
             if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
                 return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
@@ -418,7 +457,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             batches += group;
             CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
             CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(s));
+            OK(stream_sync(ctx));
             if (h_state->done) break;
             if ((uint64_t)batches * 1 > (uint64_t)maxrank + 2 * group)
                 return fail(ctx, F4LA_ERR_CUDA, "batched Gauss-Jordan did not terminate (rank %u)", h_state->rank);
@@ -440,7 +479,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         done_steps += batch;
         CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         if (h_state->done) break;
         if (done_steps > maxrank + 2 * batch)
             return fail(ctx, F4LA_ERR_CUDA, "Gauss-Jordan did not terminate (rank %u)", h_state->rank);
@@ -535,7 +574,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
         uint32_t *h_bad = (uint32_t *)ctx->h_small.p + 128;
         CU(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         ctx->compress_attempts++;
         if (*h_bad || ctx->compress_fault) { ctx->compress_rejected++; return F4LA_OK; }      /* rank lost in the compression: eliminate directly */
         ctx->d2_ld = kc;
@@ -600,18 +639,34 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
 
     CU(cudaEventRecord(ctx->ev[0], s));
 
-    /* ---- 1. pull lists (CSC of the strictly upper part of the pivot rows) ---- */
-    OK(ensure(ctx, ctx->col_cnt, ((size_t)nc + 2) * 4));
-    OK(ensure(ctx, ctx->col_ptr, ((size_t)nc + 2) * 4));
     OK(ensure(ctx, ctx->flags32, 64));
     OK(ensure_host(ctx, ctx->h_small, 1 << 20));
     uint32_t *h_small = (uint32_t *)ctx->h_small.p;
     uint32_t *d_err = as<uint32_t>(ctx->flags32);           /* [0] err, [1] changed, [2] max level */
-    CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));
     CU(cudaMemsetAsync(d_err, 0, 64, s));
     OK(ensure(ctx, ctx->refcnt, (size_t)kRefSlots * 32));
     CU(cudaMemsetAsync(ctx->refcnt.p, 0, (size_t)kRefSlots * 32, s));
     const uint32_t *colmap = nullptr;
+    PrepCache *pc = m->cache_enabled ? &m->cache : nullptr;
+    const bool cached = pc && pc->valid;
+    uint32_t nnz_pull = 0, nnz_schur = 0, nlev = 0;
+    uint32_t *d_col_ptr = nullptr, *d_invmap = nullptr, *d_sched = nullptr, *d_items = nullptr;
+    uint2 *d_ent = nullptr;
+    std::vector<uint32_t> slot_ptr_h;
+    if (cached) {
+        /* same structure as the run that filled the cache: only the values of the pull lists change */
+        nnz_pull = pc->nnz_pull; nnz_schur = pc->nnz_schur;
+        d_col_ptr = pc->col_ptr; d_ent = pc->ent; d_invmap = pc->invmap;
+        if (by_lead) colmap = pc->colmap;
+        if (nnz_pull) {
+            k_ent_refill<<<(nnz_pull + 255) / 256, 256, 0, s>>>(d_ent, pc->ent_src, m->cf, d.cf_bytes, p, nnz_pull);
+            note_launch(ctx, 1, __LINE__);
+        }
+    } else {
+    /* ---- 1. pull lists (CSC of the strictly upper part of the pivot rows) ---- */
+    OK(ensure(ctx, ctx->col_cnt, ((size_t)nc + 2) * 4));
+    OK(ensure(ctx, ctx->col_ptr, ((size_t)nc + 2) * 4));
+    CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));
     if (by_lead) {
         OK(ensure(ctx, ctx->is_piv, ((size_t)nc + 2) * 4));
         OK(ensure(ctx, ctx->pividx, ((size_t)nc + 2) * 4));
@@ -637,24 +692,24 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     CU(cudaMemcpyAsync(h_small + 1, d_err, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h_small + 2, as<uint32_t>(ctx->col_ptr) + ncl, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
-    const uint32_t nnz_pull = h_small[0];
-    const uint32_t nnz_schur = nnz_pull - h_small[2];        /* pull-list entries of the columns without pivot */
+    OK(stream_sync(ctx));
+    nnz_pull = h_small[0];
+    nnz_schur = nnz_pull - h_small[2];                       /* pull-list entries of the columns without pivot */
     if (h_small[1])
         return fail(ctx, F4LA_ERR_ARG, "malformed pivot rows (error bits 0x%x: 1 lead not first, 2 not upper "
                     "triangular, 4 column out of range, 8 lead coefficient != 1, 32 duplicate pivot column)", h_small[1]);
     OK(ensure(ctx, ctx->ent, ((size_t)nnz_pull + 1) * sizeof(uint2)));
+    if (pc) OK(cache_alloc(ctx, (void **)&pc->ent_src, ((size_t)nnz_pull + 1) * 4));
     CU(cudaMemsetAsync(ctx->col_cnt.p, 0, ((size_t)nc + 2) * 4, s));   /* reuse as cursor */
     if (npr) {
         k_pull_fill<<<blocks_for_warps(npr), 256, 0, s>>>(m->row_ptr, m->cols, m->row_cf, m->cf_ptr, m->cf, d.cf_bytes,
                                                           npr, nc, p, colmap, as<uint32_t>(ctx->col_ptr),
-                                                          as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent));
+                                                          as<uint32_t>(ctx->col_cnt), as<uint2>(ctx->ent),
+                                                          pc ? pc->ent_src : nullptr);
         note_launch(ctx, 1, __LINE__);
     }
 
     /* ---- 2. levels of the pivot columns ---- */
-    uint32_t nlev = 0;
-    std::vector<uint32_t> slot_ptr_h;
     if (ncl) {
         OK(ensure(ctx, ctx->level, (size_t)ncl * 4));
         CU(cudaMemsetAsync(ctx->level.p, 0xff, (size_t)ncl * 4, s));      /* kLevelUnset */
@@ -677,7 +732,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         note_launch(ctx, 1, __LINE__);
         CU(cudaMemcpyAsync(h_small, d_err + 2, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
+    OK(stream_sync(ctx));
         nlev = h_small[0] + 1;
         const uint32_t nslots = kLenClasses * nlev;
         k_exclusive_scan<<<1, 1024, 0, s>>>(as<uint32_t>(ctx->slots), as<uint32_t>(ctx->slot_ptr), nslots);
@@ -692,9 +747,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         h_small = (uint32_t *)ctx->h_small.p;
         CU(cudaMemcpyAsync(h_small, ctx->slot_ptr.p, ((size_t)nslots + 1) * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s));
+    OK(stream_sync(ctx));
         memcpy(slot_ptr_h.data(), h_small, ((size_t)nslots + 1) * 4);
     }
+    d_col_ptr = as<uint32_t>(ctx->col_ptr); d_ent = as<uint2>(ctx->ent);
+    if (by_lead) d_invmap = as<uint32_t>(ctx->invmap);
+    }   /* !cached */
     CU(cudaEventRecord(ctx->ev[1], s));
 
     /* Probabilistic mode (the reference's -l 42/43/44, la_ff_32.c:2305-2506): the nrl lower rows
@@ -742,6 +800,11 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     /* The columns without pivot have no dependents: V[ncl + j] = X + M * Bneg is a dense-times-sparse product.
      * When it is large it runs on the tensor cores over the non-zero 64 x 64 tiles of B (f4la_tc.cuh), and the
      * dataflow kernel only solves the pivot columns. */
+    if (!items_built && cached) {
+        items_built = true;
+        n_items = pc->n_items; schur = pc->schur;
+        d_sched = pc->sched; d_items = pc->items;
+    }
     if (!items_built)
         schur = ctx->schur_tc && ncl >= 1 && ncr >= 1 && nnz_schur >= 1 && (ncl + kTcBK - 1) / kTcBK < 65536 &&
                 (double)nnz_schur * nrl >= ctx->schur_min_macs &&
@@ -774,8 +837,27 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         k_flow_sched<<<(na + ncr + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->order), first, ncl, ncr,
                                                            as<uint32_t>(ctx->sched));
         note_launch(ctx, 1, __LINE__);
+        d_sched = as<uint32_t>(ctx->sched); d_items = as<uint32_t>(ctx->items);
+        if (pc) {
+            /* keep everything derived from the structure with the resident matrix */
+            struct { void **dst; const void *src; size_t bytes; } keep[] = {
+                {(void **)&pc->col_ptr, d_col_ptr, ((size_t)nc + 2) * 4},
+                {(void **)&pc->ent, d_ent, ((size_t)nnz_pull + 1) * sizeof(uint2)},
+                {(void **)&pc->sched, d_sched, ((size_t)na + ncr + 1) * 4},
+                {(void **)&pc->items, d_items, ((size_t)n_items + 1) * 4},
+                {(void **)&pc->colmap, by_lead ? ctx->colmap.p : nullptr, ((size_t)nc + 2) * 4},
+                {(void **)&pc->invmap, by_lead ? ctx->invmap.p : nullptr, ((size_t)nc + 2) * 4},
+            };
+            for (auto &k : keep) {
+                if (!k.src) continue;
+                OK(cache_alloc(ctx, k.dst, k.bytes));
+                CU(cudaMemcpyAsync(*k.dst, k.src, k.bytes, cudaMemcpyDeviceToDevice, s));
+            }
+            pc->nnz_pull = nnz_pull; pc->nnz_schur = nnz_schur; pc->n_items = n_items; pc->schur = schur;
+            pc->valid = true;
+        }
         /* the staging buffer is reused for the result later: the copy must be done first */
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
     }
 
     if (want_rba && rba_words) OK(ensure(ctx, ctx->rba, (size_t)nrl * rba_words * 4 + 16));
@@ -785,7 +867,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
         if (ncl) {
-            k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(as<uint32_t>(ctx->col_ptr), ncl, nc, g,
+            k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(d_col_ptr, ncl, nc, g,
                                                                as<uint32_t>(ctx->flowflags));
             note_launch(ctx, 1, __LINE__);
         }
@@ -808,9 +890,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         note_launch(ctx, 1, __LINE__);
         FlowArgs f;
         memset(&f, 0, sizeof(f));
-        f.col_ptr = as<uint32_t>(ctx->col_ptr); f.ent = as<uint2>(ctx->ent);
+        f.col_ptr = d_col_ptr; f.ent = d_ent;
         f.V = as<uint32_t>(ctx->V); f.nc = nc; f.Rc = Rc;
-        f.sched = as<uint32_t>(ctx->sched); f.items = as<uint32_t>(ctx->items);
+        f.sched = d_sched; f.items = d_items;
         f.n_items = n_items; f.G = g;
         f.flags = as<uint32_t>(ctx->flowflags); f.epoch = ++epoch;
         f.counter = d_err + 4; f.err = d_err;
@@ -828,7 +910,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             SchurArgs sa;
             memset(&sa, 0, sizeof(sa));
             sa.V = as<uint32_t>(ctx->V); sa.nc = nc; sa.ncl = ncl; sa.ncr = ncr; sa.Rc = Rc; sa.G = g;
-            sa.col_ptr = as<uint32_t>(ctx->col_ptr); sa.ent = as<uint2>(ctx->ent);
+            sa.col_ptr = d_col_ptr; sa.ent = d_ent;
             sa.mblk = g * (Rc / kTcBM); sa.nblk = (ncr + kTcBN - 1) / kTcBN; sa.nkb = (ncl + kTcBK - 1) / kTcBK;
             sa.ldp = (uint64_t)sa.mblk * kTcBM;
             sa.out = as<uint32_t>(ctx->D); sa.out_ld = ld; sa.chunk0 = c0;
@@ -850,15 +932,19 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                 k_schur_b_build<<<blocks_for_warps(ncr), 256, 0, s>>>(sa);
                 k_schur_lists<<<sa.nblk, 256, 0, s>>>(sa);
                 note_launch(ctx, 2, __LINE__);
-                uint32_t *h_cnt = (uint32_t *)ctx->h_small.p + 512;
-                OK(ensure_host(ctx, ctx->h_small, ((size_t)sa.nblk + 1024) * 4));
-                h_cnt = (uint32_t *)ctx->h_small.p + 512;
-                CU(cudaMemcpyAsync(h_cnt, ctx->scCnt.p, (size_t)sa.nblk * 4, cudaMemcpyDeviceToHost, s));
-                CU(cudaStreamSynchronize(s));
-                uint32_t mx = 0;
-                for (uint32_t k = 0; k < sa.nblk; ++k) mx = h_cnt[k] > mx ? h_cnt[k] : mx;
-                schur_nseg = (mx + kSchurSeg - 1) / kSchurSeg;
-                if (schur_nseg < 1) schur_nseg = 1;
+                if (pc && pc->schur_nseg) {
+                    schur_nseg = pc->schur_nseg;              /* the tile lists only depend on the structure */
+                } else {
+                    OK(ensure_host(ctx, ctx->h_small, ((size_t)sa.nblk + 1024) * 4));
+                    uint32_t *h_cnt = (uint32_t *)ctx->h_small.p + 512;
+                    CU(cudaMemcpyAsync(h_cnt, ctx->scCnt.p, (size_t)sa.nblk * 4, cudaMemcpyDeviceToHost, s));
+                    OK(stream_sync(ctx));
+                    uint32_t mx = 0;
+                    for (uint32_t k = 0; k < sa.nblk; ++k) mx = h_cnt[k] > mx ? h_cnt[k] : mx;
+                    schur_nseg = (mx + kSchurSeg - 1) / kSchurSeg;
+                    if (schur_nseg < 1) schur_nseg = 1;
+                    if (pc) pc->schur_nseg = schur_nseg;
+                }
             }
             sa.nseg = schur_nseg;
             OK(ensure(ctx, ctx->scP, (size_t)sa.nseg * ncr * sa.ldp * 4));
@@ -920,7 +1006,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         uint64_t *h_ref = (uint64_t *)((uint32_t *)ctx->h_small.p + 256);
         CU(cudaMemcpyAsync(h_err, d_err, 64, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(h_ref, ctx->refcnt.p, (size_t)kRefSlots * 32, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         for (uint32_t k = 0; k < kRefSlots; ++k) { ref_units += h_ref[4 * k]; ref_apps += h_ref[4 * k + 1]; }
         if (*h_err)
             return fail(ctx, F4LA_ERR_CUDA, "device pipeline reported error bits 0x%x (4: column out of range in a lower "
@@ -973,13 +1059,13 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             OK(ensure(ctx, ctx->leads, (size_t)nrl * 4 + 16));
             k_lower_leads<<<(nrl + 255) / 256, 256, 0, s>>>(m->row_ptr, m->cols, nru, nrl, as<uint32_t>(ctx->leads));
             note_launch(ctx, 1, __LINE__);
-            CU(cudaMemcpyAsync(h_invmap, ctx->invmap.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(h_invmap, d_invmap, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(h_leads, ctx->leads.p, (size_t)nrl * 4, cudaMemcpyDeviceToHost, s));
         }
         CU(cudaGetLastError());
         if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[1], s));
         const double t_copy0 = now_ms();
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         const double t_copy1 = now_ms();
         if (ctx->debug) {
             float a = 0, b = 0;
@@ -1005,7 +1091,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->row_ptr = (uint64_t *)malloc(((size_t)nout + 1) * sizeof(uint64_t));
         out->src_row = (uint32_t *)malloc((size_t)nout * sizeof(uint32_t));
         std::vector<uint64_t> rnz(nout, 0);
-#pragma omp parallel for schedule(static) if (nout > 16)
+        const int host_thr = ctx->host_threads > 0 ? ctx->host_threads : omp_get_max_threads();
+#pragma omp parallel for num_threads(host_thr) schedule(static) if (nout > 16 && host_thr > 1)
         for (uint32_t t = 0; t < nout; ++t) {
             if (pick[t] < 0) continue;
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
@@ -1024,7 +1111,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->row_ptr[nout] = nnz;
         out->cols = (uint32_t *)malloc((nnz ? nnz : 1) * sizeof(uint32_t));
         out->cf = malloc((nnz ? nnz : 1) * (size_t)d.cf_bytes);
-#pragma omp parallel for schedule(static) if (nout > 16)
+#pragma omp parallel for num_threads(host_thr) schedule(static) if (nout > 16 && host_thr > 1)
         for (uint32_t t = 0; t < nout; ++t) {
             if (pick[t] < 0) continue;
             uint64_t k = out->row_ptr[t];
@@ -1052,7 +1139,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->rba_words = rba_words;
         out->rba = (uint32_t *)malloc((size_t)nrl * rba_words * 4);
         CU(cudaMemcpyAsync(out->rba, ctx->rba.p, (size_t)nrl * rba_words * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         d2h_bytes += (uint64_t)nrl * rba_words * 4;
     }
     CU(cudaEventRecord(ctx->ev[4], s));
@@ -1154,6 +1241,9 @@ void release_resident(f4la_resident *r)
 {
     if (!r) return;
     if (r->owned) { cudaFree(r->row_ptr); cudaFree(r->cols); cudaFree(r->row_cf); cudaFree(r->cf_ptr); cudaFree(r->cf); }
+    PrepCache &pc = r->cache;
+    cudaFree(pc.col_ptr); cudaFree(pc.ent_src); cudaFree(pc.sched); cudaFree(pc.items); cudaFree(pc.colmap); cudaFree(pc.invmap);
+    cudaFree(pc.ent);
     delete r;
 }
 
@@ -1225,6 +1315,7 @@ f4la_ctx *f4la_b200_create(int device)
     if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
     ctx->debug = dbg && atoi(dbg) != 0;
+    { const char *gc = getenv("F4LA_B200_GRID_CAP"); if (gc) ctx->grid_cap = (uint32_t)atoi(gc); }
     const char *dsy = getenv("F4LA_B200_SYNC");
     ctx->debug_sync = dsy && atoi(dsy) != 0;
     const char *wd = getenv("F4LA_B200_WATCHDOG_MS");
@@ -1267,6 +1358,13 @@ void f4la_b200_destroy(f4la_ctx *ctx)
 
 const char *f4la_b200_last_error(const f4la_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 
+void f4la_b200_set_host_mode(f4la_ctx *ctx, int host_threads, int blocking_sync)
+{
+    if (!ctx) return;
+    ctx->host_threads = host_threads > 0 ? host_threads : 0;
+    ctx->blocking_sync = blocking_sync != 0;
+}
+
 void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed) { if (ctx) ctx->seed = seed ? seed : 0x9e3779b97f4a7c15ull; }
 
 void *f4la_b200_pinned_alloc(size_t bytes)
@@ -1294,6 +1392,7 @@ int f4la_b200_resident_update(f4la_ctx *ctx, f4la_resident *m, uint32_t fc, cons
     if (fc < 2 || fc >= 0x80000000u) return fail(ctx, F4LA_ERR_ARG, "field characteristic %u out of range", fc);
     cudaSetDevice(ctx->device);
     m->dims.fc = fc;
+    m->cache_enabled = true;          /* the structure will be reused: keep what the layout kernels derive from it */
     if (m->ncoef)
         CU(cudaMemcpyAsync(m->cf, cf, m->ncoef * m->dims.cf_bytes, cudaMemcpyHostToDevice, ctx->stream));
     return F4LA_OK;
@@ -1421,7 +1520,7 @@ int f4la_b200_modp_gemm(f4la_ctx *ctx, const uint32_t *A, const uint32_t *B, uin
         uint32_t h_err = 0;
         CU(cudaMemcpyAsync(&h_err, ctx->flags32.p, 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpy2DAsync(C, (size_t)M * 4, dC, Mp * 4, (size_t)M * 4, N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        OK(stream_sync(ctx));
         if (h_err) return fail(ctx, F4LA_ERR_CUDA, "tensor-core product reported error bits 0x%x (64: pipeline wait expired)", h_err);
         if (kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); *kernel_ms = ms; }
         return F4LA_OK;

@@ -79,6 +79,16 @@ __device__ __forceinline__ uint32_t shoup_pre(uint32_t sc, uint32_t p)
     return (uint32_t)(((uint64_t)sc << 32) / p);
 }
 
+/* the same without a 64-bit division: pinv = floor((2^64 - 1) / p) */
+__device__ __forceinline__ uint32_t shoup_pre_fast(uint32_t sc, uint32_t p, uint64_t pinv)
+{
+    const uint64_t x = (uint64_t)sc << 32;
+    uint64_t q = __umul64hi(x, pinv);
+    uint64_t r = x - q * p;
+    while (r >= p) { r -= p; ++q; }
+    return (uint32_t)q;
+}
+
 __device__ __forceinline__ uint32_t shoup_mul(uint32_t f, uint32_t sc, uint32_t w, uint32_t p)
 {
     const uint32_t q = __umulhi(f, w);
@@ -192,7 +202,8 @@ __global__ void k_pull_fill(const uint64_t *__restrict__ row_ptr,
                             uint32_t nru, uint32_t nc, uint32_t p,
                             const uint32_t *__restrict__ colmap,
                             const uint32_t *__restrict__ col_ptr,
-                            uint32_t *__restrict__ cursor, uint2 *__restrict__ ent)
+                            uint32_t *__restrict__ cursor, uint2 *__restrict__ ent,
+                            uint32_t *__restrict__ ent_src)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -215,8 +226,20 @@ __global__ void k_pull_fill(const uint64_t *__restrict__ row_ptr,
             const uint32_t v = load_cf(cf, cf_bytes, c0 + (k - a)) % p;
             const uint32_t pos = col_ptr[j] + atomicAdd(&cursor[j], 1u);
             ent[pos] = make_uint2(id, v == 0 ? 0u : p - v);
+            if (ent_src) ent_src[pos] = (uint32_t)(c0 + (k - a));      /* where the coefficient lives in the pool */
         }
     }
+}
+
+/* Same structure, other coefficients (f4la_b200_resident_update: another prime of the multi-modular loop): only the
+ * values of the pull lists are refreshed, from the recorded pool positions. */
+__global__ void k_ent_refill(uint2 *__restrict__ ent, const uint32_t *__restrict__ ent_src, const void *__restrict__ cf,
+                             uint32_t cf_bytes, uint32_t p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = load_cf(cf, cf_bytes, ent_src[i]) % p;
+    ent[i].y = v == 0 ? 0u : p - v;
 }
 
 /* Column renumbering for matrices whose known pivots are keyed by their lead
@@ -1538,7 +1561,7 @@ __device__ __forceinline__ bool ge_grid_barrier(const GeFusedArgs &A, uint32_t &
 __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t *s_used)
 {
     __shared__ uint32_t s_cols[kPanelMax], s_cand[kPanelMax], s_pj[kPanelMax], s_prow[kPanelMax], s_pinv[kPanelMax];
-    __shared__ uint32_t s_wcnt[kFusedThreads / 32], s_m, s_next, s_sel, s_mult[kPanelMax], s_multw[kPanelMax], s_scale[kPanelMax], s_isc[kPanelMax], s_pivw;
+    __shared__ uint32_t s_wcnt[kFusedThreads / 32], s_m, s_next, s_scale[kPanelMax], s_isc[kPanelMax];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nrows = A.nrows, nrows4 = A.nrows4, ncr = A.ncr, pw = A.pw, p = A.p;
     GEState *st = A.st;
@@ -1602,54 +1625,50 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
      * final extraction, which normalises ROWS with the inverse of the pivot entry; so the accumulated scale of every
      * column is tracked and divided out when a pivot column is written back.  No modular inverse sits on the
      * per-pivot critical path; the inverses are computed once per panel, in parallel. */
-    const uint32_t grp = tid >> 8, gt = tid & 255;          /* 4 groups of 256 threads: group g takes the columns js+1+g, +4, ... */
+    /* One warp per panel column (at most 32 columns, 32 warps), and every warp repeats the tiny pivot selection for
+     * itself: ONE block barrier per pivot.  (A former version gave each column to a group of 256 threads, four columns
+     * at a time behind three more barriers: 4.7k cycles per pivot on a 127-row block, now a few hundred.) */
     for (;;) {
         tk0 = clock64();
         /* leftmost column at or after `cur` with a candidate */
-        if (tid < 32) {
-            uint32_t j = cur + lane;
+        uint32_t js;
+        {
+            const uint32_t j = cur + lane;
             const bool has = j < m && s_cand[j] != 0xffffffffu;
             const uint32_t bal = __ballot_sync(0xffffffffu, has);
-            if (lane == 0) s_sel = bal ? cur + (uint32_t)__ffs(bal) - 1 : 0xffffffffu;
+            js = bal ? cur + (uint32_t)__ffs(bal) - 1 : 0xffffffffu;
         }
-        __syncthreads();
-        const uint32_t js = s_sel;
         if (js == 0xffffffffu) break;
         const uint32_t rs = s_cand[js];
         const uint32_t *pc = s_panel + (size_t)js * nrows4;
         const uint32_t piv = pc[rs];
-        __syncthreads();                                    /* everybody has read s_cand[js] / s_sel */
-        if (tid == 0) { s_pj[np] = js; s_prow[np] = rs; s_used[rs] = 1; s_pivw = shoup_pre(piv, p); }
-        if (tid > js && tid < m) {                          /* Shoup constants of the two fixed multipliers of a column */
-            const uint32_t e = s_panel[(size_t)tid * nrows4 + rs];
-            const uint32_t neg = e ? p - e : 0u;
-            s_mult[tid] = neg; s_multw[tid] = shoup_pre(neg, p);
-            s_cand[tid] = 0xffffffffu;
-        }
-        __syncthreads();
+        if (tid == kFusedThreads - 1) { s_pj[np] = js; s_prow[np] = rs; s_used[rs] = 1; }   /* warp 31 never owns a column */
         tk1 = clock64(); tsel += tk1 - tk0; tk0 = tk1;
         /* column j <- piv * column j - e_j * pivot column (entry of the pivot row: piv * e_j); new candidates */
-        for (uint32_t j = js + 1 + grp; j < m; j += 4) {
+        const uint32_t j = js + 1 + warp;
+        if (j < m) {
             uint32_t *col = s_panel + (size_t)j * nrows4;
-            const uint32_t neg = s_mult[j], negw = s_multw[j], pivw = s_pivw;
+            const uint32_t e = col[rs];
+            const uint32_t neg = e ? p - e : 0u;
+            const uint32_t negw = shoup_pre_fast(neg, p, A.pinv), pivw = shoup_pre_fast(piv, p, A.pinv);
             uint32_t cand = 0xffffffffu;
-#pragma unroll 3
-            for (uint32_t r = gt; r < nrows4; r += 256) {
+#pragma unroll 4
+            for (uint32_t r = lane; r < nrows4; r += 32) {
                 const uint32_t f = r == rs ? 0u : pc[r];
                 uint32_t v = shoup_mul(col[r], piv, pivw, p) + shoup_mul(f, neg, negw, p);
                 v = v >= p ? v - p : v;
                 col[r] = v;
-                if (v && !s_used[r]) cand = min(cand, r);
+                if (v && r != rs && !s_used[r]) cand = min(cand, r);
             }
             for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-            if (lane == 0 && cand != 0xffffffffu) atomicMin(&s_cand[j], cand);
-            if (gt == 0) s_scale[j] = mulmod(s_scale[j], piv, p, A.pinv);
+            if (lane == 0) { s_cand[j] = cand; s_scale[j] = mulmod(s_scale[j], piv, p, A.pinv); }
         }
         __syncthreads();
         tk1 = clock64(); telim += tk1 - tk0;
         ++np;
         cur = js + 1;
     }
+    __syncthreads();
     /* un-scaling factors and the inverses of the (true) pivot entries, all at once */
     if (tid < np) {
         const uint32_t isc = modinv(s_scale[s_pj[tid]], p);
@@ -1676,7 +1695,6 @@ __device__ void ge_panel_factor(const GeFusedArgs &A, uint32_t *s_panel, uint8_t
         st->visits += m; st->batches += np != 0;
         st->t[2] += tsel; st->t[3] += telim; st->t[4] += clock64() - tk0;
     }
-    (void)s_mult;
 }
 
 /* all CTAs: rank-b update with the pivots [k0, k1), the body of k_ge_batch_update_cached with L2 loads of

@@ -187,6 +187,10 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
     uint64_t ncoef = 0;
     const int nthr = fld<int32_t>(st, L.md_nthrds) > 1 ? fld<int32_t>(st, L.md_nthrds) : 1;
     f4la_ctx *cx = ctx();
+    {   /* the host side of the call uses the threads this F4 run was given (st->nthrds), not OpenMP's default */
+        static const bool blocking = getenv("F4LA_B200_BLOCKING_SYNC") && atoi(getenv("F4LA_B200_BLOCKING_SYNC")) != 0;
+        f4la_b200_set_host_mode(cx, nthr, blocking);
+    }
     dbg_t[0] = now_ms() - dbg_t0;
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
@@ -632,8 +636,9 @@ f4la_tape *f4la_b200_neogb_tape_end(void)
 void f4la_b200_tape_free(f4la_tape *tape)
 {
     if (!tape) return;
+    /* the contexts the structures were uploaded through may be gone already: release without touching them */
     for (auto &kv : tape->resident)
-        for (f4la_resident *r : kv.second) f4la_b200_release((f4la_ctx *)kv.first, r);
+        for (f4la_resident *r : kv.second) f4la_b200_release(nullptr, r);
     delete tape;
 }
 
@@ -676,9 +681,13 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
         if (tape->init_len[i] && len != tape->init_len[i]) return F4LA_ERR_ARG;
         cf[i].assign(init_cf + init_off[i], init_cf + init_off[i + 1]);
     }
+    static const bool dbg = getenv("F4LA_B200_TAPE_DEBUG") != nullptr;
+    double d_pool = 0, d_upd = 0, d_red = 0, d_post = 0, d_gpu[4] = {0, 0, 0, 0};
+    uint32_t d_launch = 0;
     for (size_t c = 0; c < tape->calls.size(); ++c) {
         const TapeCall &tc = tape->calls[c];
         const uint64_t ncoef = tc.cf_ptr.back();
+        const double tc0 = now_ms();
         if ((ncoef + 1) * 4 > T.pool_cap) {
             if (T.pool) f4la_b200_pinned_free(T.pool);
             T.pool_cap = 2 * (ncoef + 1) * 4 + (1 << 16);
@@ -693,9 +702,23 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
             memcpy(pool + tc.cf_ptr[sl], src.data(), len * 4);
         }
         f4la_resident *rm = (*res_vec)[c];
+        const double tc1 = now_ms();
         if (f4la_b200_resident_update(cx, rm, p, pool) != F4LA_OK) return F4LA_ERR_CUDA;
+        const double tc2 = now_ms();
         f4la_flat_result res;
-        if (f4la_b200_reduce_resident(cx, rm, &res, nullptr) != F4LA_OK) return F4LA_ERR_CUDA;
+        f4la_stats st;
+        if (f4la_b200_reduce_resident(cx, rm, &res, dbg ? &st : nullptr) != F4LA_OK) return F4LA_ERR_CUDA;
+        const double tc3 = now_ms();
+        if (dbg) {
+            d_gpu[0] += st.ms_prep; d_gpu[1] += st.ms_reduce; d_gpu[2] += st.ms_echelon; d_gpu[3] += st.ms_d2h;
+            d_launch += st.kernel_launches;
+            static const bool dbg2 = atoi(getenv("F4LA_B200_TAPE_DEBUG")) > 1;
+            if (dbg2)
+                fprintf(stderr, "[f4la tape]   call %zu: %u+%u rows, %u+%u cols, %llu coefs, rank %u: prep %.3f reduce %.3f "
+                        "echelon %.3f d2h %.3f ms, %u launches, wall %.3f\n", c, tc.nru, tc.nrl, tc.ncl, tc.ncr,
+                        (unsigned long long)ncoef, st.rank, st.ms_prep, st.ms_reduce, st.ms_echelon, st.ms_d2h,
+                        st.kernel_launches, tc3 - tc2);
+        }
         const uint32_t np = (uint32_t)tc.out_row_ptr.size() - 1;
         int rc = F4LA_OK;
         if (res.nrows != np) rc = F4LA_ERR_BADPRIME;                                   /* f4.c:433-441 */
@@ -716,7 +739,12 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
         }
         f4la_b200_free_result(&res);
         if (rc != F4LA_OK) return rc;
+        d_pool += tc1 - tc0; d_upd += tc2 - tc1; d_red += tc3 - tc2; d_post += now_ms() - tc3;
     }
+    if (dbg)
+        fprintf(stderr, "[f4la tape] prime %u: %.2f ms (setup %.2f, pools %.2f, update %.2f, reduce %.2f [device: prep %.2f "
+                "reduce %.2f echelon %.2f d2h %.2f; %u launches], results %.2f)\n", p, now_ms() - t0, 0.0, d_pool, d_upd,
+                d_red, d_gpu[0], d_gpu[1], d_gpu[2], d_gpu[3], d_launch, d_post);
     if (la_ms) *la_ms += now_ms() - t0;
     return F4LA_OK;
 }

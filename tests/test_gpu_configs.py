@@ -222,6 +222,24 @@ def test_gpu_qq_tape_replay_matches_reference(name):
             rc, resid, ms = tape.replay(be, p, cf, off)
             assert rc == 0, (name, p, rc)
             assert np.array_equal(resid, ref_resid[k]), (name, p)
+        # several host threads, one context each, replaying different primes of the same tape concurrently
+        import threading
+        inits = [rh.qq_initial_basis(p) for p in primes[1:]]
+        bes = [Backend(0) for _ in range(3)]
+        bad = []
+
+        def work(t):
+            for rep in range(2):
+                for k in range(t, len(inits), 3):
+                    rc, resid, _ = tape.replay(bes[t], primes[1 + k], *inits[k])
+                    if rc != 0 or not np.array_equal(resid, ref_resid[k]):
+                        bad.append((t, k, rc))
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        [b.close() for b in bes]
+        assert not bad, bad
     finally:
         if tape is not None:
             tape.free()
