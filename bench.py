@@ -48,11 +48,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+ALL_CPUS = os.sched_getaffinity(0)       # before any OpenMP runtime loads and pins this thread (see below)
+
 # the reference's OpenMP row loops (and the adapter's gather of the rows): one thread per core, no migration.
 # Not under torchrun: every rank would bind its threads to the same first cores.
 if int(os.environ.get("WORLD_SIZE", "1")) == 1:
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
+# the multi-modular section drives one stream per host thread: give each its own hardware queue (the default is 8)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
@@ -532,7 +536,7 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
     ncpu = os.cpu_count() or 8
     threads = max(1, ncpu // world)
     batch = args.qq_primes
-    all_primes = rh.primes_above(1 << 30, 2 + batch + world * threads)
+    all_primes = rh.primes_above(1 << 30, 2 + batch + world * 64)
     p0, p_tape = all_primes[0], all_primes[1]
     warm_primes = sharding.shard(all_primes[2 + batch:], rank, world)
     mine = sharding.shard(all_primes[2:2 + batch], rank, world)
@@ -564,42 +568,59 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
         rec, _, rec_resid = rh.qq_apply([p_tape], threads=1, ngpus=0, residue_words=words)
         tape = Tape.end(L)
         assert tape is not None and rec[0]["err"] == 0 and tape.residue_words == words
-        nthr = min(threads, 16)
-        backends = [Backend(local) for _ in range(nthr)]
+        # host threads per GPU and how they wait: tried on warm-up primes, the fastest runs the timed batch.
+        # (spinning waits are fastest while every thread has a core; with fewer cores than it takes to keep the GPU
+        # busy -- 8 ranks on a 16-core host -- more threads that sleep in their waits do better)
+        modes = sorted({(max(1, threads // 2), False), (min(threads, 16), False),
+                        (min(2 * threads, 32), True), (min(4 * threads, 32), True)})
+        backends = [Backend(local) for _ in range(max(m[0] for m in modes))]
 
         init_lock = threading.Lock()
 
-        def replay_some(k, primes):
-            res = np.zeros((len(primes), words), dtype=np.uint32)
+        all_cpus = ALL_CPUS
+
+        def replay_some(k, nthr, primes, res):
+            """host thread k of nthr: primes k, k + nthr, ... of the batch, residues written straight into their rows"""
+            # OMP_PROC_BIND pinned the main thread to the first core and new threads inherit that mask
+            os.sched_setaffinity(0, all_cpus)
             failed, ms = [], 0.0
-            for i, p in enumerate(primes):
+            for i in range(k, len(primes), nthr):
                 with init_lock:                      # the harness (reference code + GMP) is driven from one thread at a time
-                    cf, off = rh.qq_initial_basis(p, cap=1 << 16)
-                rc, resid, m = tape.replay(backends[k], p, cf, off)
+                    cf, off = rh.qq_initial_basis(primes[i], cap=1 << 16)
+                rc, _, m = tape.replay(backends[k], primes[i], cf, off, out=res[i])
                 ms += m
                 if rc != 0:
                     failed.append(i)
-                else:
-                    res[i] = resid
-            return res, failed, ms
+            return failed, ms
 
-        def replay_batch(primes):
-            parts = [primes[k::nthr] for k in range(nthr)]
+        def replay_batch(primes, mode):
+            nthr, blocking = mode
+            for b in backends[:nthr]:
+                b.set_host_mode(1, blocking)
+            res = np.empty((len(primes), words), dtype=np.uint32)
             with ThreadPoolExecutor(max_workers=nthr) as ex:
-                outs = list(ex.map(lambda kv: replay_some(*kv), enumerate(parts)))
-            res = np.zeros((len(primes), words), dtype=np.uint32)
-            redo = []
-            for k, (r, failed, _) in enumerate(outs):
-                res[k::nthr] = r
-                redo += [k + i * nthr for i in failed]
+                outs = list(ex.map(lambda k: replay_some(k, nthr, primes, res), range(nthr)))
+            redo = [i for failed, _ in outs for i in failed]
             if redo:                                 # bad prime / other support than recorded: the ordinary per-prime path
                 _, _, rr = rh.qq_apply([primes[i] for i in redo], threads=min(threads, len(redo)), ngpus=0, residue_words=words)
                 for i, row in zip(redo, rr):
                     res[i] = row
-            return res, len(redo), sum(o[2] for o in outs)
+            return res, len(redo), sum(o[1] for o in outs)
 
         # the tape reproduces the recorded prime, and the drop-in path's result for other primes
-        chk, _, _ = replay_batch([p_tape] + warm_primes[:nthr])
+        nmax = len(backends)
+        chk, _, _ = replay_batch([p_tape] + (warm_primes * 2)[:2 * nmax], (nmax, False))     # every context warm
+        trials = []
+        for mode in modes:
+            sample = (warm_primes * 8)[:max(32, 6 * mode[0])]
+            t0 = time.perf_counter()
+            replay_batch(sample, mode)
+            trials.append({"host_threads": mode[0], "blocking_waits": mode[1],
+                           "primes_per_s": len(sample) / (time.perf_counter() - t0)})
+        best = max(range(len(modes)), key=lambda i: trials[i]["primes_per_s"])
+        mode = modes[best]
+        nthr = mode[0]
+        log(f"rank {rank}: QQ replay host modes {trials} -> {mode}")
         assert np.array_equal(chk[0], rec_resid[0]), "tape replay differs from the recorded application run"
         _, _, want = rh.qq_apply(warm_primes[:2], threads=min(2, threads), ngpus=0, residue_words=words)
         assert np.array_equal(chk[1:3], want), "tape replay differs from the drop-in application run"
@@ -608,7 +629,7 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
         if rank == 0:
             sampler.start()
         t0 = time.perf_counter()
-        resid, fallbacks, replay_ms = replay_batch(mine)
+        resid, fallbacks, replay_ms = replay_batch(mine, mode)
         gathered = sharding.gather_residues(resid, dist if world > 1 else None, device=dev)
         torch.cuda.synchronize()
         el = max_over_ranks(time.perf_counter() - t0)
@@ -639,7 +660,8 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
                        "the batch replayed from the tape (coefficient pools in, reduced basis out, no symbolic host work), "
                        "residues of all primes all-gathered; verified equal to the per-prime drop-in path",
                "value": batch / el, "unit": "primes/s", "n_gpus": world, "primes": batch, "seconds": el,
-               "host_threads_per_gpu": nthr, "host_threads_total": nthr * world, "scaling": "strong",
+               "host_threads_per_gpu": nthr, "host_threads_total": nthr * world, "blocking_waits": mode[1],
+               "host_mode_trials": trials, "host_cores_per_gpu": threads, "scaling": "strong",
                "tape_calls": tape.calls, "replay_fallbacks": int(fallbacks),
                "replay_ms_per_prime": replay_ms / max(1, len(mine)),
                "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": words,
@@ -800,7 +822,7 @@ def main():
     ap.add_argument("--no-cold", action="store_true", help="skip the one-shot (fresh process) run")
     ap.add_argument("--no-qq-cpu", action="store_true", help="skip the CPU baseline of the QQ block")
     ap.add_argument("--qq-system", default="katsura-10")
-    ap.add_argument("--qq-primes", type=int, default=512, help="size of the fixed prime batch of the QQ block")
+    ap.add_argument("--qq-primes", type=int, default=1024, help="size of the fixed prime batch of the QQ block")
     ap.add_argument("--ref-budget-s", type=float, default=1200.0,
                     help="--impl reference: wall-clock budget; fewer steps are timed when K passes do not fit")
     args = ap.parse_args()

@@ -272,11 +272,14 @@ class Tape:
         h = lib.f4la_b200_neogb_tape_end()
         return Tape(lib, h) if h else None
 
-    def replay(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray):
-        """-> (return code, residues uint32 [residue_words], milliseconds)"""
+    def replay(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray, out: Optional[np.ndarray] = None):
+        """-> (return code, residues uint32 [residue_words], milliseconds); `out` (C-contiguous uint32 row of at least
+        residue_words) receives the residues in place when given"""
         init_cf = np.ascontiguousarray(init_cf, dtype=np.uint32)
         init_off = np.ascontiguousarray(init_off, dtype=np.uint64)
-        out = np.zeros(self.residue_words, dtype=np.uint32)
+        if out is None:
+            out = np.zeros(self.residue_words, dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= self.residue_words
         ms = C.c_double(0.0)
         rc = self.lib.f4la_b200_tape_replay(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data,
                                             out.ctypes.data, C.byref(ms))

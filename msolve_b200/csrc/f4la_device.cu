@@ -62,10 +62,9 @@ struct f4la_ctx {
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
     DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
-    DevBuf gebar;
     size_t        fused_smem_optin = 0;
     int           coop_ok = 0;          /* device supports cooperative launches (k_ge_fused) */
-    DevBuf sched, items, flowflags, refcnt, tcA, tcB, scB, scFlagA, scFlagB, scList, scCnt, scP;
+    DevBuf sched, items, flowflags, tcA, tcB, scB, scFlagA, scFlagB, scList, scCnt, scP;
     int           ge_mode = 0;          /* F4LA_B200_GE: (default) one persistent cooperative launch (k_ge_fused); "batched": two launches per
                                            batch of 8 pivots with the batch's pivot columns in shared memory (the round-1 default);
                                            "uncached": batched, pivot columns re-read from L2; "columnwise": one find + one
@@ -332,13 +331,14 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
     OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
     OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
     OK(ensure(ctx, ctx->used, (size_t)ld + 16));
-    OK(ensure(ctx, ctx->gestate, sizeof(GEState)));
+    OK(ensure(ctx, ctx->gestate, 256 + 64));                        /* GEState | grid barrier words of k_ge_fused */
     OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
     OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
     OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
     CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
     CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
-    CU(cudaMemsetAsync(ctx->gestate.p, 0, sizeof(GEState), s));
+    static_assert(sizeof(GEState) <= 256, "GEState");
+    CU(cudaMemsetAsync(ctx->gestate.p, 0, 256 + 64, s));
     GEState *h_state = (GEState *)ctx->h_small.p;
     const size_t smem_cap = (size_t)216 * 1024;
     /* pivots per batch such that the batch's pivot columns (+ one column, + the used bytes) fit in
@@ -362,8 +362,6 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             CU(cudaFuncSetAttribute(k_ge_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * 1024)));
             ctx->fused_smem_optin = (size_t)200 * 1024;
         }
-        OK(ensure(ctx, ctx->gebar, 64));
-        CU(cudaMemsetAsync(ctx->gebar.p, 0, 64, s));
         k_ge_init_flags<<<ncr, 256, 0, s>>>(Dm, ld, nrl, ncr, as<uint8_t>(ctx->colflag));
         note_launch(ctx, 1, __LINE__);
         GeFusedArgs a;
@@ -373,7 +371,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         a.st = as<GEState>(ctx->gestate);
         a.pivcol = as<uint32_t>(ctx->pivcol); a.pivrow = as<uint32_t>(ctx->pivrow); a.pivinv = as<uint32_t>(ctx->pivinv);
         a.p = p; a.two64 = (uint32_t)(((~0ull) % p + 1) % p); a.pinv = pinv;
-        a.bar = as<uint32_t>(ctx->gebar); a.err = as<uint32_t>(ctx->flags32);
+        a.bar = as<uint32_t>(ctx->gestate) + 64; a.err = as<uint32_t>(ctx->flags32);
         a.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6); a.max_iter = ncr + 8;
         unsigned grid = (ncr + 31) / 32;
         if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;
@@ -637,15 +635,15 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         return F4LA_OK;
     }
 
-    CU(cudaEventRecord(ctx->ev[0], s));
+    const bool timed = st != nullptr || ctx->debug;
+    if (timed) CU(cudaEventRecord(ctx->ev[0], s));
 
-    OK(ensure(ctx, ctx->flags32, 64));
+    OK(ensure(ctx, ctx->flags32, 64 + (size_t)kRefSlots * 32));     /* error/flag words | unit counters: one memset, one read-back */
     OK(ensure_host(ctx, ctx->h_small, 1 << 20));
     uint32_t *h_small = (uint32_t *)ctx->h_small.p;
     uint32_t *d_err = as<uint32_t>(ctx->flags32);           /* [0] err, [1] changed, [2] max level */
-    CU(cudaMemsetAsync(d_err, 0, 64, s));
-    OK(ensure(ctx, ctx->refcnt, (size_t)kRefSlots * 32));
-    CU(cudaMemsetAsync(ctx->refcnt.p, 0, (size_t)kRefSlots * 32, s));
+    unsigned long long *d_ref = reinterpret_cast<unsigned long long *>(d_err + 16);
+    CU(cudaMemsetAsync(d_err, 0, 64 + (size_t)kRefSlots * 32, s));
     const uint32_t *colmap = nullptr;
     PrepCache *pc = m->cache_enabled ? &m->cache : nullptr;
     const bool cached = pc && pc->valid;
@@ -753,7 +751,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     d_col_ptr = as<uint32_t>(ctx->col_ptr); d_ent = as<uint2>(ctx->ent);
     if (by_lead) d_invmap = as<uint32_t>(ctx->invmap);
     }   /* !cached */
-    CU(cudaEventRecord(ctx->ev[1], s));
+    if (timed) CU(cudaEventRecord(ctx->ev[1], s));
 
     /* Probabilistic mode (the reference's -l 42/43/44, la_ff_32.c:2305-2506): the nrl lower rows
      * are replaced by k << nrl random linear combinations of them; when the echelon form of the
@@ -868,7 +866,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
         if (ncl) {
             k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(d_col_ptr, ncl, nc, g,
-                                                               as<uint32_t>(ctx->flowflags));
+                                                               as<uint32_t>(ctx->flowflags), d_err + 4);
             note_launch(ctx, 1, __LINE__);
         }
         if (ctx->copy_pending) {                  /* the lower rows of a split host->device copy */
@@ -902,8 +900,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6);
         /* reference-equivalent unit count: pivots keyed by row index, true lower rows only */
         f.piv_row_ptr = (!by_lead && !combos && !getenv("F4LA_B200_NOUNITS")) ? m->row_ptr : nullptr;
-        f.ref_units = as<unsigned long long>(ctx->refcnt);
-        CU(cudaMemsetAsync(d_err + 4, 0, 4, s));
+        f.ref_units = d_ref;
+        if (!ncl) CU(cudaMemsetAsync(d_err + 4, 0, 4, s));      /* else: zeroed by k_flow_reset_flags */
         if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
         if (schur) {
@@ -967,7 +965,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             note_launch(ctx, 1, __LINE__);
         }
     }
-    CU(cudaEventRecord(ctx->ev[2], s));
+    if (timed) CU(cudaEventRecord(ctx->ev[2], s));
 
     /* ---- 4. Gauss-Jordan on the trailing block (not in normal-form mode) ---- */
     maxrank = nrl < ncr ? nrl : ncr;
@@ -1003,16 +1001,15 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint64_t ref_units = 0, ref_apps = 0;
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
-        uint64_t *h_ref = (uint64_t *)((uint32_t *)ctx->h_small.p + 256);
-        CU(cudaMemcpyAsync(h_err, d_err, 64, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(h_ref, ctx->refcnt.p, (size_t)kRefSlots * 32, cudaMemcpyDeviceToHost, s));
+        uint64_t *h_ref = (uint64_t *)(h_err + 16);
+        CU(cudaMemcpyAsync(h_err, d_err, 64 + (size_t)kRefSlots * 32, cudaMemcpyDeviceToHost, s));
         OK(stream_sync(ctx));
         for (uint32_t k = 0; k < kRefSlots; ++k) { ref_units += h_ref[4 * k]; ref_apps += h_ref[4 * k + 1]; }
         if (*h_err)
             return fail(ctx, F4LA_ERR_CUDA, "device pipeline reported error bits 0x%x (4: column out of range in a lower "
                         "row, 16: dataflow watchdog expired)", *h_err);
     }
-    CU(cudaEventRecord(ctx->ev[3], s));
+    if (timed) CU(cudaEventRecord(ctx->ev[3], s));
 
     /* ---- 5. result rows back to the host ---- */
     const uint32_t ndense = (nf_mode || by_lead) ? nrl : rank;       /* dense rows produced on the device */
@@ -1092,13 +1089,21 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->src_row = (uint32_t *)malloc((size_t)nout * sizeof(uint32_t));
         std::vector<uint64_t> rnz(nout, 0);
         const int host_thr = ctx->host_threads > 0 ? ctx->host_threads : omp_get_max_threads();
-#pragma omp parallel for num_threads(host_thr) schedule(static) if (nout > 16 && host_thr > 1)
-        for (uint32_t t = 0; t < nout; ++t) {
-            if (pick[t] < 0) continue;
+        /* (a thread that never enters an OpenMP construct is never touched by the runtime: with OMP_PROC_BIND set,
+         * libgomp pins every foreign thread that does -- even for a serialised region -- to the first place) */
+        const bool par = nout > 16 && host_thr > 1;
+        auto count_row = [&](uint32_t t) {
+            if (pick[t] < 0) return;
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
             uint64_t n = by_lead ? 1 : 0;                          /* by_lead: the lead term itself */
             for (uint32_t c = 0; c < ncr; ++c) n += row[c] != 0;
             rnz[t] = n;
+        };
+        if (par) {
+#pragma omp parallel for num_threads(host_thr) schedule(static)
+            for (uint32_t t = 0; t < nout; ++t) count_row(t);
+        } else {
+            for (uint32_t t = 0; t < nout; ++t) count_row(t);
         }
         uint64_t nnz = 0;
         for (uint32_t t = 0; t < nout; ++t) {
@@ -1111,9 +1116,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         out->row_ptr[nout] = nnz;
         out->cols = (uint32_t *)malloc((nnz ? nnz : 1) * sizeof(uint32_t));
         out->cf = malloc((nnz ? nnz : 1) * (size_t)d.cf_bytes);
-#pragma omp parallel for num_threads(host_thr) schedule(static) if (nout > 16 && host_thr > 1)
-        for (uint32_t t = 0; t < nout; ++t) {
-            if (pick[t] < 0) continue;
+        auto fill_row = [&](uint32_t t) {
+            if (pick[t] < 0) return;
             uint64_t k = out->row_ptr[t];
             const uint32_t *row = h_dense + (size_t)pick[t] * ncr;
             if (by_lead) {
@@ -1132,6 +1136,12 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                 else ((uint8_t *)out->cf)[k] = (uint8_t)v;
                 ++k;
             }
+        };
+        if (par) {
+#pragma omp parallel for num_threads(host_thr) schedule(static)
+            for (uint32_t t = 0; t < nout; ++t) fill_row(t);
+        } else {
+            for (uint32_t t = 0; t < nout; ++t) fill_row(t);
         }
     }
     if (ctx->debug) fprintf(stderr, "[f4la debug] result: %u rows, wait for extract + D2H %.3f ms, host compaction %.3f ms\n", nout, dbg_copy_ms, now_ms() - dbg_t1);
@@ -1142,8 +1152,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         OK(stream_sync(ctx));
         d2h_bytes += (uint64_t)nrl * rba_words * 4;
     }
-    CU(cudaEventRecord(ctx->ev[4], s));
-    CU(cudaEventSynchronize(ctx->ev[4]));
+    if (timed) {
+        CU(cudaEventRecord(ctx->ev[4], s));
+        CU(cudaEventSynchronize(ctx->ev[4]));
+    }
 
     if (st) {
         float ms = 0;
@@ -1335,7 +1347,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
                       &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
                       &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
-                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->refcnt, &ctx->gebar, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
+                      &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
     for (auto b : bufs) free_dev(*b);

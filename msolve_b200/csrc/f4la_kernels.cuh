@@ -801,9 +801,10 @@ k_pull_flow(const FlowArgs A)
  * ready, zero"; k_scatter_lower upgrades the touched ones to "non-zero".  The words of the
  * other columns are left alone (their epoch is stale until the column is solved). */
 __global__ void k_flow_reset_flags(const uint32_t *__restrict__ col_ptr, uint32_t ncl, uint32_t nc, uint32_t g,
-                                   uint32_t *__restrict__ flags)
+                                   uint32_t *__restrict__ flags, uint32_t *__restrict__ counter)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *counter = 0;                    /* work counter of the dataflow kernel that follows */
     if (j >= ncl || col_ptr[j + 1] != col_ptr[j]) return;
     for (uint32_t k = 0; k < g; ++k) flags[(size_t)k * nc + j] = kFlagAlwaysZ;
 }

@@ -55,7 +55,8 @@ struct f4la_tape {
     bool valid = true;
     /* per context: the structures resident in HBM (uploaded at the first replay on that context) */
     std::mutex mu;
-    std::map<void *, std::vector<f4la_resident *>> resident;
+    struct PerCtx { std::vector<f4la_resident *> res; void *pool = nullptr; };   /* pool: pinned, largest call */
+    std::map<void *, PerCtx> resident;
 };
 
 namespace {
@@ -68,12 +69,9 @@ struct ThreadState {
     size_t cap[5] = {0, 0, 0, 0, 0};
     f4la_neogb_totals tot = {};
     f4la_tape *tape = nullptr;          /* recording (f4la_b200_neogb_tape_begin) */
-    void *pool = nullptr;               /* pinned coefficient pool of the replays */
-    size_t pool_cap = 0;
     ~ThreadState()
     {
         for (auto &b : buf) if (b) f4la_b200_pinned_free(b);
-        if (pool) f4la_b200_pinned_free(pool);
         delete tape;
         if (ctx) f4la_b200_destroy(ctx);
     }
@@ -637,8 +635,10 @@ void f4la_b200_tape_free(f4la_tape *tape)
 {
     if (!tape) return;
     /* the contexts the structures were uploaded through may be gone already: release without touching them */
-    for (auto &kv : tape->resident)
-        for (f4la_resident *r : kv.second) f4la_b200_release(nullptr, r);
+    for (auto &kv : tape->resident) {
+        for (f4la_resident *r : kv.second.res) f4la_b200_release(nullptr, r);
+        if (kv.second.pool) f4la_b200_pinned_free(kv.second.pool);
+    }
     delete tape;
 }
 
@@ -656,9 +656,19 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
     const double t0 = now_ms();
     /* the structures of all calls, resident in HBM once per context */
     std::vector<f4la_resident *> *res_vec;
+    f4la_tape::PerCtx *pcx;
     {
         std::lock_guard<std::mutex> lk(tape->mu);
-        res_vec = &tape->resident[vctx];
+        pcx = &tape->resident[vctx];
+        res_vec = &pcx->res;
+    }
+    if (!pcx->pool) {
+        /* one page-locked coefficient pool per context, sized for the largest call: allocating (or growing) page-locked
+         * memory synchronises the whole device, which every other context's replay would feel */
+        uint64_t mx = 0;
+        for (const TapeCall &tc : tape->calls) mx = std::max<uint64_t>(mx, tc.cf_ptr.back());
+        pcx->pool = f4la_b200_pinned_alloc((mx + 1) * 4);
+        if (!pcx->pool) return F4LA_ERR_CUDA;
     }
     if (res_vec->empty()) {
         for (const TapeCall &tc : tape->calls) {
@@ -688,13 +698,7 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
         const TapeCall &tc = tape->calls[c];
         const uint64_t ncoef = tc.cf_ptr.back();
         const double tc0 = now_ms();
-        if ((ncoef + 1) * 4 > T.pool_cap) {
-            if (T.pool) f4la_b200_pinned_free(T.pool);
-            T.pool_cap = 2 * (ncoef + 1) * 4 + (1 << 16);
-            T.pool = f4la_b200_pinned_alloc(T.pool_cap);
-            if (!T.pool) { T.pool_cap = 0; return F4LA_ERR_CUDA; }
-        }
-        uint32_t *pool = (uint32_t *)T.pool;
+        uint32_t *pool = (uint32_t *)pcx->pool;
         for (size_t sl = 0; sl < tc.slot_bindex.size(); ++sl) {
             const std::vector<uint32_t> &src = cf[tc.slot_bindex[sl]];
             const uint64_t len = tc.cf_ptr[sl + 1] - tc.cf_ptr[sl];

@@ -65,7 +65,7 @@ def gather_residues(local: "np.ndarray", dist=None, device="cpu") -> "np.ndarray
     i % world, see :func:`shard`) on every rank.  One collective for the counts, one for the payload."""
     local = np.ascontiguousarray(local, dtype=np.uint32)
     if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return local.copy()
+        return local                                    # nothing to exchange
     import torch
     world = dist.get_world_size()
     k, words = local.shape

@@ -15,7 +15,11 @@ def main():
     ap.add_argument("--primes", type=int, default=64)
     ap.add_argument("--threads", default="1,4,16")
     ap.add_argument("--blocking", type=int, default=0)
+    ap.add_argument("--torch", type=int, default=0, help="initialise torch's CUDA context first (as bench.py does)")
     args = ap.parse_args()
+    if args.torch:
+        import torch
+        torch.cuda.init(); torch.zeros(1, device="cuda")
     import gpu_helpers
     from msolve_b200 import systems
     from msolve_b200.backend import Backend, Tape
