@@ -58,11 +58,13 @@ def gather_uint64(local: Sequence[int], dist=None, device="cpu") -> List[List[in
     return out
 
 
-def gather_residues(local: "np.ndarray", dist=None, device="cpu") -> "np.ndarray":
+def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarray" = None) -> "np.ndarray":
     """All-gather the modular results of a batch: ``local`` is uint32 [k, words], one row per prime of this
     rank (the coefficients of the modular Groebner basis / parametrisation, what msolve hands to CRT,
     msolve.c:2694-2712).  Returns uint32 [sum k, words] in BATCH order (prime i of the batch came from rank
-    i % world, see :func:`shard`) on every rank.  One collective for the counts, one for the payload."""
+    i % world, see :func:`shard`) on every rank.  One collective for the counts, one for the payload; the
+    interleave into batch order happens on the device, so the host sees one copy in and one copy out (at
+    PCIe speed when ``local`` and ``out`` are page-locked, see :func:`pinned_rows`)."""
     local = np.ascontiguousarray(local, dtype=np.uint32)
     if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return local                                    # nothing to exchange
@@ -74,16 +76,29 @@ def gather_residues(local: "np.ndarray", dist=None, device="cpu") -> "np.ndarray
     dist.all_gather(metas, meta)
     ks = [int(m[0].item()) for m in metas]
     assert all(int(m[1].item()) == words or int(m[0].item()) == 0 for m in metas), "ranks disagree on the residue length"
-    kmax = max(max(ks), 1)
-    pad = np.zeros((kmax, max(words, 1)), dtype=np.int32)          # NCCL / gloo: no uint32, same bits as int32
-    pad[:k, :words] = local.view(np.int32)
-    t = torch.from_numpy(pad).to(device)
-    bufs = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(bufs, t)
-    total = sum(ks)
-    out = np.zeros((total, words), dtype=np.uint32)
-    for r in range(world):
-        b = bufs[r].cpu().numpy().view(np.uint32)
-        for j in range(ks[r]):
-            out[r + j * world] = b[j, :words]
+    # round-robin sharding: the counts differ by at most one and the longer shards come first
+    assert all(ks[r] >= ks[r + 1] and ks[0] - ks[r + 1] <= 1 for r in range(world - 1)), "not a round-robin shard"
+    kmax, total = max(max(ks), 1), sum(ks)
+    words = max(words, 1)
+    t = torch.zeros((kmax, words), dtype=torch.int32, device=device)          # NCCL / gloo: no uint32, same bits
+    if k:
+        t[:k].copy_(torch.from_numpy(local.view(np.int32)), non_blocking=True)
+    big = torch.empty((world, kmax, words), dtype=torch.int32, device=device)
+    dist.all_gather(list(big.unbind(0)), t)
+    inter = big.transpose(0, 1).reshape(world * kmax, words)[:total]          # row r + j * world = row j of rank r
+    if out is None:
+        out = np.empty((total, words), dtype=np.uint32)
+    assert out.shape == (total, words) and out.dtype == np.uint32 and out.flags.c_contiguous
+    torch.from_numpy(out.view(np.int32)).copy_(inter)
     return out
+
+
+def pinned_rows(rows: int, words: int) -> "np.ndarray":
+    """uint32 [rows, words] in page-locked host memory (the residues of a batch: written by the replays, read by the
+    copy engine).  The torch tensor that owns the memory is kept alive by the array."""
+    import torch
+    t = torch.empty((max(rows, 1), max(words, 1)), dtype=torch.int32)
+    if torch.cuda.is_available():
+        t = t.pin_memory()
+    a = t.numpy().view(np.uint32)[:rows, :words]
+    return a
