@@ -93,6 +93,7 @@ struct f4la_ctx {
     int           flow_blocks_per_sm[2][kMaxT + 1] = {};
     size_t        l2_budget = 0;
     double        watchdog_ms = 20000.0; /* F4LA_B200_WATCHDOG_MS: longest wait for a source column in the dataflow kernel */
+    uint32_t      ge_panel = 0;                   /* panel width cap of k_ge_fused (0: kPanelMax) */
     uint32_t      grid_cap = 0;                   /* CTAs a persistent kernel of this context may occupy (0: the device) */
     int           host_threads = 0;               /* threads of the host-side result compaction (0: OpenMP default) */
     bool          blocking_sync = false;          /* waits sleep on a blocking event instead of spinning */
@@ -355,6 +356,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         const size_t dyn_cap = (size_t)200 * 1024;
         if ((size_t)nrows4 * 9 <= dyn_cap) pw = (uint32_t)((dyn_cap - nrows4) / ((size_t)nrows4 * 4));
         if (pw > kPanelMax) pw = kPanelMax;
+        if (ctx->ge_panel && pw > ctx->ge_panel) pw = ctx->ge_panel;
     }
     if (pw >= 2 && ctx->ge_mode == 0 && ctx->coop_ok) {
         const size_t dyn = (size_t)pw * nrows4 * 4 + nrows4;
@@ -372,7 +374,7 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         a.pivcol = as<uint32_t>(ctx->pivcol); a.pivrow = as<uint32_t>(ctx->pivrow); a.pivinv = as<uint32_t>(ctx->pivinv);
         a.p = p; a.two64 = (uint32_t)(((~0ull) % p + 1) % p); a.pinv = pinv;
         a.bar = as<uint32_t>(ctx->gestate) + 64; a.err = as<uint32_t>(ctx->flags32);
-        a.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6); a.max_iter = ncr + 8;
+        a.watchdog_ns = (uint64_t)(ctx->watchdog_ms * 1e6); a.max_iter = ncr + 8; a.debug = ctx->debug ? 1u : 0u;
         unsigned grid = (ncr + 31) / 32;
         if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;
         if (grid < 1) grid = 1;
@@ -388,9 +390,10 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->dbg_ev[0], ctx->dbg_ev[1]);
             fprintf(stderr, "[f4la debug] k_ge_fused %u x %u: %.3f ms, grid %u, panel width %u; CTA 0 kilo-cycles: gather %llu load %llu "
-                    "select+inverse %llu eliminate %llu write-back %llu update %llu barriers %llu total %llu\n", nrl, ncr, ms, grid, pw,
+                    "select+inverse %llu eliminate %llu write-back %llu update %llu barriers %llu total %llu; any CTA: longest update %llu, "
+                    "longest wait for the panel %llu\n", nrl, ncr, ms, grid, pw,
                     h_state->t[0] / 1000, h_state->t[1] / 1000, h_state->t[2] / 1000, h_state->t[3] / 1000, h_state->t[4] / 1000,
-                    h_state->t[5] / 1000, h_state->t[6] / 1000, h_state->t[7] / 1000);
+                    h_state->t[5] / 1000, h_state->t[6] / 1000, h_state->t[7] / 1000, h_state->t[8] / 1000, h_state->t[9] / 1000);
         }
         if (!h_state->done)
             return fail(ctx, F4LA_ERR_CUDA, "fused Gauss-Jordan did not finish (rank %u, next column %u of %u)", h_state->rank,
@@ -1327,6 +1330,7 @@ f4la_ctx *f4la_b200_create(int device)
     if (zc) ctx->zerocopy = atoi(zc) != 0;
     const char *dbg = getenv("F4LA_B200_DEBUG");
     ctx->debug = dbg && atoi(dbg) != 0;
+    { const char *gp = getenv("F4LA_B200_GE_PANEL"); if (gp && atoi(gp) >= 2) ctx->ge_panel = (uint32_t)atoi(gp); }
     { const char *gc = getenv("F4LA_B200_GRID_CAP"); if (gc) ctx->grid_cap = (uint32_t)atoi(gc); }
     const char *dsy = getenv("F4LA_B200_SYNC");
     ctx->debug_sync = dsy && atoi(dsy) != 0;

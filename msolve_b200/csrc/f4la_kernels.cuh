@@ -834,8 +834,8 @@ struct GEState {
     uint32_t visits;     /* columns loaded by the discovery (statistics)     */
     uint32_t batches;    /* non-empty batches (statistics)                   */
     uint32_t pad;
-    unsigned long long t[8];   /* k_ge_fused, CTA 0, clock cycles: gather, load, select + inverse, eliminate, write-back,
-                                  update, barrier waits, total */
+    unsigned long long t[10];  /* k_ge_fused, CTA 0, clock cycles: gather, load, select + inverse, eliminate, write-back,
+                                  update, barrier waits, total; [8] longest update of any CTA, [9] longest first wait */
 };
 
 /* colflag[c] = 1 iff column c has a non-zero entry in a row that is not a
@@ -1526,7 +1526,7 @@ struct GeFusedArgs {
     uint32_t *pivcol, *pivrow, *pivinv;
     uint32_t p, two64; uint64_t pinv;
     uint32_t *bar;            /* [0] arrival counter, [1] abort flag; zeroed before the launch */
-    uint32_t *err; uint64_t watchdog_ns; uint32_t max_iter;
+    uint32_t *err; uint64_t watchdog_ns; uint32_t max_iter; uint32_t debug;
 };
 
 /* true = abort (watchdog expired somewhere) */
@@ -1777,6 +1777,7 @@ k_ge_fused(const GeFusedArgs A)
     uint32_t round = 0;
     const bool t0 = blockIdx.x == 0 && threadIdx.x == 0;
     const long long t_begin = clock64();
+    long long upd_cycles = 0, wait1_cycles = 0;
     for (uint32_t it = 0; it < A.max_iter; ++it) {
         if (blockIdx.x == 0) ge_panel_factor(A, s_dyn, s_used);
         long long ta = clock64();
@@ -1784,8 +1785,13 @@ k_ge_fused(const GeFusedArgs A)
         long long tb = clock64();
         const uint32_t k0 = __ldcg(&A.st->cur_col), k1 = __ldcg(&A.st->rank), done = __ldcg(&A.st->done);
         if (k0 < k1) ge_fused_update(A, k0, k1, s_dyn, s_used);
-        else if (done) { if (t0) A.st->t[7] += clock64() - t_begin; return; }
+        else if (done) {
+            if (t0) A.st->t[7] += clock64() - t_begin;
+            if (A.debug && threadIdx.x == 0) { atomicMax(&A.st->t[8], (unsigned long long)upd_cycles); if (blockIdx.x) atomicMax(&A.st->t[9], (unsigned long long)wait1_cycles); }
+            return;
+        }
         long long tc = clock64();
+        upd_cycles += tc - tb; wait1_cycles += tb - ta;
         if (ge_grid_barrier(A, round)) return;
         if (t0) { A.st->t[5] += tc - tb; A.st->t[6] += (tb - ta) + (clock64() - tc); }
     }
