@@ -51,6 +51,7 @@ struct f4la_ctx {
     cudaStream_t  stream = nullptr;
     cudaStream_t  copy_stream = nullptr;  /* f4la_b200_reduce(): the lower rows travel while the pull lists are built */
     cudaEvent_t   ev_copy = nullptr;
+    cudaEvent_t   ev_side[2] = {nullptr, nullptr};   /* fork / join of the side stream that builds the Schur B tiles */
     bool          copy_pending = false;
     int           split_h2d = 1;          /* F4LA_B200_SPLIT_H2D=0: one copy on the compute stream */
     cudaEvent_t   ev[8] = {};
@@ -769,7 +770,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     uint32_t rank = 0, Rc = 0, nchunks = 0, G = 0, n_items = 0, maxrank = 0;
     uint64_t ld = 0;
     int T = 1, n_flow_ev = 0;
-    bool items_built = false, schur = false, schur_b_built = false;
+    bool items_built = false, schur = false, schur_b_built = false, schur_side_pending = false;
     uint32_t *Dm = nullptr;
     uint64_t ge_ld = 0;               /* leading dimension of the block the reduced rows are read from */
     uint32_t echelon_path = 0;
@@ -863,6 +864,35 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
 
     if (want_rba && rba_words) OK(ensure(ctx, ctx->rba, (size_t)nrl * rba_words * 4 + 16));
 
+    if (schur && !schur_b_built) {
+        /* The tiles of B (stage images of the non-pivot pull lists) depend on the pivot rows only: they are built once
+         * per matrix, on the side stream, while the main stream scatters the lower rows and runs the dataflow kernel. */
+        schur_b_built = true;
+        SchurArgs sb;
+        memset(&sb, 0, sizeof(sb));
+        sb.nc = nc; sb.ncl = ncl; sb.ncr = ncr; sb.col_ptr = d_col_ptr; sb.ent = d_ent;
+        sb.nblk = (ncr + kTcBN - 1) / kTcBN; sb.nkb = (ncl + kTcBK - 1) / kTcBK;
+        OK(ensure(ctx, ctx->scB, (size_t)sb.nblk * sb.nkb * kTcStageB));
+        OK(ensure(ctx, ctx->scFlagB, (size_t)sb.nblk * sb.nkb + 16));
+        OK(ensure(ctx, ctx->scList, (size_t)sb.nblk * sb.nkb * 4 + 16));
+        OK(ensure(ctx, ctx->scCnt, (size_t)sb.nblk * 4 + 16));
+        OK(ensure_host(ctx, ctx->h_small, ((size_t)sb.nblk + 1024) * 4));
+        sb.Bsplit = as<uint8_t>(ctx->scB); sb.flagB = as<uint8_t>(ctx->scFlagB);
+        sb.list = as<uint32_t>(ctx->scList); sb.list_cnt = as<uint32_t>(ctx->scCnt);
+        cudaStream_t s2 = ctx->copy_stream;
+        CU(cudaEventRecord(ctx->ev_side[0], s));
+        CU(cudaStreamWaitEvent(s2, ctx->ev_side[0], 0));
+        CU(cudaMemsetAsync(ctx->scB.p, 0, (size_t)sb.nblk * sb.nkb * kTcStageB, s2));
+        CU(cudaMemsetAsync(ctx->scFlagB.p, 0, (size_t)sb.nblk * sb.nkb, s2));
+        k_schur_b_build<<<blocks_for_warps(ncr), 256, 0, s2>>>(sb);
+        k_schur_lists<<<sb.nblk, 256, 0, s2>>>(sb);
+        note_launch(ctx, 2, __LINE__);
+        if (!(pc && pc->schur_nseg))
+            CU(cudaMemcpyAsync((uint32_t *)ctx->h_small.p + 512, ctx->scCnt.p, (size_t)sb.nblk * 4, cudaMemcpyDeviceToHost, s2));
+        CU(cudaEventRecord(ctx->ev_side[1], s2));
+        schur_side_pending = true;
+    }
+
     uint32_t epoch = 0;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
@@ -925,27 +955,21 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             sa.Asplit = as<uint8_t>(ctx->tcA); sa.Bsplit = as<uint8_t>(ctx->scB);
             sa.flagA = as<uint8_t>(ctx->scFlagA); sa.flagB = as<uint8_t>(ctx->scFlagB);
             sa.list = as<uint32_t>(ctx->scList); sa.list_cnt = as<uint32_t>(ctx->scCnt);
-            if (!schur_b_built) {
-                /* B does not depend on the lower rows: built once per matrix */
-                schur_b_built = true;
-                CU(cudaMemsetAsync(ctx->scB.p, 0, (size_t)sa.nblk * sa.nkb * kTcStageB, s));
-                CU(cudaMemsetAsync(ctx->scFlagB.p, 0, (size_t)sa.nblk * sa.nkb, s));
-                k_schur_b_build<<<blocks_for_warps(ncr), 256, 0, s>>>(sa);
-                k_schur_lists<<<sa.nblk, 256, 0, s>>>(sa);
-                note_launch(ctx, 2, __LINE__);
-                if (pc && pc->schur_nseg) {
-                    schur_nseg = pc->schur_nseg;              /* the tile lists only depend on the structure */
-                } else {
-                    OK(ensure_host(ctx, ctx->h_small, ((size_t)sa.nblk + 1024) * 4));
-                    uint32_t *h_cnt = (uint32_t *)ctx->h_small.p + 512;
-                    CU(cudaMemcpyAsync(h_cnt, ctx->scCnt.p, (size_t)sa.nblk * 4, cudaMemcpyDeviceToHost, s));
-                    OK(stream_sync(ctx));
+            if (schur_side_pending) {
+                /* join the side stream that built the tiles of B while the dataflow kernel ran */
+                schur_side_pending = false;
+                if (!(pc && pc->schur_nseg)) {
+                    CU(cudaStreamSynchronize(ctx->copy_stream));
+                    const uint32_t *h_cnt = (const uint32_t *)ctx->h_small.p + 512;
                     uint32_t mx = 0;
                     for (uint32_t k = 0; k < sa.nblk; ++k) mx = h_cnt[k] > mx ? h_cnt[k] : mx;
                     schur_nseg = (mx + kSchurSeg - 1) / kSchurSeg;
                     if (schur_nseg < 1) schur_nseg = 1;
                     if (pc) pc->schur_nseg = schur_nseg;
+                } else {
+                    schur_nseg = pc->schur_nseg;              /* the tile lists only depend on the structure */
                 }
+                CU(cudaStreamWaitEvent(s, ctx->ev_side[1], 0));
             }
             sa.nseg = schur_nseg;
             OK(ensure(ctx, ctx->scP, (size_t)sa.nseg * ncr * sa.ldp * 4));
@@ -1304,6 +1328,7 @@ f4la_ctx *f4la_b200_create(int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    for (auto &e : ctx->ev_side) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     { const char *sp = getenv("F4LA_B200_SPLIT_H2D"); if (sp) ctx->split_h2d = atoi(sp) != 0; }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->dbg_ev) cudaEventCreate(&e);
@@ -1368,6 +1393,7 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaEventDestroy(ctx->ev_copy);
+    for (auto &e : ctx->ev_side) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -23,6 +23,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <emmintrin.h>
 
 #include "f4la_b200.h"
 #include "f4la_b200_neogb.h"
@@ -78,6 +79,34 @@ struct ThreadState {
 };
 
 thread_local ThreadState T;
+
+/* Gather copy into a page-locked staging piece.  The piece is written once and then read by the copy engine, never by
+ * this CPU: non-temporal stores skip the read-for-ownership of the destination lines (a third of the DRAM traffic of a
+ * plain memcpy at these sizes).  F4LA_B200_NT_COPY=0 restores memcpy. */
+static const bool g_nt_copy = !(getenv("F4LA_B200_NT_COPY") && atoi(getenv("F4LA_B200_NT_COPY")) == 0);
+
+static inline void copy_to_staging(void *dst, const void *src, size_t n)
+{
+    unsigned char *d = (unsigned char *)dst;
+    const unsigned char *s = (const unsigned char *)src;
+    if (!g_nt_copy || n < 512) { memcpy(d, s, n); return; }
+    const size_t head = (64 - ((uintptr_t)d & 63)) & 63;
+    memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a0 = _mm_loadu_si128((const __m128i *)(s + 64 * i));
+        const __m128i a1 = _mm_loadu_si128((const __m128i *)(s + 64 * i + 16));
+        const __m128i a2 = _mm_loadu_si128((const __m128i *)(s + 64 * i + 32));
+        const __m128i a3 = _mm_loadu_si128((const __m128i *)(s + 64 * i + 48));
+        _mm_stream_si128((__m128i *)(d + 64 * i), a0);
+        _mm_stream_si128((__m128i *)(d + 64 * i + 16), a1);
+        _mm_stream_si128((__m128i *)(d + 64 * i + 32), a2);
+        _mm_stream_si128((__m128i *)(d + 64 * i + 48), a3);
+    }
+    memcpy(d + 64 * blocks, s + 64 * blocks, n - 64 * blocks);
+    _mm_sfence();
+}
 
 template <typename V> V &fld(void *base, uint32_t off) { return *reinterpret_cast<V *>((char *)base + off); }
 template <typename V> const V &fld(const void *base, uint32_t off) { return *reinterpret_cast<const V *>((const char *)base + off); }
@@ -227,7 +256,7 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
             for (uint32_t r = r_lo; r < r_hi; ++r) {
                 const uint32_t *row = r < nru ? rr[r] : tr[r - nru];
                 const uint64_t lo = std::max<uint64_t>(row_ptr[r], a), hi = std::min<uint64_t>(row_ptr[r + 1], b);
-                if (hi > lo) memcpy(dst + (lo - a), row + L.row_offset + (lo - row_ptr[r]), (size_t)(hi - lo) * 4);
+                if (hi > lo) copy_to_staging(dst + (lo - a), row + L.row_offset + (lo - row_ptr[r]), (size_t)(hi - lo) * 4);
             }
             const double tc = now_ms();
             if (f4la_b200_stage_commit(cx, F4LA_STAGE_COLS, 4, a, b - a, nnz) != F4LA_OK) die(f4la_b200_last_error(cx));
@@ -248,7 +277,7 @@ int echelon(void *mat, const void *tbr, const void *bs, void *st, Entry entry = 
 #pragma omp parallel for num_threads(nthr) schedule(static) if (c_hi - c_lo > 64)
             for (uint32_t c = c_lo; c < c_hi; ++c) {
                 const uint64_t lo = std::max<uint64_t>(cfp[c], a), hi = std::min<uint64_t>(cfp[c + 1], b);
-                if (hi > lo) memcpy(dst + (lo - a) * w, (const unsigned char *)cfsrc[c] + (lo - cfp[c]) * w, (size_t)(hi - lo) * w);
+                if (hi > lo) copy_to_staging(dst + (lo - a) * w, (const unsigned char *)cfsrc[c] + (lo - cfp[c]) * w, (size_t)(hi - lo) * w);
             }
             if (f4la_b200_stage_commit(cx, F4LA_STAGE_CF, w, a, b - a, ncoef) != F4LA_OK) die(f4la_b200_last_error(cx));
             a = b;
