@@ -270,7 +270,7 @@ def run_gpu(args, rank, world):
     in_bytes = sum(int(m.row_ptr.nbytes + m.cols.nbytes + m.row_cf.nbytes + m.cf_ptr.nbytes + m.cf.nbytes) for m in mats)
 
     KEYS_V = ("ms_prep", "ms_reduce", "ms_echelon", "ms_d2h", "kernel_launches", "bytes_d2h", "ms_hot_kernel",
-              "hot_kernel_launches", "units", "dense_macs")
+              "hot_kernel_launches", "units", "dense_macs", "ms_schur", "schur_macs")
 
     def pass_resident():
         agg = dict.fromkeys(KEYS_V, 0.0)
@@ -400,6 +400,10 @@ def run_gpu(args, rank, world):
     ms_hot = sum(a["ms_hot_kernel"] for a in aggs_v) / steps
     n_hot = sum(a["hot_kernel_launches"] for a in aggs_v) / steps
     dense_macs = sum(a["dense_macs"] for a in aggs_v) / steps
+    ms_schur = sum(a["ms_schur"] for a in aggs_v) / steps
+    schur_macs = sum(a["schur_macs"] for a in aggs_v) / steps
+    ms_flow = ms_hot - ms_schur
+    flow_macs = dense_macs - schur_macs
     known_units = sum(a["units"] for a in aggs_v) / steps
     peak, peak_src = measured_peaks()
     bpu = BYTES_PER_UNIT[cf_bytes]
@@ -412,14 +416,19 @@ def run_gpu(args, rank, world):
     one_shot = None
     if world == 1 and not args.no_cold:
         try:
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_f4_gpu.py"), args.workload, "--prime",
-                                  str(args.prime), "--threads", str(host_threads)], capture_output=True, text=True, timeout=900,
-                                 env=dict(os.environ, F4LA_B200_DEVICE=str(local)))
-            row = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-            one_shot = {"what": "fresh process (no torch), one F4 run with all LA pointers on the GPU: tools/run_f4_gpu.py",
+            runs = []
+            for _ in range(2):       # two fresh processes: the first one on a box also pays for paging the libraries in
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_f4_gpu.py"), args.workload, "--prime",
+                                      str(args.prime), "--threads", str(host_threads)], capture_output=True, text=True,
+                                     timeout=900, env=dict(os.environ, F4LA_B200_DEVICE=str(local)))
+                runs.append(json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1]))
+            row = min(runs, key=lambda r: r["la_seconds_gpu"])
+            one_shot = {"what": "fresh process (no torch), one F4 run with all LA pointers on the GPU: tools/run_f4_gpu.py; "
+                                "two such processes, the faster one reported, both listed",
                         "f4_seconds": row["f4_seconds_gpu_la"], "la_seconds": row["la_seconds_gpu"],
+                        "la_seconds_all_runs": [r["la_seconds_gpu"] for r in runs],
                         "la_breakdown_ms": row["device_ms"], "bit_exact_vs_reference": row["bit_exact_vs_reference"]}
-            log(f"[bench] one-shot process: F4 {row['f4_seconds_gpu_la']} s, LA {row['la_seconds_gpu']} s")
+            log(f"[bench] one-shot process: F4 {row['f4_seconds_gpu_la']} s, LA {[r['la_seconds_gpu'] for r in runs]} s")
         except Exception as e:
             one_shot = {"error": repr(e)}
 
@@ -432,20 +441,39 @@ def run_gpu(args, rank, world):
         # pipe, not HBM; `achieved / peak / frac` keep the contract's definition on the survey's yardstick
         # (reference units x algorithmic bytes / kernel time vs the measured HBM copy peak) and can exceed 1
         # because the restructured kernel keeps the vectors in L2 and moves far fewer DRAM bytes
-        "bound": "l2+imad", "kernel": "k_pull_flow", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "l2+imad", "kernel": "k_pull_flow (+ k_schur_gemm for the columns without pivot)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "frac_survey_yardstick": achieved / peak,
-        "traffic": 2.36e10 if args.workload == "katsura-12" else None,
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (largest matrix), "
-                          "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv; algorithmic bytes of that launch 3.2e11",
-        "binding": {"pipe": "IMAD.WIDE issue (fmaheavy pipe)", "peak_mac_per_s": mac_peak,
-                    "peak_source": "f4la_b200_measure_mac_peak(): 96-bit multiply-accumulate with register operands, "
-                                   "measured in this run on this GPU",
-                    "dense_macs_per_step": dense_macs, "achieved_mac_per_s": dense_macs / (ms_hot / 1e3) if ms_hot else None,
-                    "frac_nominal": dense_macs / (ms_hot / 1e3) / mac_peak if ms_hot and mac_peak else None,
-                    "note": "dense_macs counts every (pull-list entry, lower row) pair, the all-zero source vectors the "
-                            "kernel skips included: the executed fraction is lower",
-                    "l2": {"ncu_bytes_per_launch": 2.30e11, "ncu_TB_per_s": 14.3,
-                           "source": "profiles/r01_ncu_full_k_pull_flow_v5_raw.csv (lts__t_sectors_srcunit_tex_op_read)"}},
+        "traffic": 1.16e10 if args.workload == "katsura-12" else None,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant k_pull_flow launch (largest matrix, "
+                          "16 of its 20 row chunks), profiles/r02_ncu_full_k_pull_flow_k_schur_gemm_raw.csv: 10.6 GB + 0.97 GB "
+                          "(the k_schur_gemm launch that follows it: 13.8 GB + 0.40 GB); algorithmic bytes of that launch 3.2e11",
+        "binding": {
+            "what": "the reduction by the known pivots runs on two pipes: the dataflow solve of the pivot columns on the "
+                    "multiplier pipe (IMAD.WIDE), the product for the columns without pivot on the tensor pipe "
+                    "(tcgen05.mma.kind::i8, 16 int8 products per residue product, non-zero 64x64 tiles only)",
+            "pivot_columns": {
+                "kernel": "k_pull_flow", "ms_per_step": ms_flow, "nominal_macs_per_step": flow_macs,
+                "peak_mac_per_s": mac_peak,
+                "peak_source": "f4la_b200_measure_mac_peak(): the kernel's 96-bit multiply-accumulate with register "
+                               "operands, measured in this run on this GPU",
+                "achieved_mac_per_s": flow_macs / (ms_flow / 1e3) if ms_flow > 0 else None,
+                "frac_nominal": flow_macs / (ms_flow / 1e3) / mac_peak if ms_flow > 0 and mac_peak else None,
+                "note": "nominal = every (pull-list entry, lower row) pair, the all-zero source vectors the kernel skips "
+                        "included: the executed fraction is lower; ncu: issue slots 49 %, L2 40 %, warps active 50 %",
+            },
+            "other_columns": {
+                "kernel": "k_schur_a_split + k_schur_gemm + k_schur_combine", "ms_per_step": ms_schur,
+                "nominal_macs_per_step": schur_macs,
+                "achieved_residue_mac_per_s": schur_macs / (ms_schur / 1e3) if ms_schur > 0 else None,
+                "tensor_pipe_active_ncu": [0.659, 0.718],
+                "source": "profiles/r02_ncu_full_k_pull_flow_k_schur_gemm_raw.csv "
+                          "(sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the two launches of the "
+                          "largest matrix)",
+            } if ms_schur > 0 else None,
+            "l2": {"ncu_bytes_per_launch": 5.69e10, "ncu_TB_per_s": 9.1,
+                   "source": "profiles/r02_ncu_full_k_pull_flow_k_schur_gemm_raw.csv "
+                             "(lts__t_sectors_srcunit_tex_op_read of the dominant k_pull_flow launch, 6.27 ms)"}},
         "peak_source": peak_src, "bytes_per_unit": bpu, "launches_per_step": n_hot, "kernel_ms_per_step": ms_hot,
         "algorithmic_bytes_per_launch": units * bpu / max(n_hot, 1), "ms_per_launch": ms_hot / max(n_hot, 1),
         "reference_units_known_pivots_counted_on_device": known_units,

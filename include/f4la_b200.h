@@ -144,6 +144,10 @@ typedef struct f4la_stats {
                                  all-zero source vectors included (the hot kernel skips those)             */
     uint64_t ref_applications;/* (known pivot, lower row) pairs with a non-zero multiplier: the reference's
                                  application_nr_red for the reduction by the known pivots                 */
+    double   ms_schur;        /* part of ms_hot_kernel spent in the tensor-core product for the columns without
+                                 pivot (k_schur_a_split + k_schur_gemm + k_schur_combine); 0 when they are
+                                 solved by the dataflow kernel                                              */
+    uint64_t schur_macs;      /* part of dense_macs computed by that product                                */
 } f4la_stats;
 
 typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */

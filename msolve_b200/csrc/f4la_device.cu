@@ -42,7 +42,7 @@ double now_ms()
 
 } // namespace
 
-constexpr int kMaxFlowEvents = 512;
+constexpr int kMaxFlowEvents = 510;                /* 3 per launch group: before / after the dataflow kernel / after the Schur product */
 constexpr int kRingSlots = 4;
 constexpr size_t kRingPieceBytes = (size_t)16 << 20;
 
@@ -935,8 +935,10 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         f.piv_row_ptr = (!by_lead && !combos && !getenv("F4LA_B200_NOUNITS")) ? m->row_ptr : nullptr;
         f.ref_units = d_ref;
         if (!ncl) CU(cudaMemsetAsync(d_err + 4, 0, 4, s));      /* else: zeroed by k_flow_reset_flags */
-        if (st && n_flow_ev + 2 <= kMaxFlowEvents) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
+        const bool ev_ok = st && n_flow_ev + 3 <= kMaxFlowEvents;
+        if (ev_ok) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev], s));
         launch_flow(ctx, T, f, wide);
+        if (ev_ok) CU(cudaEventRecord(ctx->flow_ev[n_flow_ev + 1], s));
         if (schur) {
             SchurArgs sa;
             memset(&sa, 0, sizeof(sa));
@@ -984,7 +986,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             note_launch(ctx, 3, __LINE__);
         }
         /* "hot kernel" time = the reduction by the known pivots: dataflow solve + (when used) the tensor-core Schur product */
-        if (st && n_flow_ev + 2 <= kMaxFlowEvents) { CU(cudaEventRecord(ctx->flow_ev[n_flow_ev + 1], s)); n_flow_ev += 2; }
+        if (ev_ok) { CU(cudaEventRecord(ctx->flow_ev[n_flow_ev + 2], s)); n_flow_ev += 3; }
         if (want_rba && rba_words) {
             dim3 grid(rba_words, g * (Rc / 128));
             k_rba_bits<<<grid, 128, 0, s>>>(as<uint32_t>(ctx->V), nc, Rc, ncl, c0, nrl, rba_words,
@@ -1190,11 +1192,14 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_reduce = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st->ms_echelon = ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_d2h = ms;
-        for (int k = 0; k < n_flow_ev; k += 2) {
-            cudaEventElapsedTime(&ms, ctx->flow_ev[k], ctx->flow_ev[k + 1]);
+        for (int k = 0; k < n_flow_ev; k += 3) {
+            cudaEventElapsedTime(&ms, ctx->flow_ev[k], ctx->flow_ev[k + 2]);
             st->ms_hot_kernel += ms;
+            cudaEventElapsedTime(&ms, ctx->flow_ev[k + 1], ctx->flow_ev[k + 2]);
+            if (schur) st->ms_schur += ms;
         }
-        st->hot_kernel_launches = (uint32_t)(n_flow_ev / 2);
+        st->hot_kernel_launches = (uint32_t)(n_flow_ev / 3);
+        st->schur_macs = schur ? (uint64_t)nnz_schur * nrl : 0;
         st->units = ref_units;
         st->ref_applications = ref_apps;
         st->dense_macs = (uint64_t)nnz_pull * nrl;

@@ -53,6 +53,7 @@ class CStats(C.Structure):
         ("kernel_launches", C.c_uint32), ("rank", C.c_uint32),
         ("ms_hot_kernel", C.c_double), ("hot_kernel_launches", C.c_uint32), ("echelon_path", C.c_uint32),
         ("dense_macs", C.c_uint64), ("ref_applications", C.c_uint64),
+        ("ms_schur", C.c_double), ("schur_macs", C.c_uint64),
     ]
 
     def as_dict(self):
