@@ -153,6 +153,26 @@ typedef struct f4la_stats {
 typedef struct f4la_ctx f4la_ctx;           /* one per host thread / stream   */
 typedef struct f4la_resident f4la_resident; /* a matrix already in HBM        */
 
+/* One recorded call of a device-resident replay (f4la_b200_replay_call): everything the call needs is on the device.
+ * All pointers are DEVICE pointers (f4la_b200_device_alloc).  "arena" holds the coefficient arrays of the basis
+ * elements of the prime being replayed; the call gathers its coefficient pool from it, runs the pipeline on the
+ * resident structure WITHOUT any host round trip, and writes the coefficients of the result rows back into the arena
+ * at the recorded support.  A rank or support other than the recorded one, or a device error, sets bits in *status
+ * (1 rank, 2 support, 4 device error with the error bits << 8). */
+typedef struct f4la_replay_call {
+    uint32_t        expect_rows;   /* rows of the recorded result (new pivots; all lower rows for pivot-by-lead)   */
+    uint32_t        nslots;        /* coefficient arrays of the matrix                                            */
+    const uint64_t *gather_src;    /* [nslots] arena offset of the array (words)                                  */
+    const uint64_t *gather_dst;    /* [nslots] offset in the coefficient pool of the resident matrix (= cf_ptr)    */
+    const uint32_t *gather_len;    /* [nslots]                                                                    */
+    const uint64_t *row_ptr;       /* [expect_rows + 1] recorded support                                          */
+    const uint32_t *idx;           /* per recorded entry: column of the dense result row (global column - ncl_effective,
+                                      through the column map for pivot-by-lead); 0xffffffff = lead term, value 1   */
+    const uint64_t *row_dst;       /* [expect_rows] arena offset that receives row i's coefficients                */
+    uint32_t       *arena;
+    uint32_t       *status;
+} f4la_replay_call;
+
 /* Library / device management. */
 const char *f4la_b200_version(void);
 int  f4la_b200_device_count(void);
@@ -170,6 +190,10 @@ void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed);
  * `blocking_sync` != 0 makes every wait for the device sleep on a blocking event instead of spinning in the driver, so
  * that more host threads than cores can each drive a context. */
 void f4la_b200_set_host_mode(f4la_ctx *ctx, int host_threads, int blocking_sync);
+/* Upper bound on the CTAs of this context's persistent dataflow kernel (0 = fill the device, the default).  When many
+ * contexts share one GPU (one per host thread in the multi-modular loop) each of their small latency-bound launches
+ * would otherwise occupy every SM and serialise the others; 64 measured best for 16-32 contexts. */
+void f4la_b200_set_grid_cap(f4la_ctx *ctx, uint32_t ctas);
 
 /* Page-locked host memory for the flat arrays handed to f4la_b200_reduce():
  * host->device copies from such buffers run at full PCIe rate and
@@ -206,6 +230,19 @@ int f4la_b200_stage_commit(f4la_ctx *ctx, int which, uint32_t elem_bytes, uint64
 f4la_resident *f4la_b200_upload(f4la_ctx *ctx, const f4la_flat_matrix *in);
 int  f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m,
                                f4la_flat_result *out, f4la_stats *stats);
+
+/* Device-resident replay (used by the tape of f4la_b200_neogb.h; see f4la_replay_call above).
+ * f4la_b200_replay_call needs a resident matrix that went through f4la_b200_resident_update and ONE ordinary
+ * f4la_b200_reduce_resident (which fills its layout cache); it only enqueues work on the context's stream.
+ * f4la_b200_device_copy: host<->device copy on that stream (to_device != 0: host -> device), waits for the stream when
+ * `wait` != 0.  f4la_b200_resident_layout: the column map the pipeline uses for this matrix (identity unless
+ * F4LA_FLAG_PIVOT_BY_LEAD) and the effective number of pivot columns. */
+void *f4la_b200_device_alloc(f4la_ctx *ctx, size_t bytes);
+void  f4la_b200_device_free(f4la_ctx *ctx, void *p);
+int   f4la_b200_device_copy(f4la_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device, int wait);
+int   f4la_b200_device_zero(f4la_ctx *ctx, void *dst, size_t bytes);
+int   f4la_b200_resident_layout(f4la_ctx *ctx, const f4la_resident *m, uint32_t *colmap, uint32_t *ncl_effective);
+int   f4la_b200_replay_call(f4la_ctx *ctx, f4la_resident *m, uint32_t fc, const f4la_replay_call *rc);
 void f4la_b200_release(f4la_ctx *ctx, f4la_resident *m);
 /* A resident matrix with the same structure but other coefficients (and another prime): overwrites the coefficient
  * pool from host memory (same layout and size as at upload time) and sets the field characteristic.  This is how

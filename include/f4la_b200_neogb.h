@@ -129,6 +129,20 @@ uint64_t f4la_b200_tape_residue_words(const f4la_tape *tape);
 int f4la_b200_tape_replay(const f4la_tape *tape, void *ctx, uint32_t p, const uint32_t *init_cf,
                           const uint64_t *init_off, uint32_t *residues, double *la_ms);
 
+/* The same replay WITHOUT host round trips: the coefficient arrays of all basis elements of the prime stay on the
+ * device (an arena per context), every recorded call gathers its coefficient pool from there, runs the pipeline on the
+ * resident structure with the recorded rank and support as expectation, and writes its result rows back into the
+ * arena; one device->host copy of the residues at the end.  _enqueue only queues work on the context's stream (up to
+ * 16 primes per context between two _collect calls) -- `residues` must stay valid until _collect, which waits for the
+ * stream and returns, in enqueue order, F4LA_OK / F4LA_ERR_BADPRIME (another rank) / F4LA_ERR_PATTERN (another
+ * support) / F4LA_ERR_CUDA per prime (return value: number of results, -1 on bad arguments).  The first replay on a
+ * context, and every replay of a tape that cannot be expressed this way (blocks that need compress-and-verify,
+ * 8/16-bit coefficients), run through f4la_b200_tape_replay inside _enqueue; F4LA_B200_TAPE_ASYNC=0 forces that.
+ * Page-locked `residues` (f4la_b200_pinned_alloc) keep the final copy asynchronous. */
+int f4la_b200_tape_replay_enqueue(const f4la_tape *tape, void *ctx, uint32_t p, const uint32_t *init_cf,
+                                  const uint64_t *init_off, uint32_t *residues);
+int f4la_b200_tape_replay_collect(const f4la_tape *tape, void *ctx, int *rcs, int max_rcs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libf4la_b200.so")
 EXPORTED_SYMBOLS = [
     # include/f4la_b200.h
     "f4la_b200_version", "f4la_b200_device_count", "f4la_b200_create", "f4la_b200_destroy",
-    "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_set_host_mode", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
+    "f4la_b200_last_error", "f4la_b200_set_seed", "f4la_b200_set_host_mode", "f4la_b200_set_grid_cap", "f4la_b200_device_alloc", "f4la_b200_device_free", "f4la_b200_device_copy", "f4la_b200_device_zero", "f4la_b200_resident_layout", "f4la_b200_replay_call", "f4la_b200_pinned_alloc", "f4la_b200_pinned_free",
     "f4la_b200_reduce", "f4la_b200_stage_cols", "f4la_b200_stage_acquire", "f4la_b200_stage_commit", "f4la_b200_upload", "f4la_b200_reduce_resident", "f4la_b200_release", "f4la_b200_resident_update",
     "f4la_b200_free_result", "f4la_b200_measure_mac_peak", "f4la_b200_modp_gemm",
     # include/f4la_b200_neogb.h
@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "f4la_b200_interreduce_matrix_rows", "f4la_b200_neogb_set_free_basis_elements", "f4la_b200_neogb_get_totals",
     "f4la_b200_neogb_tape_begin", "f4la_b200_neogb_tape_end", "f4la_b200_tape_free", "f4la_b200_tape_calls",
     "f4la_b200_tape_initial_elements", "f4la_b200_tape_initial_length", "f4la_b200_tape_residue_words",
-    "f4la_b200_tape_replay",
+    "f4la_b200_tape_replay", "f4la_b200_tape_replay_enqueue", "f4la_b200_tape_replay_collect",
 ]
 
 
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
     L.f4la_b200_last_error.argtypes = [C.c_void_p]
     L.f4la_b200_set_seed.argtypes = [C.c_void_p, C.c_uint64]
     L.f4la_b200_set_host_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.f4la_b200_set_grid_cap.argtypes = [C.c_void_p, C.c_uint32]
     L.f4la_b200_pinned_alloc.restype = C.c_void_p
     L.f4la_b200_pinned_alloc.argtypes = [C.c_size_t]
     L.f4la_b200_pinned_free.argtypes = [C.c_void_p]
@@ -143,6 +144,9 @@ class Backend:
 
     def set_host_mode(self, host_threads: int, blocking_sync: bool) -> None:
         self.lib.f4la_b200_set_host_mode(self.ctx, host_threads, 1 if blocking_sync else 0)
+
+    def set_grid_cap(self, ctas: int) -> None:
+        self.lib.f4la_b200_set_grid_cap(self.ctx, ctas)
 
     def set_seed(self, seed: int) -> None:
         self.lib.f4la_b200_set_seed(self.ctx, seed)
@@ -257,6 +261,10 @@ class Tape:
         lib.f4la_b200_tape_replay.restype = C.c_int
         lib.f4la_b200_tape_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.POINTER(C.c_double)]
+        lib.f4la_b200_tape_replay_enqueue.restype = C.c_int
+        lib.f4la_b200_tape_replay_enqueue.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.f4la_b200_tape_replay_collect.restype = C.c_int
+        lib.f4la_b200_tape_replay_collect.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int]
         lib.f4la_b200_tape_free.argtypes = [C.c_void_p]
         self.calls = int(lib.f4la_b200_tape_calls(handle))
         self.initial_elements = int(lib.f4la_b200_tape_initial_elements(handle))
@@ -284,6 +292,27 @@ class Tape:
         rc = self.lib.f4la_b200_tape_replay(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data,
                                             out.ctypes.data, C.byref(ms))
         return int(rc), out, ms.value
+
+    MAX_INFLIGHT = 16
+
+    def enqueue(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray, out: np.ndarray) -> None:
+        """Device-resident replay: queues the prime on the backend's stream; `out` (C-contiguous uint32 row, page-locked
+        for a truly asynchronous copy) receives the residues and must stay alive until collect()."""
+        assert init_cf.dtype == np.uint32 and init_cf.flags.c_contiguous
+        assert init_off.dtype == np.uint64 and init_off.flags.c_contiguous
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= self.residue_words
+        rc = self.lib.f4la_b200_tape_replay_enqueue(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data,
+                                                    out.ctypes.data)
+        if rc != 0:
+            raise F4LAError(f"f4la_b200_tape_replay_enqueue: error {rc}")
+
+    def collect(self, be: Backend):
+        """Waits for the backend's stream; return codes of the primes enqueued since the last collect, in order."""
+        rcs = (C.c_int * 64)()
+        n = self.lib.f4la_b200_tape_replay_collect(self.handle, be.ctx, rcs, 64)
+        if n < 0:
+            raise F4LAError("f4la_b200_tape_replay_collect failed")
+        return [int(rcs[i]) for i in range(n)]
 
     def free(self) -> None:
         if self.handle:

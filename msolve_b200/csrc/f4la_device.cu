@@ -326,7 +326,7 @@ int launch_tc_gemm(f4la_ctx *ctx, TcGemmArgs g)
  * inverses are left in ctx->pivcol / pivrow / pivinv, the block holds the reduced rows unnormalised
  * (k_ge_extract scales them). */
 int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_t ncr, uint32_t p, uint64_t pinv,
-                 uint32_t *rank_out)
+                 uint32_t *rank_out, const uint32_t *expect_rank = nullptr)
 {
     cudaStream_t s = ctx->stream;
     const uint32_t maxrank = nrl < ncr ? nrl : ncr;
@@ -359,6 +359,8 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         if (pw > kPanelMax) pw = kPanelMax;
         if (ctx->ge_panel && pw > ctx->ge_panel) pw = ctx->ge_panel;
     }
+    if (expect_rank && !(pw >= 2 && ctx->ge_mode == 0 && ctx->coop_ok))
+        return fail(ctx, F4LA_ERR_ARG, "a replay without host round trips needs the persistent Gauss-Jordan kernel");
     if (pw >= 2 && ctx->ge_mode == 0 && ctx->coop_ok) {
         const size_t dyn = (size_t)pw * nrows4 * 4 + nrows4;
         if (dyn > ctx->fused_smem_optin) {
@@ -384,6 +386,10 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
         CU(cudaLaunchCooperativeKernel((const void *)k_ge_fused, dim3(grid), dim3(kFusedThreads), kargs, dyn, s));
         if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[1], s));
         note_launch(ctx, 1, __LINE__);
+        if (expect_rank) {          /* replay: no read-back; the state stays on the device for k_replay_compact */
+            *rank_out = *expect_rank;
+            return F4LA_OK;
+        }
         CU(cudaMemcpyAsync(h_state, ctx->gestate.p, sizeof(GEState), cudaMemcpyDeviceToHost, s));
         CU(cudaGetLastError());
         OK(stream_sync(ctx));
@@ -551,7 +557,7 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
             dim3 grid(rank, (ncr + 255) / 256);
             k_ge_extract<<<grid, 256, 0, s>>>(D2, kc, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
-                                              as<uint32_t>(ctx->dense_out), p, pinv);
+                                              as<uint32_t>(ctx->dense_out), p, pinv, nullptr);
             note_launch(ctx, 1, __LINE__);
         }
         uint32_t *d_bad = as<uint32_t>(ctx->flags32) + 8;
@@ -591,7 +597,8 @@ int compress_and_verify(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, 
 }
 
 /* The whole pipeline on a device-resident matrix. */
-int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f4la_stats *st)
+int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f4la_stats *st,
+                 const f4la_replay_call *ax = nullptr)
 {
     const f4la_flat_matrix &d = m->dims;
     const uint32_t nru = d.nru, nrl_in = d.nrl, p = d.fc;
@@ -628,6 +635,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         return fail(ctx, F4LA_ERR_ARG, "pivots keyed by row index need nru == ncl (got %u, %u)", nru, d.ncl);
     if (m->nnz >= 0xfffffff0ull)
         return fail(ctx, F4LA_ERR_ARG, "matrix too large: %llu non-zeros", (unsigned long long)m->nnz);
+    if (ax && (nrl == 0 || ncr == 0))
+        return fail(ctx, F4LA_ERR_ARG, "f4la_b200_replay_call: degenerate matrix (no lower rows or no column without pivot)");
     if (nrl == 0 || (ncr == 0 && !by_lead && !nf_mode)) { empty_result(out, d.cf_bytes); return F4LA_OK; }
     if (ncr == 0 && !by_lead) {           /* every lower row reduces to zero */
         empty_result(out, d.cf_bytes);
@@ -651,6 +660,9 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     const uint32_t *colmap = nullptr;
     PrepCache *pc = m->cache_enabled ? &m->cache : nullptr;
     const bool cached = pc && pc->valid;
+    if (ax && (!cached || want_rba || nf_mode || (d.flags & F4LA_FLAG_PROBABILISTIC) || d.cf_bytes != 4))
+        return fail(ctx, F4LA_ERR_ARG, "f4la_b200_replay_call needs a resident matrix with a filled layout cache (one ordinary "
+                    "run after f4la_b200_resident_update), 32-bit coefficients, and no trace / normal-form / probabilistic flag");
     uint32_t nnz_pull = 0, nnz_schur = 0, nlev = 0;
     uint32_t *d_col_ptr = nullptr, *d_invmap = nullptr, *d_sched = nullptr, *d_items = nullptr;
     uint2 *d_ent = nullptr;
@@ -1002,6 +1014,8 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     rank = 0;
     if (!nf_mode && !by_lead) {
         bool compressed = false;
+        if (ax && ctx->ge_compress && nrl >= 2 * ctx->compress_rows)
+            return fail(ctx, F4LA_ERR_ARG, "a replay without host round trips does not cover compress-and-verify blocks");
         if (!want_rba && !combos && ctx->ge_compress && nrl >= 2 * ctx->compress_rows) {
             const uint64_t rej0 = ctx->compress_rejected, esc0 = ctx->compress_escalated;
             int rc = compress_and_verify(ctx, Dm, ld, nrl, ncr, p, pinv, &rank, &compressed);
@@ -1021,13 +1035,38 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
                 }
         }
         if (compressed) { Dm = as<uint32_t>(ctx->D2); ge_ld = ctx->d2_ld; }
-        else OK(gauss_jordan(ctx, Dm, ld, nrl, ncr, p, pinv, &rank));
+        else OK(gauss_jordan(ctx, Dm, ld, nrl, ncr, p, pinv, &rank, ax ? &ax->expect_rows : nullptr));
     }
     /* probabilistic mode: accept when the rank stays clear of the number of combinations */
     if (!combos || rank + kProbSlack <= nvr) break;
     nvr = (uint64_t)nvr * 4 >= nrl_in / 2 ? nrl_in : nvr * 4;
     }   /* attempts */
     uint64_t ref_units = 0, ref_apps = 0;
+    if (ax) {
+        /* ---- 5'. replay: dense rows stay on the device, coefficients go to the arena at the recorded support ---- */
+        const uint32_t nrows_x = ax->expect_rows;
+        if (by_lead && nrows_x != nrl)
+            return fail(ctx, F4LA_ERR_ARG, "replay: %u rows expected, the matrix has %u lower rows", nrows_x, nrl);
+        OK(ensure(ctx, ctx->dense_out, (size_t)(nrows_x ? nrows_x : 1) * (ncr ? ncr : 1) * 4 + 16));
+        if (by_lead && ncr && nrows_x) {
+            dim3 grid((ncr + 31) / 32, (nrl + 31) / 32), block(32, 8);
+            k_transpose_rows<<<grid, block, 0, s>>>(Dm, ld, ncr, nrl, p, as<uint32_t>(ctx->dense_out));
+            note_launch(ctx, 1, __LINE__);
+        } else if (!by_lead && nrows_x) {
+            dim3 grid(nrows_x, (ncr + 255) / 256);
+            k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, nrows_x, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
+                                              as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
+                                              as<uint32_t>(ctx->dense_out), p, pinv, as<GEState>(ctx->gestate));
+            note_launch(ctx, 1, __LINE__);
+        }
+        unsigned blocks = (nrows_x + 7) / 8;
+        if (blocks < 1) blocks = 1;
+        k_replay_compact<<<blocks, 256, 0, s>>>(as<uint32_t>(ctx->dense_out), ncr, nrows_x, ax->row_ptr, ax->idx, ax->row_dst,
+                                                ax->arena, by_lead ? nullptr : as<GEState>(ctx->gestate), d_err, ax->status);
+        note_launch(ctx, 1, __LINE__);
+        CU(cudaGetLastError());
+        return F4LA_OK;
+    }
     {
         uint32_t *h_err = (uint32_t *)ctx->h_small.p + 64;
         uint64_t *h_ref = (uint64_t *)(h_err + 16);
@@ -1066,7 +1105,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
             dim3 grid(rank, (ncr + 255) / 256);
             k_ge_extract<<<grid, 256, 0, s>>>(Dm, ge_ld, ncr, rank, as<uint32_t>(ctx->pivcol), as<uint32_t>(ctx->pivrow),
                                               as<uint32_t>(ctx->pivinv), as<uint8_t>(ctx->ispiv),
-                                              dense_dst, p, pinv);
+                                              dense_dst, p, pinv, nullptr);
             note_launch(ctx, 1, __LINE__);
         }
         if (ctx->debug) CU(cudaEventRecord(ctx->dbg_ev[0], s));
@@ -1412,6 +1451,8 @@ void f4la_b200_set_host_mode(f4la_ctx *ctx, int host_threads, int blocking_sync)
     ctx->blocking_sync = blocking_sync != 0;
 }
 
+void f4la_b200_set_grid_cap(f4la_ctx *ctx, uint32_t ctas) { if (ctx) ctx->grid_cap = ctas; }
+
 void f4la_b200_set_seed(f4la_ctx *ctx, uint64_t seed) { if (ctx) ctx->seed = seed ? seed : 0x9e3779b97f4a7c15ull; }
 
 void *f4la_b200_pinned_alloc(size_t bytes)
@@ -1460,6 +1501,71 @@ int f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m, f4la_flat_result 
     int rc = run_pipeline(ctx, m, out, stats);
     if (stats) stats->ms_total = now_ms() - t0;
     return rc;
+}
+
+/* ---- device-resident replay (the tape of f4la_neogb.cpp drives these) ---- */
+void *f4la_b200_device_alloc(f4la_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void f4la_b200_device_free(f4la_ctx *ctx, void *p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFree(p);
+}
+
+int f4la_b200_device_copy(f4la_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device, int wait)
+{
+    if (!ctx || (!dst && bytes) || (!src && bytes)) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (wait) OK(stream_sync(ctx));
+    return F4LA_OK;
+}
+
+int f4la_b200_device_zero(f4la_ctx *ctx, void *dst, size_t bytes)
+{
+    if (!ctx || !dst) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+    return F4LA_OK;
+}
+
+int f4la_b200_resident_layout(f4la_ctx *ctx, const f4la_resident *m, uint32_t *colmap, uint32_t *ncl_effective)
+{
+    if (!ctx || !m) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const f4la_flat_matrix &d = m->dims;
+    const bool by_lead = (d.flags & F4LA_FLAG_PIVOT_BY_LEAD) != 0;
+    if (ncl_effective) *ncl_effective = by_lead ? d.nru + d.nrl : d.ncl;
+    if (colmap) {
+        const uint32_t nc = d.ncl + d.ncr;
+        if (!by_lead) { for (uint32_t c = 0; c < nc; ++c) colmap[c] = c; return F4LA_OK; }
+        if (!m->cache.valid || !m->cache.colmap) return fail(ctx, F4LA_ERR_ARG, "the layout cache of this matrix is empty");
+        CU(cudaMemcpyAsync(colmap, m->cache.colmap, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        OK(stream_sync(ctx));
+    }
+    return F4LA_OK;
+}
+
+int f4la_b200_replay_call(f4la_ctx *ctx, f4la_resident *m, uint32_t fc, const f4la_replay_call *rc)
+{
+    if (!ctx || !m || !rc || !rc->arena || !rc->status) return F4LA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    m->dims.fc = fc;
+    if (rc->nslots) {
+        unsigned blocks = (rc->nslots + 7) / 8;
+        if (blocks > 1024) blocks = 1024;
+        k_replay_gather<<<blocks, 256, 0, ctx->stream>>>(rc->arena, reinterpret_cast<uint32_t *>(m->cf), rc->gather_src,
+                                                        rc->gather_dst, rc->gather_len, rc->nslots);
+        note_launch(ctx, 1, __LINE__);
+    }
+    return run_pipeline(ctx, m, nullptr, nullptr, rc);
 }
 
 int f4la_b200_stage_cols(f4la_ctx *ctx, const uint32_t *cols, uint64_t first, uint64_t count, uint64_t total_nnz)

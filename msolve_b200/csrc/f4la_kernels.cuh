@@ -1411,11 +1411,15 @@ k_ge_verify(const uint32_t *__restrict__ D, uint64_t ld, uint32_t nrows_pad, uin
 __global__ void k_ge_extract(const uint32_t *__restrict__ D, uint64_t ld, uint32_t ncr, uint32_t rank,
                              const uint32_t *__restrict__ pivcol, const uint32_t *__restrict__ pivrow,
                              const uint32_t *__restrict__ pivinv, const uint8_t *__restrict__ ispiv,
-                             uint32_t *__restrict__ out, uint32_t p, uint64_t pinv)
+                             uint32_t *__restrict__ out, uint32_t p, uint64_t pinv,
+                             const GEState *__restrict__ expect_state)
 {
     const uint32_t t = blockIdx.x;                     /* rank can exceed the 65535 limit of grid.y */
     const uint32_t c = blockIdx.y * blockDim.x + threadIdx.x;
     if (t >= rank || c >= ncr) return;
+    /* replay without a host round trip: `rank` is the EXPECTED rank; if the elimination found another one the pivot
+     * arrays do not describe `rank` pivots -- write nothing (k_replay_compact reports the mismatch) */
+    if (expect_state && expect_state->rank != rank) return;
     const uint32_t k = rank - 1 - t;
     const uint32_t ck = pivcol[k];
     uint32_t v;
@@ -1796,6 +1800,66 @@ k_ge_fused(const GeFusedArgs A)
         if (t0) { A.st->t[5] += tc - tb; A.st->t[6] += (tb - ta) + (clock64() - tc); }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.err, kErrGeBarrier);       /* did not terminate */
+}
+
+/* ====================================================================================================== */
+/* Device-resident replay of a recorded call (f4la_b200_replay_call): no host round trip                    */
+/* ====================================================================================================== */
+constexpr uint32_t kReplayLead = 0xffffffffu;
+constexpr uint32_t kReplayBadRank = 1u, kReplayBadSupport = 2u, kReplayDeviceError = 4u;
+
+/* coefficient pool of the call <- coefficient arrays of the basis elements (arena); one warp per slot */
+__global__ void k_replay_gather(const uint32_t *__restrict__ arena, uint32_t *__restrict__ pool,
+                                const uint64_t *__restrict__ src, const uint64_t *__restrict__ dst,
+                                const uint32_t *__restrict__ len, uint32_t nslots)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t sl = warp; sl < nslots; sl += nwarps) {
+        const uint32_t *a = arena + src[sl];
+        uint32_t *b = pool + dst[sl];
+        const uint32_t n = len[sl];
+        for (uint32_t i = lane; i < n; i += 32) b[i] = a[i];
+    }
+}
+
+/* Dense result rows -> coefficient arrays of the new basis elements, at the RECORDED support: row i has entries at
+ * the dense columns idx[row_ptr[i] .. row_ptr[i+1]) (kReplayLead = the lead term of a pivot-by-lead row, value 1).
+ * The support is the recorded one iff the row has exactly that many non-zeros and all of them sit at recorded
+ * positions; a different rank, another support or a device error is reported in *status (the prime then takes the
+ * ordinary path on the host, like a bad prime of the reference, f4.c:433-441).  One warp per row. */
+__global__ void k_replay_compact(const uint32_t *__restrict__ dense, uint32_t ncr, uint32_t nrows,
+                                 const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ idx,
+                                 const uint64_t *__restrict__ row_dst, uint32_t *__restrict__ arena,
+                                 const GEState *__restrict__ st, const uint32_t *__restrict__ d_err,
+                                 uint32_t *__restrict__ status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool bad_rank = st && (st->rank != nrows || !st->done);
+    if (warp == 0 && lane == 0) {
+        if (bad_rank) atomicOr(status, kReplayBadRank);
+        if (*d_err) atomicOr(status, kReplayDeviceError | (*d_err << 8));
+    }
+    if (bad_rank) return;
+    for (uint32_t i = warp; i < nrows; i += nwarps) {
+        const uint32_t *row = dense + (size_t)i * ncr;
+        const uint64_t a = row_ptr[i], b = row_ptr[i + 1];
+        uint32_t cnt = 0;
+        for (uint32_t c = lane; c < ncr; c += 32) cnt += row[c] != 0;
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        uint32_t leads = 0, bad = 0;
+        uint32_t *out = arena + row_dst[i];
+        for (uint64_t t = a + lane; t < b; t += 32) {
+            const uint32_t c = idx[t];
+            uint32_t v = 1;
+            if (c == kReplayLead) ++leads; else v = row[c];
+            bad |= v == 0;
+            out[t - a] = v;
+        }
+        for (int o = 16; o; o >>= 1) { leads += __shfl_xor_sync(0xffffffffu, leads, o); bad |= __shfl_xor_sync(0xffffffffu, bad, o); }
+        if (lane == 0 && (bad || (uint64_t)cnt + leads != b - a)) atomicOr(status, kReplayBadSupport);
+    }
 }
 
 } /* namespace f4la */

@@ -56,7 +56,23 @@ struct f4la_tape {
     bool valid = true;
     /* per context: the structures resident in HBM (uploaded at the first replay on that context) */
     std::mutex mu;
-    struct PerCtx { std::vector<f4la_resident *> res; void *pool = nullptr; };   /* pool: pinned, largest call */
+    static constexpr int kInflight = 16;             /* replays enqueued per context before the host has to wait */
+    struct PerCtx {
+        std::vector<f4la_resident *> res;
+        void *pool = nullptr;                         /* pinned, largest call (host-assembled replay) */
+        /* device-resident replay (f4la_b200_tape_replay_enqueue): */
+        int async_state = 0;                          /* 0 not built, 1 ready, -1 not possible for this tape */
+        bool warmed = false;                          /* one host-assembled replay ran here: layout caches are filled */
+        std::vector<f4la_replay_call> plan;           /* one per recorded call, device pointers */
+        std::vector<void *> dev;                      /* everything allocated on the device for the plan */
+        std::vector<uint64_t> init_off;               /* layout of the initial elements the plan was built for */
+        uint32_t *arena = nullptr, *d_status = nullptr;
+        uint64_t arena_words = 0, residue_off = 0;
+        uint32_t *h_init = nullptr, *h_status = nullptr;   /* pinned: kInflight slots of initial coefficients / status words */
+        int inflight = 0;
+        std::vector<int> done_rc;                     /* results of replays that ran synchronously, in enqueue order ... */
+        std::vector<int> order;                       /* ... 1 = next result comes from done_rc, 0 = from an in-flight slot */
+    };
     std::map<void *, PerCtx> resident;
 };
 
@@ -667,6 +683,9 @@ void f4la_b200_tape_free(f4la_tape *tape)
     for (auto &kv : tape->resident) {
         for (f4la_resident *r : kv.second.res) f4la_b200_release(nullptr, r);
         if (kv.second.pool) f4la_b200_pinned_free(kv.second.pool);
+        for (void *d : kv.second.dev) f4la_b200_device_free(nullptr, d);
+        if (kv.second.h_init) f4la_b200_pinned_free(kv.second.h_init);
+        if (kv.second.h_status) f4la_b200_pinned_free(kv.second.h_status);
     }
     delete tape;
 }
@@ -781,6 +800,190 @@ int f4la_b200_tape_replay(const f4la_tape *ctape, void *vctx, uint32_t p, const 
     if (la_ms) *la_ms += now_ms() - t0;
     return F4LA_OK;
 }
+
+} /* extern "C" */
+
+namespace {
+
+template <typename V> const void *to_device(f4la_ctx *cx, f4la_tape::PerCtx &pc, const std::vector<V> &v)
+{
+    void *d = f4la_b200_device_alloc(cx, v.size() * sizeof(V) + 16);
+    if (!d) return nullptr;
+    pc.dev.push_back(d);
+    if (!v.empty() && f4la_b200_device_copy(cx, d, v.data(), v.size() * sizeof(V), 1, 1) != F4LA_OK) return nullptr;
+    return d;
+}
+
+/* Everything a replay needs, on the device: where every coefficient array of every call comes from in the arena of
+ * basis elements, the recorded support of every result row as dense-column indices, and where the rows go. */
+bool build_plan(f4la_tape *tape, f4la_tape::PerCtx &pc, f4la_ctx *cx, const uint64_t *init_off)
+{
+    std::vector<uint64_t> elem_off(tape->ninit), elem_len(tape->ninit);
+    for (uint32_t i = 0; i < tape->ninit; ++i) { elem_off[i] = init_off[i]; elem_len[i] = init_off[i + 1] - init_off[i]; }
+    uint64_t words = init_off[tape->ninit];
+    pc.init_off.assign(init_off, init_off + tape->ninit + 1);
+    pc.plan.clear();
+    for (size_t c = 0; c < tape->calls.size(); ++c) {
+        const TapeCall &tc = tape->calls[c];
+        if (tc.cf_bytes != 4) return false;
+        f4la_replay_call rc;
+        memset(&rc, 0, sizeof(rc));
+        const uint32_t nslots = (uint32_t)tc.slot_bindex.size();
+        std::vector<uint64_t> src(nslots), dst(nslots);
+        std::vector<uint32_t> len(nslots);
+        for (uint32_t sl = 0; sl < nslots; ++sl) {
+            const uint32_t e = tc.slot_bindex[sl];
+            const uint64_t l = tc.cf_ptr[sl + 1] - tc.cf_ptr[sl];
+            if (e >= elem_off.size() || elem_len[e] != l) return false;
+            src[sl] = elem_off[e]; dst[sl] = tc.cf_ptr[sl]; len[sl] = (uint32_t)l;
+        }
+        const uint32_t np = (uint32_t)tc.out_row_ptr.size() - 1;
+        const uint32_t nc = tc.ncl + tc.ncr;
+        const bool by_lead = (tc.flags & F4LA_FLAG_PIVOT_BY_LEAD) != 0;
+        std::vector<uint32_t> colmap(nc);
+        uint32_t ncl_eff = 0;
+        if (f4la_b200_resident_layout(cx, pc.res[c], colmap.data(), &ncl_eff) != F4LA_OK) return false;
+        std::vector<uint32_t> idx(tc.out_cols.size());
+        for (uint32_t i = 0; i < np; ++i)
+            for (uint64_t t = tc.out_row_ptr[i]; t < tc.out_row_ptr[i + 1]; ++t) {
+                if (by_lead && t == tc.out_row_ptr[i]) { idx[t] = 0xffffffffu; continue; }      /* the lead term, value 1 */
+                const uint32_t col = tc.out_cols[t];
+                if (col >= nc || colmap[col] < ncl_eff) return false;
+                idx[t] = colmap[col] - ncl_eff;
+            }
+        std::vector<uint64_t> row_dst(np);
+        if (tc.final_step) {
+            /* f4.c:612-622: element i of the reduced basis = row i; the rows, one after the other, are the residues */
+            pc.residue_off = words;
+            for (uint32_t i = 0; i < np; ++i) row_dst[i] = words + tc.out_row_ptr[i];
+            words += tc.out_row_ptr[np];
+        } else {
+            /* convert_sparse_matrix_rows_to_basis_elements(-1, ...): element bs_ld + k is result row np-1-k */
+            if (elem_off.size() < (size_t)tc.bs_ld + np) { elem_off.resize((size_t)tc.bs_ld + np); elem_len.resize((size_t)tc.bs_ld + np); }
+            for (uint32_t k = 0; k < np; ++k) {
+                const uint32_t i = np - 1 - k;
+                const uint64_t l = tc.out_row_ptr[i + 1] - tc.out_row_ptr[i];
+                elem_off[tc.bs_ld + k] = words; elem_len[tc.bs_ld + k] = l;
+                row_dst[i] = words;
+                words += l;
+            }
+        }
+        rc.expect_rows = np; rc.nslots = nslots;
+        rc.gather_src = (const uint64_t *)to_device(cx, pc, src);
+        rc.gather_dst = (const uint64_t *)to_device(cx, pc, dst);
+        rc.gather_len = (const uint32_t *)to_device(cx, pc, len);
+        rc.row_ptr = (const uint64_t *)to_device(cx, pc, tc.out_row_ptr);
+        rc.idx = (const uint32_t *)to_device(cx, pc, idx);
+        rc.row_dst = (const uint64_t *)to_device(cx, pc, row_dst);
+        if (!rc.gather_src || !rc.gather_dst || !rc.gather_len || !rc.row_ptr || !rc.idx || !rc.row_dst) return false;
+        pc.plan.push_back(rc);
+    }
+    if (tape->calls.empty() || !tape->calls.back().final_step) return false;
+    pc.arena_words = words;
+    pc.arena = (uint32_t *)f4la_b200_device_alloc(cx, words * 4 + 16);
+    pc.d_status = (uint32_t *)f4la_b200_device_alloc(cx, f4la_tape::kInflight * 4);
+    if (!pc.arena || !pc.d_status) return false;
+    pc.dev.push_back(pc.arena); pc.dev.push_back(pc.d_status);
+    pc.h_init = (uint32_t *)f4la_b200_pinned_alloc((size_t)f4la_tape::kInflight * (init_off[tape->ninit] + 1) * 4);
+    pc.h_status = (uint32_t *)f4la_b200_pinned_alloc(f4la_tape::kInflight * 4);
+    if (!pc.h_init || !pc.h_status) return false;
+    for (auto &rc : pc.plan) rc.arena = pc.arena;
+    return true;
+}
+
+f4la_tape::PerCtx *per_ctx(f4la_tape *tape, void *vctx)
+{
+    std::lock_guard<std::mutex> lk(tape->mu);
+    return &tape->resident[vctx];
+}
+
+int status_to_rc(uint32_t st)
+{
+    if (st & 4u) return F4LA_ERR_CUDA;
+    if (st & 1u) return F4LA_ERR_BADPRIME;
+    if (st & 2u) return F4LA_ERR_PATTERN;
+    return F4LA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int f4la_b200_tape_replay_collect(const f4la_tape *ctape, void *vctx, int *rcs, int max_rcs)
+{
+    f4la_tape *tape = const_cast<f4la_tape *>(ctape);
+    f4la_ctx *cx = (f4la_ctx *)vctx;
+    if (!tape || !cx) return -1;
+    f4la_tape::PerCtx *pc = per_ctx(tape, vctx);
+    if (pc->inflight && f4la_b200_device_copy(cx, nullptr, nullptr, 0, 0, 1) != F4LA_OK) {
+        /* the stream failed: every replay in flight is lost */
+        for (int k = 0; k < pc->inflight; ++k) pc->h_status[k] = 4u;
+    }
+    int n = 0, slot = 0;
+    size_t sync_k = 0;
+    for (int which : pc->order) {
+        const int rc = which ? pc->done_rc[sync_k++] : status_to_rc(pc->h_status[slot++]);
+        if (rcs && n < max_rcs) rcs[n] = rc;
+        ++n;
+    }
+    pc->order.clear(); pc->done_rc.clear(); pc->inflight = 0;
+    return n;
+}
+
+int f4la_b200_tape_replay_enqueue(const f4la_tape *ctape, void *vctx, uint32_t p, const uint32_t *init_cf,
+                                  const uint64_t *init_off, uint32_t *residues)
+{
+    f4la_tape *tape = const_cast<f4la_tape *>(ctape);
+    f4la_ctx *cx = (f4la_ctx *)vctx;
+    if (!tape || !cx || !init_cf || !init_off || !residues) return F4LA_ERR_ARG;
+    f4la_tape::PerCtx *pc = per_ctx(tape, vctx);
+    static const bool no_async = getenv("F4LA_B200_TAPE_ASYNC") && atoi(getenv("F4LA_B200_TAPE_ASYNC")) == 0;
+    if (pc->warmed && pc->async_state == 0 && !no_async)
+        pc->async_state = build_plan(tape, *pc, cx, init_off) ? 1 : -1;
+    const bool same_layout = pc->async_state == 1 &&
+        memcmp(pc->init_off.data(), init_off, ((size_t)tape->ninit + 1) * 8) == 0;
+    if (!same_layout || no_async) {
+        /* host-assembled replay (also the first one on a context: it uploads the structures and fills the layout
+         * caches the device-resident replay needs); everything enqueued before it must be done first */
+        if (pc->inflight == f4la_tape::kInflight) return F4LA_ERR_ARG;      /* collect first */
+        const int rc = f4la_b200_tape_replay(tape, vctx, p, init_cf, init_off, residues, nullptr);
+        pc->warmed = true;
+        pc->done_rc.push_back(rc);
+        pc->order.push_back(1);
+        return F4LA_OK;
+    }
+    if (pc->inflight == f4la_tape::kInflight) return F4LA_ERR_ARG;          /* collect first */
+    const int slot = pc->inflight;
+    const uint64_t init_words = init_off[tape->ninit];
+    uint32_t *h_init = pc->h_init + (size_t)slot * (init_words + 1);
+    memcpy(h_init, init_cf, init_words * 4);
+    uint32_t *d_status = pc->d_status + slot;
+    if (f4la_b200_device_copy(cx, pc->arena, h_init, init_words * 4, 1, 0) != F4LA_OK) return F4LA_ERR_CUDA;
+    if (f4la_b200_device_zero(cx, d_status, 4) != F4LA_OK) return F4LA_ERR_CUDA;
+    for (size_t c = 0; c < pc->plan.size(); ++c) {
+        f4la_replay_call rc = pc->plan[c];
+        rc.status = d_status;
+        if (f4la_b200_replay_call(cx, pc->res[c], p, &rc) != F4LA_OK) {
+            /* not expressible without host round trips (e.g. a block that needs compress-and-verify): from now on the
+             * host-assembled replay; this prime's partial work is abandoned */
+            pc->async_state = -1;
+            f4la_b200_device_copy(cx, nullptr, nullptr, 0, 0, 1);
+            const int r2 = f4la_b200_tape_replay(tape, vctx, p, init_cf, init_off, residues, nullptr);
+            pc->done_rc.push_back(r2);
+            pc->order.push_back(1);
+            return F4LA_OK;
+        }
+    }
+    if (f4la_b200_device_copy(cx, residues, pc->arena + pc->residue_off, tape->residue_words * 4, 0, 0) != F4LA_OK) return F4LA_ERR_CUDA;
+    if (f4la_b200_device_copy(cx, pc->h_status + slot, d_status, 4, 0, 0) != F4LA_OK) return F4LA_ERR_CUDA;
+    pc->inflight++;
+    pc->order.push_back(0);
+    return F4LA_OK;
+}
+
+} /* extern "C" */
+
+extern "C" {
 
 void f4la_b200_neogb_get_totals(f4la_neogb_totals *t, int reset)
 {

@@ -58,13 +58,14 @@ def gather_uint64(local: Sequence[int], dist=None, device="cpu") -> List[List[in
     return out
 
 
-def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarray" = None) -> "np.ndarray":
+def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarray" = None, root: int = None) -> "np.ndarray":
     """All-gather the modular results of a batch: ``local`` is uint32 [k, words], one row per prime of this
     rank (the coefficients of the modular Groebner basis / parametrisation, what msolve hands to CRT,
     msolve.c:2694-2712).  Returns uint32 [sum k, words] in BATCH order (prime i of the batch came from rank
     i % world, see :func:`shard`) on every rank.  One collective for the counts, one for the payload; the
     interleave into batch order happens on the device, so the host sees one copy in and one copy out (at
-    PCIe speed when ``local`` and ``out`` are page-locked, see :func:`pinned_rows`)."""
+    PCIe speed when ``local`` and ``out`` are page-locked, see :func:`pinned_rows`).  With ``root`` set only that
+    rank copies the gathered block to its host (msolve lifts by CRT in one place); the others return None."""
     local = np.ascontiguousarray(local, dtype=np.uint32)
     if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return local                                    # nothing to exchange
@@ -85,6 +86,8 @@ def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarr
         t[:k].copy_(torch.from_numpy(local.view(np.int32)), non_blocking=True)
     big = torch.empty((world, kmax, words), dtype=torch.int32, device=device)
     dist.all_gather(list(big.unbind(0)), t)
+    if root is not None and dist.get_rank() != root:
+        return None
     inter = big.transpose(0, 1).reshape(world * kmax, words)[:total]          # row r + j * world = row j of rank r
     if out is None:
         out = np.empty((total, words), dtype=np.uint32)

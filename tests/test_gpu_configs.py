@@ -240,6 +240,26 @@ def test_gpu_qq_tape_replay_matches_reference(name):
         [t.join() for t in ts]
         [b.close() for b in bes]
         assert not bad, bad
+        # device-resident replay: primes are only enqueued, one wait per batch; twice, so that both the warm-up replay of
+        # the context and the queued ones are covered
+        be2 = Backend(0)
+        for rep in range(2):
+            outs = np.zeros((len(inits), tape.residue_words), dtype=np.uint32)
+            for k in range(len(inits)):
+                tape.enqueue(be2, primes[1 + k], inits[k][0], inits[k][1], outs[k])
+            rcs = tape.collect(be2)
+            assert rcs == [0] * len(inits), (name, rcs)
+            assert np.array_equal(outs, ref_resid), name
+        # a prime whose structure differs must be reported, not silently replayed: with all coefficients zero every
+        # row vanishes, so the rank of the first call already differs from the recorded one
+        zeros = np.zeros_like(inits[0][0])
+        out = np.zeros(tape.residue_words, dtype=np.uint32)
+        tape.enqueue(be2, primes[1], zeros, inits[0][1], out)
+        tape.enqueue(be2, primes[2], inits[1][0], inits[1][1], outs[1])
+        rcs = tape.collect(be2)
+        assert len(rcs) == 2 and rcs[0] != 0 and rcs[1] == 0, (name, rcs)
+        assert np.array_equal(outs[1], ref_resid[1])
+        be2.close()
     finally:
         if tape is not None:
             tape.free()

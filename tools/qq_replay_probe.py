@@ -15,6 +15,8 @@ def main():
     ap.add_argument("--primes", type=int, default=64)
     ap.add_argument("--threads", default="1,4,16")
     ap.add_argument("--blocking", type=int, default=0)
+    ap.add_argument("--mode", default="replay", choices=["replay", "enqueue"],
+                    help="replay: host-assembled, one prime at a time; enqueue: device-resident, 16 primes per wait")
     ap.add_argument("--torch", type=int, default=0, help="initialise torch's CUDA context first (as bench.py does)")
     args = ap.parse_args()
     if args.torch:
@@ -38,12 +40,24 @@ def main():
     t0 = time.perf_counter()
     bases = [rh.qq_initial_basis(p, cap=1 << 16) for p in primes[2:]]
     print(f"initial bases: {(time.perf_counter() - t0) / len(bases) * 1e3:.2f} ms/prime, tape calls {tape.calls}", flush=True)
+    import torch
+    outs_t = torch.empty((len(bases), tape.residue_words), dtype=torch.int32).pin_memory()
+    outs = outs_t.numpy().view(np.uint32)
     for nthr in tl:
         backends = [Backend(0) for _ in range(nthr)]
         for b in backends:
             b.set_host_mode(1, bool(args.blocking))
         def work(k):
             ms = 0.0
+            if args.mode == "enqueue":
+                mine = list(range(k, len(bases), nthr))
+                for a0 in range(0, len(mine), Tape.MAX_INFLIGHT):
+                    part = mine[a0:a0 + Tape.MAX_INFLIGHT]
+                    for i in part:
+                        tape.enqueue(backends[k], primes[2 + i], bases[i][0], bases[i][1], outs[i])
+                    rcs = tape.collect(backends[k])
+                    assert rcs == [0] * len(part), rcs
+                return 0.0
             for i in range(k, len(bases), nthr):
                 rc, resid, m = tape.replay(backends[k], primes[2 + i], *bases[i])
                 assert rc == 0, rc
