@@ -607,8 +607,9 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
 
         all_cpus = ALL_CPUS
 
-        def replay_some(k, nthr, primes, res):
-            """host thread k of nthr: primes k, k + nthr, ... of the batch, residues written straight into their rows"""
+        def replay_some(k, nthr, primes, res, res_ptr=None):
+            """host thread k of nthr: primes k, k + nthr, ... of the batch, residues written straight into their rows
+            (res: host array; res_ptr: address of the [len(primes), words] uint32 batch buffer in HBM instead)"""
             # OMP_PROC_BIND pinned the main thread to the first core and new threads inherit that mask
             os.sched_setaffinity(0, all_cpus)
             failed, t0 = [], time.perf_counter()
@@ -619,27 +620,33 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
                 for i in part:
                     with init_lock:                  # the harness (reference code + GMP) is driven from one thread at a time
                         cf, off = rh.qq_initial_basis(primes[i], cap=1 << 16)
-                    tape.enqueue(backends[k], primes[i], cf, off, res[i])
+                    tape.enqueue(backends[k], primes[i], cf, off, res[i] if res_ptr is None else res_ptr + 4 * words * i)
                 rcs = tape.collect(backends[k])
                 assert len(rcs) == len(part)
                 failed += [i for i, rc in zip(part, rcs) if rc != 0]
             return failed, (time.perf_counter() - t0) * 1e3
 
-        def replay_batch(primes, mode, res=None):
+        def replay_batch(primes, mode, res=None, res_dev=None):
+            """res_dev: int32 torch tensor [len(primes), words] in HBM that receives the residues (they then never touch
+            the host before the gather); else a host array"""
             nthr, blocking = mode
             for b in backends[:nthr]:
                 b.set_host_mode(1, blocking)
                 b.set_grid_cap(64)                   # many contexts share the GPU: none may occupy every SM
-            if res is None:
+            if res is None and res_dev is None:
                 res = np.empty((len(primes), words), dtype=np.uint32)
+            ptr = None if res_dev is None else int(res_dev.data_ptr())
             with ThreadPoolExecutor(max_workers=nthr) as ex:
-                outs = list(ex.map(lambda k: replay_some(k, nthr, primes, res), range(nthr)))
+                outs = list(ex.map(lambda k: replay_some(k, nthr, primes, res, ptr), range(nthr)))
             redo = [i for failed, _ in outs for i in failed]
             if redo:                                 # bad prime / other support than recorded: the ordinary per-prime path
                 _, _, rr = rh.qq_apply([primes[i] for i in redo], threads=min(threads, len(redo)), ngpus=0, residue_words=words)
                 for i, row in zip(redo, rr):
-                    res[i] = row
-            return res, len(redo), sum(o[1] for o in outs)
+                    if res_dev is None:
+                        res[i] = row
+                    else:
+                        res_dev[i].copy_(torch.from_numpy(np.ascontiguousarray(row).view(np.int32)))
+            return (res if res_dev is None else res_dev), len(redo), sum(o[1] for o in outs)
 
         # the tape reproduces the recorded prime, and the drop-in path's result for other primes
         nmax = len(backends)
@@ -659,22 +666,27 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
         _, _, want = rh.qq_apply(warm_primes[:2], threads=min(2, threads), ngpus=0, residue_words=words)
         assert np.array_equal(chk[1:3], want), "tape replay differs from the drop-in application run"
         # page-locked once, outside the timed region (msolve keeps its modular images for the whole run)
-        resid_pinned = sharding.pinned_rows(len(mine), words)
-        gathered_pinned = sharding.pinned_rows(batch, words) if world > 1 and rank == 0 else None
+        init_bytes = int(rh.qq_initial_basis(p_tape, cap=1 << 16)[1][-1]) * 4            # what a replay sends to the device
+        resid_dev = torch.empty((len(mine), words), dtype=torch.int32, device=dev)       # this rank's residues, in HBM
+        gathered_pinned = sharding.pinned_rows(batch, words) if rank == 0 else None
+        # warm-up of the collective on a few rows (NCCL connects its channels on the first large call)
+        sharding.gather_residues(resid_dev[:min(4, len(mine))].contiguous(), dist if world > 1 else None, device=dev, root=0)
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         t0 = time.perf_counter()
-        resid, fallbacks, replay_ms = replay_batch(mine, mode, res=resid_pinned)
+        _, fallbacks, replay_ms = replay_batch(mine, mode, res_dev=resid_dev)
         t_replay = time.perf_counter() - t0
         # the residues of every rank meet on the device (one all-gather over NVLink); rank 0 -- where msolve lifts by CRT,
         # msolve.c:2694-2712 -- copies the batch to its host
-        gathered = sharding.gather_residues(resid, dist if world > 1 else None, device=dev, out=gathered_pinned, root=0)
+        gathered = sharding.gather_residues(resid_dev, dist if world > 1 else None, device=dev, out=gathered_pinned, root=0)
         torch.cuda.synchronize()
         el_local = time.perf_counter() - t0
         el = max_over_ranks(el_local)
         util = sampler.stop() if rank == 0 else None
+        resid = resid_dev.cpu().numpy().view(np.uint32)                  # (untimed) every rank's own rows, for the checks below
+        del resid_dev
         if rank == 0:
             assert gathered.shape == (batch, words)
             for j in range(len(mine)):
@@ -711,7 +723,7 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
                "replay_ms_per_prime": replay_ms / max(1, len(mine)),
                "rank0_replay_seconds": t_replay, "rank0_gather_seconds": el_local - t_replay,
                "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": words,
-               "gathered_bytes": int(batch * words * 4), "h2d_bytes": int(len(mine) * words * 4), "d2h_bytes": int(resid.nbytes),
+               "gathered_bytes": int(batch * words * 4), "h2d_bytes": int(len(mine) * init_bytes), "d2h_bytes": int(batch * words * 4) if rank == 0 else 0,
                "gpu0_util_pct_mean": util.get("gpu_util_pct_mean") if util else None,
                "collective": "nccl all_gather of the residues on the devices (uint32 [primes, words]), batch copied to the host "
                              "of rank 0" if world > 1 else "none (1 GPU)",

@@ -138,7 +138,8 @@ int f4la_b200_tape_replay(const f4la_tape *tape, void *ctx, uint32_t p, const ui
  * support) / F4LA_ERR_CUDA per prime (return value: number of results, -1 on bad arguments).  The first replay on a
  * context, and every replay of a tape that cannot be expressed this way (blocks that need compress-and-verify,
  * 8/16-bit coefficients), run through f4la_b200_tape_replay inside _enqueue; F4LA_B200_TAPE_ASYNC=0 forces that.
- * Page-locked `residues` (f4la_b200_pinned_alloc) keep the final copy asynchronous. */
+ * Page-locked `residues` (f4la_b200_pinned_alloc) keep the final copy asynchronous; `residues` may also point into
+ * DEVICE memory of the context's GPU (the batch then stays in HBM, e.g. for an NCCL gather). */
 int f4la_b200_tape_replay_enqueue(const f4la_tape *tape, void *ctx, uint32_t p, const uint32_t *init_cf,
                                   const uint64_t *init_off, uint32_t *residues);
 int f4la_b200_tape_replay_collect(const f4la_tape *tape, void *ctx, int *rcs, int max_rcs);

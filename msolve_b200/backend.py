@@ -295,14 +295,18 @@ class Tape:
 
     MAX_INFLIGHT = 16
 
-    def enqueue(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray, out: np.ndarray) -> None:
+    def enqueue(self, be: Backend, p: int, init_cf: np.ndarray, init_off: np.ndarray, out) -> None:
         """Device-resident replay: queues the prime on the backend's stream; `out` (C-contiguous uint32 row, page-locked
-        for a truly asynchronous copy) receives the residues and must stay alive until collect()."""
+        for a truly asynchronous copy, or the integer address of a row in device memory) receives the residues and
+        must stay alive until collect()."""
         assert init_cf.dtype == np.uint32 and init_cf.flags.c_contiguous
         assert init_off.dtype == np.uint64 and init_off.flags.c_contiguous
-        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= self.residue_words
-        rc = self.lib.f4la_b200_tape_replay_enqueue(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data,
-                                                    out.ctypes.data)
+        if isinstance(out, int):                  # address of residue_words uint32 in device (or page-locked) memory
+            dst = out
+        else:
+            assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= self.residue_words
+            dst = out.ctypes.data
+        rc = self.lib.f4la_b200_tape_replay_enqueue(self.handle, be.ctx, p, init_cf.ctypes.data, init_off.ctypes.data, dst)
         if rc != 0:
             raise F4LAError(f"f4la_b200_tape_replay_enqueue: error {rc}")
 

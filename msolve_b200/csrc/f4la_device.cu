@@ -1523,7 +1523,8 @@ int f4la_b200_device_copy(f4la_ctx *ctx, void *dst, const void *src, size_t byte
 {
     if (!ctx || (!dst && bytes) || (!src && bytes)) return F4LA_ERR_ARG;
     cudaSetDevice(ctx->device);
-    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    /* to_device == 0: the destination may be host OR device memory (unified addressing tells which) */
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDefault, ctx->stream));
     if (wait) OK(stream_sync(ctx));
     return F4LA_OK;
 }

@@ -66,12 +66,20 @@ def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarr
     interleave into batch order happens on the device, so the host sees one copy in and one copy out (at
     PCIe speed when ``local`` and ``out`` are page-locked, see :func:`pinned_rows`).  With ``root`` set only that
     rank copies the gathered block to its host (msolve lifts by CRT in one place); the others return None."""
-    local = np.ascontiguousarray(local, dtype=np.uint32)
+    on_device = not isinstance(local, np.ndarray)       # a torch int32 tensor already in HBM (same bits as uint32)
+    if not on_device:
+        local = np.ascontiguousarray(local, dtype=np.uint32)
     if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return local                                    # nothing to exchange
+        if not on_device:
+            return local                                # nothing to exchange
+        import torch
+        if out is None:
+            out = np.empty(tuple(local.shape), dtype=np.uint32)
+        torch.from_numpy(out.view(np.int32)).copy_(local)
+        return out
     import torch
     world = dist.get_world_size()
-    k, words = local.shape
+    k, words = tuple(local.shape)
     meta = torch.tensor([k, words], dtype=torch.int64, device=device)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta)
@@ -81,9 +89,12 @@ def gather_residues(local: "np.ndarray", dist=None, device="cpu", out: "np.ndarr
     assert all(ks[r] >= ks[r + 1] and ks[0] - ks[r + 1] <= 1 for r in range(world - 1)), "not a round-robin shard"
     kmax, total = max(max(ks), 1), sum(ks)
     words = max(words, 1)
-    t = torch.zeros((kmax, words), dtype=torch.int32, device=device)          # NCCL / gloo: no uint32, same bits
-    if k:
-        t[:k].copy_(torch.from_numpy(local.view(np.int32)), non_blocking=True)
+    if on_device and k == kmax and tuple(local.shape) == (kmax, words) and local.is_contiguous():
+        t = local                                                             # full shard already in HBM: no staging copy
+    else:
+        t = torch.zeros((kmax, words), dtype=torch.int32, device=device)      # NCCL / gloo: no uint32, same bits
+        if k:
+            t[:k].copy_(local if on_device else torch.from_numpy(local.view(np.int32)), non_blocking=True)
     big = torch.empty((world, kmax, words), dtype=torch.int32, device=device)
     dist.all_gather(list(big.unbind(0)), t)
     if root is not None and dist.get_rank() != root:
