@@ -305,13 +305,26 @@ def set_device_callback(fn) -> None:
 
 
 def primes_above(start: int, n: int):
-    """n successive primes > start (trial division; 31-bit)."""
-    out, c = [], start + 1
+    """n successive primes > start (segmented sieve; start + window < 2^32)."""
+    out = []
+    lo = start + 1
     while len(out) < n:
-        if c % 2 and all(c % d for d in range(3, int(c ** 0.5) + 1, 2)):
-            out.append(c)
-        c += 1
-    return out
+        span = max(4096, 32 * (n - len(out)))
+        hi = lo + span
+        lim = int(hi ** 0.5) + 1
+        small = np.ones(lim + 1, dtype=bool)
+        small[:2] = False
+        for q in range(2, int(lim ** 0.5) + 1):
+            if small[q]:
+                small[q * q::q] = False
+        mark = np.ones(span, dtype=bool)
+        for q in np.nonzero(small)[0]:
+            q = int(q)
+            first = max(q * q, (lo + q - 1) // q * q)
+            mark[first - lo::q] = False
+        out += [int(lo + i) for i in np.nonzero(mark)[0]]
+        lo = hi
+    return out[:n]
 
 
 def call_entry(m: FlatMatrix, which: int, fn=None, threads: int = 1):
