@@ -676,11 +676,44 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
         if rank == 0:
             sampler.start()
         t0 = time.perf_counter()
-        _, fallbacks, replay_ms = replay_batch(mine, mode, res_dev=resid_dev)
+        # The batch goes through in chunks: while the host threads replay chunk c+1, a background thread gathers chunk c --
+        # the residues of every rank meet on the device (one all-gather over NVLink per chunk) and rank 0, where msolve
+        # lifts by CRT (msolve.c:2694-2712), copies them to its host.  With equal shards the local rows [a, b) of every
+        # rank are the rows [a * world, b * world) of the batch.
+        L_loc = len(mine)
+        n_chunks = 4 if batch % world == 0 and L_loc >= 1024 else 1
+        bounds = [(c * L_loc // n_chunks, (c + 1) * L_loc // n_chunks) for c in range(n_chunks)]
+        gather_err = []
+
+        def gather_chunks(q):
+            try:
+                torch.cuda.set_device(local)
+                while True:
+                    item = q.get()
+                    if item is None:
+                        return
+                    a, b_ = item
+                    sharding.gather_residues(resid_dev[a:b_], dist if world > 1 else None, device=dev,
+                                             out=gathered_pinned[a * world:b_ * world] if rank == 0 else None, root=0)
+            except Exception as e:                   # noqa: BLE001 -- reported by the main thread
+                gather_err.append(e)
+
+        import queue
+        gq = queue.Queue()
+        gthread = threading.Thread(target=gather_chunks, args=(gq,))
+        gthread.start()
+        fallbacks, replay_ms = 0, 0.0
+        for a, b_ in bounds:
+            _, fb, ms = replay_batch(mine[a:b_], mode, res_dev=resid_dev[a:b_])
+            fallbacks += fb
+            replay_ms += ms
+            gq.put((a, b_))
         t_replay = time.perf_counter() - t0
-        # the residues of every rank meet on the device (one all-gather over NVLink); rank 0 -- where msolve lifts by CRT,
-        # msolve.c:2694-2712 -- copies the batch to its host
-        gathered = sharding.gather_residues(resid_dev, dist if world > 1 else None, device=dev, out=gathered_pinned, root=0)
+        gq.put(None)
+        gthread.join()
+        if gather_err:
+            raise gather_err[0]
+        gathered = gathered_pinned
         torch.cuda.synchronize()
         el_local = time.perf_counter() - t0
         el = max_over_ranks(el_local)
@@ -725,10 +758,11 @@ def run_qq(args, rank, world, local, dist, torch, cpu):
                "replay_ms_per_prime": replay_ms / max(1, len(mine)),
                "rank0_replay_seconds": t_replay, "rank0_gather_seconds": el_local - t_replay,
                "learn_seconds": learn["seconds"], "gb_elements": learn["nelts"], "residue_words_per_prime": words,
-               "gathered_bytes": int(batch * words * 4), "h2d_bytes": int(len(mine) * init_bytes), "d2h_bytes": int(batch * words * 4) if rank == 0 else 0,
+               "gather_chunks": n_chunks, "gathered_bytes": int(batch * words * 4), "h2d_bytes": int(len(mine) * init_bytes), "d2h_bytes": int(batch * words * 4) if rank == 0 else 0,
                "gpu0_util_pct_mean": util.get("gpu_util_pct_mean") if util else None,
-               "collective": "nccl all_gather of the residues on the devices (uint32 [primes, words]), batch copied to the host "
-                             "of rank 0" if world > 1 else "none (1 GPU)",
+               "collective": "nccl all_gather of the residues on the devices (uint32 [primes, words]) per chunk of the batch, "
+                             "overlapped with the replay of the next chunk; batch copied to the host of rank 0"
+                             if world > 1 else "none (1 GPU; device -> host copy per chunk, overlapped)",
                "drop_in": {"what": "the reference's per-prime F4 replay on the host, every LA call on the GPU through the plugin "
                                    "pointer (bound by the host's symbolic work, msolve.c:1815-1824)",
                            "value": n_drop / el2, "unit": "primes/s", "seconds": el2, "primes": n_drop,
