@@ -921,7 +921,7 @@ def main():
     ap.add_argument("--qq-dropin-primes", type=int, default=512,
                     help="primes of the batch the per-prime drop-in path is timed (and compared) on")
     ap.add_argument("--qq-primes", type=int, default=8192, help="size of the fixed prime batch of the QQ block")
-    ap.add_argument("--ref-budget-s", type=float, default=1200.0,
+    ap.add_argument("--ref-budget-s", type=float, default=300.0,
                     help="--impl reference: wall-clock budget; fewer steps are timed when K passes do not fit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
