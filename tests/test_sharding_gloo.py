@@ -15,6 +15,30 @@ from oracle import refharness as rh
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_primes_above_is_a_sieve_of_successive_primes():
+    def slow(start, n):
+        out, c = [], start + 1
+        while len(out) < n:
+            if c > 1 and all(c % d for d in range(2, int(c ** 0.5) + 1)):
+                out.append(c)
+            c += 1
+        return out
+    for start, n in ((1, 30), (100, 25), (65000, 12), (1 << 20, 40)):
+        assert rh.primes_above(start, n) == slow(start, n)
+    big = rh.primes_above(1 << 30, 3000)
+    assert big[:3] == [1073741827, 1073741831, 1073741833] and len(set(big)) == 3000 and big == sorted(big)
+
+
+def test_gather_residues_single_process_device_tensor():
+    import numpy as np
+    import torch
+    a = np.arange(12, dtype=np.uint32).reshape(3, 4) + (1 << 31)
+    assert sharding.gather_residues(a) is not None and np.array_equal(sharding.gather_residues(a), a)
+    t = torch.from_numpy(a.view(np.int32))
+    out = np.zeros((3, 4), dtype=np.uint32)
+    assert sharding.gather_residues(t, out=out, root=0) is out and np.array_equal(out, a)
+
+
 def test_shard_roundtrip():
     items = list(range(100, 117))
     for world in (1, 2, 3, 8):
@@ -45,6 +69,19 @@ allres = sharding.gather_residues(resid, dist)
 assert allres.shape == (len(primes) - 1, learn["nterms"])
 for i, p in enumerate(primes[1:]):
     assert int(allres[i].max()) < p
+# gather to the rank that lifts by CRT only; the batch may also come as an int32 tensor (the replay leaves it in HBM),
+# in chunks of equal local size, each chunk = a contiguous range of the batch
+import numpy as np, torch
+root_only = sharding.gather_residues(resid, dist, root=0)
+assert (root_only is None) == (rank != 0)
+if rank == 0:
+    assert np.array_equal(root_only, allres)
+k = min(len(mine), (len(primes) - 1) // world)            # equal shards: the head of every rank's rows
+t = torch.from_numpy(np.ascontiguousarray(resid[:k]).view(np.int32))
+out = np.zeros((k * world, learn["nterms"]), dtype=np.uint32) if rank == 0 else None
+got = sharding.gather_residues(t, dist, out=out, root=0)
+if rank == 0:
+    assert got is out and np.array_equal(out, allres[:k * world])
 if rank == 0:
     print("RESULT " + json.dumps(sharding.unshard(parts)))
     print("RESID " + json.dumps([rh.residue_digest(row) for row in allres]))
