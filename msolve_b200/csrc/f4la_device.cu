@@ -62,7 +62,8 @@ struct f4la_ctx {
     uint32_t      launches = 0;
     /* scratch (grow-only) */
     DevBuf col_cnt, col_ptr, cursor, ent, level, slots, slot_ptr, order, flags32;
-    DevBuf V, D, colflag, used, ispiv, gestate, pivcol, pivrow, pivinv, dense_out;
+    DevBuf V, D, colflag, gebytes, pivcol, pivrow, pivinv, dense_out;
+    DevBuf used, ispiv, gestate;                  /* views into gebytes (never allocated or freed themselves) */
     size_t        fused_smem_optin = 0;
     int           coop_ok = 0;          /* device supports cooperative launches (k_ge_fused) */
     DevBuf sched, items, flowflags, tcA, tcB, scB, scFlagA, scFlagB, scList, scCnt, scP;
@@ -331,16 +332,19 @@ int gauss_jordan(f4la_ctx *ctx, uint32_t *Dm, uint64_t ld, uint32_t nrl, uint32_
     cudaStream_t s = ctx->stream;
     const uint32_t maxrank = nrl < ncr ? nrl : ncr;
     OK(ensure(ctx, ctx->colflag, (size_t)ncr + 16));
-    OK(ensure(ctx, ctx->ispiv, (size_t)ncr + 16));
-    OK(ensure(ctx, ctx->used, (size_t)ld + 16));
-    OK(ensure(ctx, ctx->gestate, 256 + 64));                        /* GEState | grid barrier words of k_ge_fused */
+    /* used bytes | pivot-column bytes | GEState + grid barrier words of k_ge_fused: one buffer, ONE memset
+     * (ctx->used / ispiv / gestate are views into it) */
+    const size_t off_ispiv = ((size_t)ld + 16 + 255) & ~(size_t)255;
+    const size_t off_state = off_ispiv + (((size_t)ncr + 16 + 255) & ~(size_t)255);
+    OK(ensure(ctx, ctx->gebytes, off_state + 256 + 64));
+    ctx->used.p = ctx->gebytes.p;
+    ctx->ispiv.p = static_cast<char *>(ctx->gebytes.p) + off_ispiv;
+    ctx->gestate.p = static_cast<char *>(ctx->gebytes.p) + off_state;
     OK(ensure(ctx, ctx->pivcol, ((size_t)maxrank + 1) * 4));
     OK(ensure(ctx, ctx->pivrow, ((size_t)maxrank + 1) * 4));
     OK(ensure(ctx, ctx->pivinv, ((size_t)maxrank + 1) * 4));
-    CU(cudaMemsetAsync(ctx->ispiv.p, 0, (size_t)ncr + 16, s));
-    CU(cudaMemsetAsync(ctx->used.p, 0, (size_t)ld + 16, s));
     static_assert(sizeof(GEState) <= 256, "GEState");
-    CU(cudaMemsetAsync(ctx->gestate.p, 0, 256 + 64, s));
+    CU(cudaMemsetAsync(ctx->gebytes.p, 0, off_state + 256 + 64, s));
     GEState *h_state = (GEState *)ctx->h_small.p;
     const size_t smem_cap = (size_t)216 * 1024;
     /* pivots per batch such that the batch's pivot columns (+ one column, + the used bytes) fit in
@@ -809,7 +813,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
     OK(ensure(ctx, ctx->V, (size_t)G * nc * Rc * 4));
     OK(ensure(ctx, ctx->D, (size_t)ncr * ld * 4));
     OK(ensure(ctx, ctx->flowflags, (size_t)G * nc * 4));
-    CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));
+    if (!ncl) CU(cudaMemsetAsync(ctx->flowflags.p, 0, (size_t)G * nc * 4, s));   /* else: written by k_flow_reset_flags */
 
     /* The columns without pivot have no dependents: V[ncl + j] = X + M * Bneg is a dense-times-sparse product.
      * When it is large it runs on the tensor cores over the non-zero 64 x 64 tiles of B (f4la_tc.cuh), and the
@@ -910,7 +914,7 @@ int run_pipeline(f4la_ctx *ctx, const f4la_resident *m, f4la_flat_result *out, f
         const uint32_t g = (c0 + G <= nchunks) ? G : nchunks - c0;
         CU(cudaMemsetAsync(ctx->V.p, 0, (size_t)g * nc * Rc * 4, s));
         if (ncl) {
-            k_flow_reset_flags<<<(ncl + 255) / 256, 256, 0, s>>>(d_col_ptr, ncl, nc, g,
+            k_flow_reset_flags<<<(nc + 255) / 256, 256, 0, s>>>(d_col_ptr, ncl, nc, g,
                                                                as<uint32_t>(ctx->flowflags), d_err + 4);
             note_launch(ctx, 1, __LINE__);
         }
@@ -1418,8 +1422,8 @@ void f4la_b200_destroy(f4la_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->col_cnt, &ctx->col_ptr, &ctx->cursor, &ctx->ent, &ctx->level, &ctx->slots, &ctx->slot_ptr,
-                      &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->used, &ctx->ispiv,
-                      &ctx->gestate, &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
+                      &ctx->order, &ctx->flags32, &ctx->V, &ctx->D, &ctx->colflag, &ctx->gebytes,
+                      &ctx->pivcol, &ctx->pivrow, &ctx->pivinv, &ctx->dense_out,
                       &ctx->sched, &ctx->items, &ctx->flowflags, &ctx->tcA, &ctx->tcB, &ctx->scB, &ctx->scFlagA, &ctx->scFlagB, &ctx->scList, &ctx->scCnt, &ctx->scP, &ctx->in_row_ptr, &ctx->in_cols,
                       &ctx->in_row_cf, &ctx->in_cf_ptr, &ctx->in_cf, &ctx->is_piv, &ctx->pividx, &ctx->colmap,
                       &ctx->invmap, &ctx->leads, &ctx->rba, &ctx->D2, &ctx->combo};
@@ -1498,7 +1502,9 @@ int f4la_b200_reduce_resident(f4la_ctx *ctx, f4la_resident *m, f4la_flat_result 
     cudaSetDevice(ctx->device);
     if (stats) memset(stats, 0, sizeof(*stats));
     const double t0 = now_ms();
+    memset(out, 0, sizeof(*out));
     int rc = run_pipeline(ctx, m, out, stats);
+    if (rc != F4LA_OK) f4la_b200_free_result(out);      /* nothing half-built is handed back */
     if (stats) stats->ms_total = now_ms() - t0;
     return rc;
 }
@@ -1630,7 +1636,9 @@ int f4la_b200_reduce(f4la_ctx *ctx, const f4la_flat_matrix *in, f4la_flat_result
     /* the pipeline runs on the same stream: no synchronisation needed before it;
      * the H2D time is measured with events */
     cudaEventRecord(ctx->ev[5], ctx->stream);
+    memset(out, 0, sizeof(*out));
     if (rc == F4LA_OK) rc = run_pipeline(ctx, &r, out, stats);
+    if (rc != F4LA_OK) f4la_b200_free_result(out);      /* nothing half-built is handed back */
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_pending) {                  /* the pipeline returned before it needed the lower rows */
         cudaStreamSynchronize(ctx->copy_stream);

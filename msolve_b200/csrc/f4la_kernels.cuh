@@ -797,16 +797,18 @@ k_pull_flow(const FlowArgs A)
     }
 }
 
-/* ready words of the columns without sources, for the g chunk slots of a group: "always
- * ready, zero"; k_scatter_lower upgrades the touched ones to "non-zero".  The words of the
- * other columns are left alone (their epoch is stale until the column is solved). */
+/* ready words of a launch group (g chunk slots): columns without sources are "always ready, zero"
+ * (k_scatter_lower upgrades the touched ones to "non-zero"), every other word is reset to "not ready";
+ * also zeroes the work counter of the dataflow kernel (one launch instead of two memsets and a kernel). */
 __global__ void k_flow_reset_flags(const uint32_t *__restrict__ col_ptr, uint32_t ncl, uint32_t nc, uint32_t g,
                                    uint32_t *__restrict__ flags, uint32_t *__restrict__ counter)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) *counter = 0;                    /* work counter of the dataflow kernel that follows */
-    if (j >= ncl || col_ptr[j + 1] != col_ptr[j]) return;
-    for (uint32_t k = 0; k < g; ++k) flags[(size_t)k * nc + j] = kFlagAlwaysZ;
+    if (j >= nc) return;
+    /* every ready word of the launch group: "not ready", except pivot columns without sources (never solved: zero) */
+    const uint32_t v = (j < ncl && col_ptr[j + 1] == col_ptr[j]) ? kFlagAlwaysZ : 0u;
+    for (uint32_t k = 0; k < g; ++k) flags[(size_t)k * nc + j] = v;
 }
 
 /* schedule = pivot columns with sources in level order, then the non-pivot columns */
