@@ -30,9 +30,12 @@ capturing what it hands to the backend.  Only this library's calls are timed.
 
 With --gpus N > 1 (torchrun, one rank per GPU) the headline becomes the metric
 north_star names for several GPUs: QQ primes/s of the multi-modular tracer
-application phase, a FIXED batch of primes sharded over the ranks, all host
-cores in use at every N, residues gathered with NCCL; the per-GPU replicas of
-the single-prime workload are reported under `replicas`.
+application phase (structure-cached, device-resident replay of a recorded
+application run, include/f4la_b200_neogb.h), a FIXED batch of primes sharded
+over the ranks, all host cores in use at every N, residues gathered with NCCL
+to the rank that would lift them by CRT; the per-GPU replicas of the
+single-prime workload are reported under `replicas`.  At N = 1 the same block
+is reported under `qq` next to the single-prime headline.
 """
 from __future__ import annotations
 
