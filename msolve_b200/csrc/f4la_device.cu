@@ -184,7 +184,9 @@ int ensure(f4la_ctx *ctx, DevBuf &b, size_t bytes)
     if (bytes <= b.cap) return F4LA_OK;
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr; b.cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    /* the matrices of an F4 run grow from call to call: doubling keeps the number of (synchronising) re-allocations of
+     * a cold process small; beyond 2 GB only a quarter of head-room */
+    size_t want = (bytes < ((size_t)2 << 30) ? 2 * bytes : bytes + bytes / 4) + 256;
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
     return F4LA_OK;
@@ -195,7 +197,7 @@ int ensure_host(f4la_ctx *ctx, HostBuf &b, size_t bytes)
     if (bytes <= b.cap) return F4LA_OK;
     if (b.p) CU(cudaFreeHost(b.p));
     b.p = nullptr; b.cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    size_t want = (bytes < ((size_t)256 << 20) ? 2 * bytes : bytes + bytes / 4) + 256;     /* page-locking is slow: re-pin rarely */
     CU(cudaMallocHost(&b.p, want));
     b.cap = want;
     return F4LA_OK;
